@@ -1,0 +1,98 @@
+"""In-tree build of the native libraries (no JIT cache: the .so files travel with the repo).
+
+  avir_b200/libavirb200.so        CUDA kernels + C ABI (include/avirb200.h), sm_100a only
+  avir_b200/libavirb200_host.so   the header-only C++ front-ends instantiated behind a C API
+                                  (what the Python tests / bench drive)
+
+The oracles (test infrastructure) are built by oracle/Makefile, see build_oracles().
+"""
+import os
+import shutil
+import subprocess
+import sys
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(PKG)
+CSRC = os.path.join(PKG, "csrc")
+INC = os.path.join(ROOT, "include")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "-fmad=false",  # products and sums stay separate IEEE operations (bit-exact contract)
+    "-Xcompiler", "-fPIC", "-I" + INC, "-I" + CSRC,
+]
+
+
+def _nvcc():
+    for cand in (shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found")
+
+
+def _newer(target, sources):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(s) > t for s in sources)
+
+
+def _run(cmd):
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout)
+        raise RuntimeError("build failed: " + " ".join(cmd))
+    return r.stdout
+
+
+def _sources(dirs, exts):
+    out = []
+    for d in dirs:
+        for f in sorted(os.listdir(d)):
+            if f.endswith(exts):
+                out.append(os.path.join(d, f))
+    return out
+
+
+def build_cuda(force=False, verbose=False):
+    target = os.path.join(PKG, "libavirb200.so")
+    cus = [os.path.join(CSRC, "engine.cu"), os.path.join(CSRC, "lancir.cu")]
+    deps = _sources([CSRC, INC], (".cu", ".cuh", ".h", ".hpp"))
+    if not force and not _newer(target, deps):
+        return target
+    objs = []
+    for cu in cus:
+        obj = os.path.join(PKG, os.path.basename(cu)[:-3] + ".o")
+        out = _run([_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", cu, "-o", obj])
+        if verbose:
+            print(out)
+        objs.append(obj)
+    _run([_nvcc(), "-shared", "-o", target] + objs + ["-lcudart_static", "-ldl", "-lpthread", "-lrt"])
+    return target
+
+
+def build_host(force=False):
+    target = os.path.join(PKG, "libavirb200_host.so")
+    src = os.path.join(CSRC, "host_capi.cpp")
+    deps = [src] + _sources([INC], (".h", ".hpp")) + [os.path.join(PKG, "libavirb200.so")]
+    if not force and not _newer(target, deps):
+        return target
+    _run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-I" + INC,
+          "-o", target, src, "-L" + PKG, "-lavirb200", "-Wl,-rpath,$ORIGIN", "-pthread"])
+    return target
+
+
+def build_oracles():
+    """C port always; the upstream-compiled oracle only where /root/reference exists."""
+    _run(["make", "-C", os.path.join(ROOT, "oracle"), "all"])
+
+
+def build_all(force=False, verbose=False):
+    build_cuda(force, verbose)
+    build_host(force)
+    build_oracles()
+
+
+if __name__ == "__main__":
+    build_all(force="--force" in sys.argv, verbose="-v" in sys.argv)
+    print("built")

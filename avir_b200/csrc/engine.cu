@@ -1,0 +1,680 @@
+// engine.cu -- libavirb200.so: C ABI (include/avirb200.h) over the sm_100a kernels.
+//
+// Host responsibilities here are strictly device plumbing: copy the planner's tables into
+// one device arena, pick tile sizes that fit shared memory, launch the row pass and the
+// column pass, move host images for the convenience entry point, and exchange halo rows
+// between row-sharded GPUs.  All arithmetic lives in the kernels.
+//
+// There is no CPU execution path in this library: without a usable CUDA device every
+// entry point fails with AVIRB200_ERR_NO_DEVICE / AVIRB200_ERR_CUDA.
+
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <charconv>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "avirb200.h"
+#include "device_plan.h"
+#include "fast_pass.cuh"
+#include "generic_pass.cuh"
+
+using namespace avb;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                       \
+    do {                                                                                     \
+        cudaError_t e_ = (expr);                                                             \
+        if (e_ != cudaSuccess)                                                               \
+            return fail(e_ == cudaErrorMemoryAllocation ? AVIRB200_ERR_ALLOC                 \
+                                                        : (e_ == cudaErrorNoDevice ||        \
+                                                           e_ == cudaErrorInsufficientDriver \
+                                                               ? AVIRB200_ERR_NO_DEVICE      \
+                                                               : AVIRB200_ERR_CUDA),         \
+                        std::string(#expr) + ": " + cudaGetErrorString(e_));                 \
+    } while (0)
+
+size_t dtype_size(int t) { return t == AVIRB200_U8 ? 1 : (t == AVIRB200_U16 ? 2 : 4); }
+
+// The u8 sRGB->linear table: upstream ships 256 float literals (avir.h:234-286) that equal
+// the double-precision linearisation formula printed with 7 significant digits.  Regenerated
+// here (locale-independent) instead of being copied; tests compare it with the oracle.
+void make_srgb_lut(float* lut) {
+    for (int i = 0; i < 256; ++i) {
+        const double sv = i / 255.0;
+        double r;
+        if (sv <= 0.04045) {
+            r = sv / 12.92;
+        } else {
+            const double x = (sv + 0.055) / 1.055;
+            const double x2 = x * x, x3 = x2 * x, x4 = x2 * x2;
+            r = 0.0985766365536824 + 0.839474952656502 * x2 + 0.363287814061725 * x3 -
+                0.0125559718896615 / (0.12758338921578 + 0.290283465468235 * x) -
+                0.231757513261358 * x - 0.0395365717969074 * x4;
+        }
+        char buf[64];
+        auto res = std::to_chars(buf, buf + sizeof buf, r, std::chars_format::general, 7);
+        float f = 0.0f;
+        std::from_chars(buf, res.ptr, f);
+        lut[i] = f;
+    }
+}
+
+struct PassConfig {
+    int lines_per_block = 0;
+    int tile_out = 0;
+    int span = 0;
+    int pitch = 0;
+    size_t smem = 0;
+};
+
+struct HostAxis {
+    avirb200_axis_desc desc;              // pointers are HOST copies (below)
+    std::vector<std::vector<float> > taps, frac, pdc, sdc;
+    std::vector<std::vector<int32_t> > src_pos, phase;
+    DevAxis dev;                          // device pointers
+    DevAxis hostdev;                      // same geometry, host src_pos pointers (range math)
+};
+
+} // namespace
+
+struct avirb200_plan {
+    avirb200_plan_desc desc;
+    HostAxis h, v;
+    void* arena = nullptr;
+    float* d_lut = nullptr;
+    int device = 0;
+    PassConfig cfg_h, cfg_v;
+    FastPlan fast;
+    // resize_host cache
+    std::mutex mx;
+    void* d_src = nullptr;
+    void* d_dst = nullptr;
+    void* d_ws = nullptr;
+    size_t d_src_bytes = 0, d_dst_bytes = 0, d_ws_bytes = 0;
+    cudaStream_t stream = nullptr;
+    mutable int last_launches = 0;
+};
+
+namespace {
+
+int copy_axis_host(HostAxis& ha, const avirb200_axis_desc& ad) {
+    if (ad.nsteps < 1 || ad.nsteps > AVIRB200_MAX_STEPS)
+        return fail(AVIRB200_ERR_BAD_ARG, "axis: nsteps out of range");
+    ha.desc = ad;
+    const int n = ad.nsteps;
+    ha.taps.resize(n); ha.frac.resize(n); ha.pdc.resize(n); ha.sdc.resize(n);
+    ha.src_pos.resize(n); ha.phase.resize(n);
+    int prev_len = ad.src_len;
+    int prev_lo = 0, prev_hi = ad.src_len;
+    for (int i = 0; i < n; ++i) {
+        const avirb200_step_desc& s = ad.steps[i];
+        if (s.in_len != prev_len && !(s.kind == AVIRB200_STEP_RESIZE && s.upsampled))
+            return fail(AVIRB200_ERR_BAD_ARG, "axis: step in_len does not chain");
+        if (s.kind == AVIRB200_STEP_RESIZE && s.upsampled && s.in_len != prev_len)
+            return fail(AVIRB200_ERR_BAD_ARG, "axis: upsampled resize in_len does not chain");
+        size_t nt = 0;
+        if (s.kind == AVIRB200_STEP_RESIZE) {
+            if (s.ntaps < 2 || (s.ntaps & 1) || s.nphases < 1 || s.order < 0 || s.order > 1)
+                return fail(AVIRB200_ERR_BAD_ARG, "resize step: bad bank geometry");
+            nt = (size_t)s.nphases * s.ntaps * (s.order + 1);
+            ha.src_pos[i].assign(s.src_pos, s.src_pos + s.out_len);
+            ha.phase[i].assign(s.phase, s.phase + s.out_len);
+            ha.frac[i].assign(s.frac, s.frac + s.out_len);
+            for (int j = 0; j < s.out_len; ++j) {
+                if (s.phase[j] < 0 || s.phase[j] >= s.nphases)
+                    return fail(AVIRB200_ERR_BAD_ARG, "resize step: phase index out of range");
+                if (j > 0 && s.src_pos[j] < s.src_pos[j - 1])
+                    return fail(AVIRB200_ERR_BAD_ARG, "resize step: positions not monotonic");
+            }
+        } else {
+            if (s.ntaps < 1) return fail(AVIRB200_ERR_BAD_ARG, "filter step: no taps");
+            if (s.kind == AVIRB200_STEP_FIR && s.resample < 1)
+                return fail(AVIRB200_ERR_BAD_ARG, "FIR step: resample < 1");
+            nt = (size_t)s.ntaps;
+            if (s.kind == AVIRB200_STEP_UPSAMPLE) {
+                if (s.resample != 2)
+                    return fail(AVIRB200_ERR_UNSUPPORTED, "upsample factor other than 2");
+                ha.pdc[i].assign(s.prefix_dc, s.prefix_dc + s.n_prefix_dc);
+                ha.sdc[i].assign(s.suffix_dc, s.suffix_dc + s.n_suffix_dc);
+            }
+        }
+        ha.taps[i].assign(s.taps, s.taps + nt);
+        (void)prev_lo; (void)prev_hi;
+        prev_len = s.out_len;
+    }
+    if (prev_len != ad.dst_len) return fail(AVIRB200_ERR_BAD_ARG, "axis: chain does not end at dst_len");
+    return 0;
+}
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+size_t axis_arena_bytes(const HostAxis& ha) {
+    size_t b = 0;
+    for (int i = 0; i < ha.desc.nsteps; ++i) {
+        b += align_up(ha.taps[i].size() * 4, 256) + align_up(ha.frac[i].size() * 4, 256) +
+             align_up(ha.src_pos[i].size() * 4, 256) + align_up(ha.phase[i].size() * 4, 256) +
+             align_up(ha.pdc[i].size() * 4, 256) + align_up(ha.sdc[i].size() * 4, 256);
+    }
+    return b;
+}
+
+template <class T>
+const T* stage(std::vector<char>& img, size_t& off, char* dbase, const std::vector<T>& v) {
+    if (v.empty()) return nullptr;
+    const size_t bytes = v.size() * sizeof(T);
+    std::memcpy(img.data() + off, v.data(), bytes);
+    const T* d = reinterpret_cast<const T*>(dbase + off);
+    off += align_up(bytes, 256);
+    return d;
+}
+
+void build_dev_axis(HostAxis& ha, std::vector<char>& img, size_t& off, char* dbase) {
+    DevAxis& d = ha.dev;
+    d.src_len = ha.desc.src_len;
+    d.dst_len = ha.desc.dst_len;
+    d.nsteps = ha.desc.nsteps;
+    int lo = 0, hi = ha.desc.src_len;
+    for (int i = 0; i < d.nsteps; ++i) {
+        const avirb200_step_desc& s = ha.desc.steps[i];
+        DevStep& ds = d.steps[i];
+        ds.kind = s.kind; ds.resample = s.resample; ds.latency = s.latency; ds.edge = s.edge;
+        ds.in_len = s.in_len; ds.out_len = s.out_len; ds.ntaps = s.ntaps; ds.order = s.order;
+        ds.upsampled = s.upsampled; ds.skip_odd = s.skip_odd; ds.zero_start = s.zero_start;
+        ds.nphases = s.nphases;
+        ds.out_prefix = s.out_prefix; ds.out_suffix = s.out_suffix;
+        ds.in_prefix = s.in_prefix; ds.in_suffix = s.in_suffix;
+        ds.n_prefix_dc = s.n_prefix_dc; ds.n_suffix_dc = s.n_suffix_dc;
+        ds.in_lo = lo; ds.in_hi = hi;
+        ds.taps = stage(img, off, dbase, ha.taps[i]);
+        ds.src_pos = stage(img, off, dbase, ha.src_pos[i]);
+        ds.phase = stage(img, off, dbase, ha.phase[i]);
+        ds.frac = stage(img, off, dbase, ha.frac[i]);
+        ds.prefix_dc = stage(img, off, dbase, ha.pdc[i]);
+        ds.suffix_dc = stage(img, off, dbase, ha.sdc[i]);
+        const Range od = step_output_domain(ds);
+        lo = od.a;
+        hi = od.b + 1;
+    }
+    ha.hostdev = d;
+    for (int i = 0; i < d.nsteps; ++i) {
+        ha.hostdev.steps[i].src_pos = ha.src_pos[i].empty() ? nullptr : ha.src_pos[i].data();
+        ha.hostdev.steps[i].taps = ha.taps[i].data();
+        ha.hostdev.steps[i].phase = ha.phase[i].empty() ? nullptr : ha.phase[i].data();
+        ha.hostdev.steps[i].frac = ha.frac[i].empty() ? nullptr : ha.frac[i].data();
+    }
+}
+
+// Source range a final-output range needs, through the whole chain (host side).
+Range chain_source_range(const DevAxis& hd, Range out, int* max_span) {
+    Range r = out;
+    int span = r.b - r.a + 1;
+    for (int i = hd.nsteps - 1; i >= 0; --i) {
+        r = step_input_range(hd.steps[i], r, hd.steps[i].src_pos);
+        span = imax(span, r.b - r.a + 1);
+    }
+    if (max_span) *max_span = span;
+    return r;
+}
+
+const size_t kGenericSmemBudget = 100 * 1024;
+
+PassConfig choose_generic_config(const DevAxis& hd, int channels, int out0, int out1) {
+    PassConfig c;
+    c.lines_per_block = imax(1, 64 / channels);
+    c.pitch = (c.lines_per_block * channels) | 1;
+    static const int cand[] = {1024, 768, 512, 384, 256, 192, 128, 96, 64, 48, 32, 24, 16, 12, 8, 4, 2, 1};
+    for (int t : cand) {
+        int worst = 0;
+        for (int j0 = out0; j0 < out1; j0 += t) {
+            int sp = 0;
+            Range o{j0, imin(j0 + t, out1) - 1};
+            chain_source_range(hd, o, &sp);
+            worst = imax(worst, sp);
+        }
+        const size_t smem = 2ull * worst * c.pitch * sizeof(float);
+        if (smem <= kGenericSmemBudget || t == 1) {
+            c.tile_out = t;
+            c.span = worst;
+            c.smem = smem;
+            break;
+        }
+    }
+    return c;
+}
+
+void fill_common(PassParams& p, const avirb200_plan* pl) {
+    const avirb200_plan_desc& d = pl->desc;
+    p.sum_mode = d.sum_mode;
+    p.channels = d.channels;
+    p.gamma_in = (d.use_gamma & 1) ? 1 : 0;
+    p.gamma_out = (d.use_gamma & 2) ? 1 : 0;
+    p.alpha_index = d.alpha_index;
+    p.in_gamma_mult = d.in_gamma_mult;
+    p.out_gamma_mult = d.out_gamma_mult;
+    p.srgb_lut = pl->d_lut;
+    p.round_mode = d.round_mode;
+    p.tr_mul = d.tr_mul;
+    p.tr_mul_inv = d.tr_mul_inv;
+    p.pk_out = d.pk_out;
+}
+
+int launch_generic(const PassParams& p, const PassConfig& c, cudaStream_t st) {
+    dim3 grid((p.out1 - p.out0 + c.tile_out - 1) / c.tile_out,
+              (p.n_lines + c.lines_per_block - 1) / c.lines_per_block);
+    if (grid.x == 0 || grid.y == 0) return 0;
+    if (grid.y > 65535) return fail(AVIRB200_ERR_UNSUPPORTED, "image too large for generic grid");
+    if (p.sum_mode == AVIRB200_SUM_DIL8) {
+        CUDA_TRY(cudaFuncSetAttribute(generic_pass_kernel<AVIRB200_SUM_DIL8>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));
+        generic_pass_kernel<AVIRB200_SUM_DIL8><<<grid, 256, c.smem, st>>>(p);
+    } else {
+        CUDA_TRY(cudaFuncSetAttribute(generic_pass_kernel<AVIRB200_SUM_INL>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));
+        generic_pass_kernel<AVIRB200_SUM_INL><<<grid, 256, c.smem, st>>>(p);
+    }
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+// Row pass over `rows` source rows (band starting at d_src) into the intermediate band
+// starting at d_mid; column pass producing dst rows [out0, out1) from an intermediate
+// buffer whose row 0 is global row mid_row_base.
+int run_row_pass(const avirb200_plan* pl, const void* d_src, size_t src_pitch, float* d_mid,
+                 int rows, cudaStream_t st, int* launches) {
+    if (rows <= 0) return 0;
+    const avirb200_plan_desc& d = pl->desc;
+    if (env_fast_enabled() && pl->fast.h_ok) {
+        int r = fast_row_pass(pl->fast, pl->h.dev, d, d_src, src_pitch, d_mid, rows, pl->d_lut, st);
+        if (r != 0) return fail(AVIRB200_ERR_CUDA, "fast row pass launch failed");
+        ++*launches;
+        return 0;
+    }
+    PassParams p;
+    std::memset(&p, 0, sizeof p);
+    fill_common(p, pl);
+    p.ax = pl->h.dev;
+    p.is_v = 0;
+    p.n_lines = rows;
+    p.lines_per_block = pl->cfg_h.lines_per_block;
+    p.tile_out = pl->cfg_h.tile_out;
+    p.out0 = 0;
+    p.out1 = d.dst_w;
+    p.span = pl->cfg_h.span;
+    p.pitch = pl->cfg_h.pitch;
+    p.src = d_src;
+    p.src_pitch = (long long)src_pitch;
+    p.src_type = d.in_type;
+    p.dst = d_mid;
+    p.dst_pitch = (long long)d.dst_w * d.channels;
+    p.dst_type = AVIRB200_F32;
+    ++*launches;
+    return launch_generic(p, pl->cfg_h, st);
+}
+
+int run_col_pass(const avirb200_plan* pl, const float* d_mid, int mid_row_base, void* d_dst,
+                 size_t dst_pitch, int out0, int out1, cudaStream_t st, int* launches) {
+    if (out1 <= out0) return 0;
+    const avirb200_plan_desc& d = pl->desc;
+    if (env_fast_enabled() && pl->fast.v_ok) {
+        int r = fast_col_pass(pl->fast, pl->v.dev, d, d_mid, mid_row_base, d_dst, dst_pitch, out0,
+                              out1, st);
+        if (r != 0) return fail(AVIRB200_ERR_CUDA, "fast column pass launch failed");
+        ++*launches;
+        return 0;
+    }
+    PassParams p;
+    std::memset(&p, 0, sizeof p);
+    fill_common(p, pl);
+    p.ax = pl->v.dev;
+    p.is_v = 1;
+    p.n_lines = d.dst_w;
+    PassConfig c = pl->cfg_v;
+    if (out0 != 0 || out1 != d.dst_h) c = choose_generic_config(pl->v.hostdev, d.channels, out0, out1);
+    p.lines_per_block = c.lines_per_block;
+    p.tile_out = c.tile_out;
+    p.out0 = out0;
+    p.out1 = out1;
+    p.span = c.span;
+    p.pitch = c.pitch;
+    p.src = d_mid;
+    p.src_pitch = (long long)d.dst_w * d.channels;
+    p.src_type = AVIRB200_F32;
+    p.src_row_base = mid_row_base;
+    p.dst = d_dst;
+    p.dst_pitch = (long long)dst_pitch;
+    p.dst_type = d.out_type;
+    p.dst_row_base = out0;
+    ++*launches;
+    return launch_generic(p, c, st);
+}
+
+// ---- NCCL through dlopen (no link-time dependency) -------------------------------------------
+
+struct Id128 { char b[128]; }; // ncclUniqueId (passed by value)
+
+struct Nccl {
+    void* lib = nullptr;
+    int (*GetUniqueId)(void*) = nullptr;
+    int (*CommInitRank)(void**, int, Id128, int) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    int (*Send)(const void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*Recv)(void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+
+Nccl* nccl() {
+    static Nccl n;
+    static std::once_flag once;
+    std::call_once(once, []() {
+        const char* names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char* nm : names) {
+            n.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+            if (n.lib) break;
+        }
+        if (!n.lib) return;
+        n.GetUniqueId = (int (*)(void*))dlsym(n.lib, "ncclGetUniqueId");
+        n.CommInitRank = (int (*)(void**, int, Id128, int))dlsym(n.lib, "ncclCommInitRank");
+        n.CommDestroy = (int (*)(void*))dlsym(n.lib, "ncclCommDestroy");
+        n.Send = (int (*)(const void*, size_t, int, int, void*, cudaStream_t))dlsym(n.lib, "ncclSend");
+        n.Recv = (int (*)(void*, size_t, int, int, void*, cudaStream_t))dlsym(n.lib, "ncclRecv");
+        n.GroupStart = (int (*)())dlsym(n.lib, "ncclGroupStart");
+        n.GroupEnd = (int (*)())dlsym(n.lib, "ncclGroupEnd");
+        n.GetErrorString = (const char* (*)(int))dlsym(n.lib, "ncclGetErrorString");
+    });
+    if (!n.lib || !n.GetUniqueId || !n.CommInitRank || !n.Send || !n.Recv || !n.GroupStart ||
+        !n.GroupEnd)
+        return nullptr;
+    return &n;
+}
+
+#define NCCL_TRY(expr)                                                                  \
+    do {                                                                                \
+        int r_ = (expr);                                                                \
+        if (r_ != 0)                                                                    \
+            return fail(AVIRB200_ERR_NCCL, std::string(#expr) + ": " +                  \
+                                               (nc->GetErrorString ? nc->GetErrorString(r_) \
+                                                                   : "nccl error"));     \
+    } while (0)
+
+int shard_compute(const avirb200_plan* pl, int rank, int nranks, avirb200_shard_info* info) {
+    if (nranks < 1 || rank < 0 || rank >= nranks) return fail(AVIRB200_ERR_BAD_ARG, "bad rank");
+    const avirb200_plan_desc& d = pl->desc;
+    auto src_split = [&](int r) { return (int)((long long)d.src_h * r / nranks); };
+    auto dst_split = [&](int r) { return (int)((long long)d.dst_h * r / nranks); };
+    info->src_row0 = src_split(rank);
+    info->src_rows = src_split(rank + 1) - info->src_row0;
+    info->dst_row0 = dst_split(rank);
+    info->dst_rows = dst_split(rank + 1) - info->dst_row0;
+    if (info->dst_rows <= 0 || info->src_rows <= 0)
+        return fail(AVIRB200_ERR_UNSUPPORTED, "image has fewer rows than ranks");
+    Range need = chain_source_range(pl->v.hostdev,
+                                    Range{info->dst_row0, info->dst_row0 + info->dst_rows - 1},
+                                    nullptr);
+    // The band always contains the rank's own rows (they are produced locally anyway).
+    need.a = imin(need.a, info->src_row0);
+    need.b = imax(need.b, info->src_row0 + info->src_rows - 1);
+    info->need_row0 = need.a;
+    info->need_rows = need.b - need.a + 1;
+    info->halo_up = info->src_row0 - need.a;
+    info->halo_down = need.b - (info->src_row0 + info->src_rows - 1);
+    if (rank > 0 && info->halo_up > src_split(rank) - src_split(rank - 1))
+        return fail(AVIRB200_ERR_UNSUPPORTED, "halo exceeds the neighbouring band (too many ranks)");
+    if (rank + 1 < nranks && info->halo_down > src_split(rank + 2 > nranks ? nranks : rank + 2) -
+                                                   src_split(rank + 1))
+        return fail(AVIRB200_ERR_UNSUPPORTED, "halo exceeds the neighbouring band (too many ranks)");
+    return 0;
+}
+
+} // namespace
+
+extern "C" {
+
+const char* avirb200_status_string(int s) {
+    switch (s) {
+    case AVIRB200_OK: return "ok";
+    case AVIRB200_ERR_BAD_ARG: return "bad argument";
+    case AVIRB200_ERR_CUDA: return "CUDA error";
+    case AVIRB200_ERR_NCCL: return "NCCL error";
+    case AVIRB200_ERR_UNSUPPORTED: return "unsupported configuration";
+    case AVIRB200_ERR_NO_DEVICE: return "no usable CUDA device";
+    case AVIRB200_ERR_ALLOC: return "out of memory";
+    default: return "unknown status";
+    }
+}
+
+const char* avirb200_last_error(void) { return g_err.c_str(); }
+
+int avirb200_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+int avirb200_plan_create(const avirb200_plan_desc* desc, avirb200_plan** out) {
+    if (desc == nullptr || out == nullptr) return fail(AVIRB200_ERR_BAD_ARG, "null argument");
+    *out = nullptr;
+    if (desc->channels < 1 || desc->channels > 4 || desc->src_w < 1 || desc->src_h < 1 ||
+        desc->dst_w < 1 || desc->dst_h < 1)
+        return fail(AVIRB200_ERR_BAD_ARG, "bad image geometry");
+    if (desc->in_type < 0 || desc->in_type > 2 || desc->out_type < 0 || desc->out_type > 2)
+        return fail(AVIRB200_ERR_BAD_ARG, "bad element type");
+    if (desc->h.src_len != desc->src_w || desc->h.dst_len != desc->dst_w ||
+        desc->v.src_len != desc->src_h || desc->v.dst_len != desc->dst_h)
+        return fail(AVIRB200_ERR_BAD_ARG, "axis lengths do not match the image");
+    int ndev = 0;
+    {
+        cudaError_t e = cudaGetDeviceCount(&ndev);
+        if (e != cudaSuccess || ndev == 0)
+            return fail(AVIRB200_ERR_NO_DEVICE,
+                        std::string("no CUDA device: ") + cudaGetErrorString(e));
+    }
+    std::unique_ptr<avirb200_plan> pl(new (std::nothrow) avirb200_plan());
+    if (!pl) return fail(AVIRB200_ERR_ALLOC, "host allocation failed");
+    pl->desc = *desc;
+    int r = copy_axis_host(pl->h, desc->h);
+    if (r != 0) return r;
+    r = copy_axis_host(pl->v, desc->v);
+    if (r != 0) return r;
+    CUDA_TRY(cudaGetDevice(&pl->device));
+
+    const size_t bytes = axis_arena_bytes(pl->h) + axis_arena_bytes(pl->v) + 1024 + 256;
+    CUDA_TRY(cudaMalloc(&pl->arena, bytes));
+    std::vector<char> img(bytes, 0);
+    size_t off = 0;
+    {
+        float lut[256];
+        make_srgb_lut(lut);
+        std::memcpy(img.data(), lut, sizeof lut);
+        pl->d_lut = reinterpret_cast<float*>(pl->arena);
+        off = 1024;
+    }
+    build_dev_axis(pl->h, img, off, static_cast<char*>(pl->arena));
+    build_dev_axis(pl->v, img, off, static_cast<char*>(pl->arena));
+    CUDA_TRY(cudaMemcpy(pl->arena, img.data(), bytes, cudaMemcpyHostToDevice));
+
+    pl->cfg_h = choose_generic_config(pl->h.hostdev, desc->channels, 0, desc->dst_w);
+    pl->cfg_v = choose_generic_config(pl->v.hostdev, desc->channels, 0, desc->dst_h);
+    fast_plan_init(pl->fast, pl->h.hostdev, pl->v.hostdev, pl->h.dev, pl->v.dev, *desc);
+    *out = pl.release();
+    return 0;
+}
+
+void avirb200_plan_destroy(avirb200_plan* pl) {
+    if (pl == nullptr) return;
+    cudaFree(pl->arena);
+    cudaFree(pl->d_src);
+    cudaFree(pl->d_dst);
+    cudaFree(pl->d_ws);
+    fast_plan_free(pl->fast);
+    if (pl->stream) cudaStreamDestroy(pl->stream);
+    delete pl;
+}
+
+int avirb200_plan_workspace_bytes(const avirb200_plan* pl, size_t* bytes) {
+    if (pl == nullptr || bytes == nullptr) return fail(AVIRB200_ERR_BAD_ARG, "null argument");
+    const avirb200_plan_desc& d = pl->desc;
+    *bytes = (size_t)d.dst_w * d.src_h * d.channels * sizeof(float);
+    return 0;
+}
+
+int avirb200_plan_last_launches(const avirb200_plan* pl) { return pl ? pl->last_launches : 0; }
+
+int avirb200_resize_device(const avirb200_plan* pl, const void* d_src, size_t src_pitch, void* d_dst,
+                           size_t dst_pitch, void* d_ws, void* stream) {
+    if (pl == nullptr || d_src == nullptr || d_dst == nullptr || d_ws == nullptr)
+        return fail(AVIRB200_ERR_BAD_ARG, "null argument");
+    const avirb200_plan_desc& d = pl->desc;
+    if (src_pitch < (size_t)d.src_w * d.channels || dst_pitch < (size_t)d.dst_w * d.channels)
+        return fail(AVIRB200_ERR_BAD_ARG, "pitch smaller than a row");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int launches = 0;
+    int r = run_row_pass(pl, d_src, src_pitch, static_cast<float*>(d_ws), d.src_h, st, &launches);
+    if (r != 0) return r;
+    r = run_col_pass(pl, static_cast<const float*>(d_ws), 0, d_dst, dst_pitch, 0, d.dst_h, st,
+                     &launches);
+    pl->last_launches = launches;
+    return r;
+}
+
+int avirb200_resize_host(avirb200_plan* pl, const void* h_src, size_t src_pitch, void* h_dst,
+                         size_t dst_pitch) {
+    if (pl == nullptr || h_src == nullptr || h_dst == nullptr)
+        return fail(AVIRB200_ERR_BAD_ARG, "null argument");
+    const avirb200_plan_desc& d = pl->desc;
+    std::lock_guard<std::mutex> lk(pl->mx);
+    CUDA_TRY(cudaSetDevice(pl->device));
+    const size_t in_row = (size_t)d.src_w * d.channels * dtype_size(d.in_type);
+    const size_t out_row = (size_t)d.dst_w * d.channels * dtype_size(d.out_type);
+    const size_t in_bytes = in_row * d.src_h, out_bytes = out_row * d.dst_h;
+    size_t ws = 0;
+    avirb200_plan_workspace_bytes(pl, &ws);
+    if (pl->stream == nullptr) CUDA_TRY(cudaStreamCreateWithFlags(&pl->stream, cudaStreamNonBlocking));
+    if (pl->d_src_bytes < in_bytes) {
+        cudaFree(pl->d_src); pl->d_src = nullptr; pl->d_src_bytes = 0;
+        CUDA_TRY(cudaMalloc(&pl->d_src, in_bytes));
+        pl->d_src_bytes = in_bytes;
+    }
+    if (pl->d_dst_bytes < out_bytes) {
+        cudaFree(pl->d_dst); pl->d_dst = nullptr; pl->d_dst_bytes = 0;
+        CUDA_TRY(cudaMalloc(&pl->d_dst, out_bytes));
+        pl->d_dst_bytes = out_bytes;
+    }
+    if (pl->d_ws_bytes < ws) {
+        cudaFree(pl->d_ws); pl->d_ws = nullptr; pl->d_ws_bytes = 0;
+        CUDA_TRY(cudaMalloc(&pl->d_ws, ws));
+        pl->d_ws_bytes = ws;
+    }
+    CUDA_TRY(cudaMemcpy2DAsync(pl->d_src, in_row, h_src, src_pitch * dtype_size(d.in_type), in_row,
+                               d.src_h, cudaMemcpyHostToDevice, pl->stream));
+    int r = avirb200_resize_device(pl, pl->d_src, (size_t)d.src_w * d.channels, pl->d_dst,
+                                   (size_t)d.dst_w * d.channels, pl->d_ws, pl->stream);
+    if (r != 0) return r;
+    CUDA_TRY(cudaMemcpy2DAsync(h_dst, dst_pitch * dtype_size(d.out_type), pl->d_dst, out_row,
+                               out_row, d.dst_h, cudaMemcpyDeviceToHost, pl->stream));
+    CUDA_TRY(cudaStreamSynchronize(pl->stream));
+    return 0;
+}
+
+// ---- sharded ---------------------------------------------------------------------------------
+
+int avirb200_shard_query(const avirb200_plan* pl, int rank, int nranks, avirb200_shard_info* info) {
+    if (pl == nullptr || info == nullptr) return fail(AVIRB200_ERR_BAD_ARG, "null argument");
+    return shard_compute(pl, rank, nranks, info);
+}
+
+int avirb200_shard_workspace_bytes(const avirb200_plan* pl, int rank, int nranks, size_t* bytes) {
+    if (pl == nullptr || bytes == nullptr) return fail(AVIRB200_ERR_BAD_ARG, "null argument");
+    avirb200_shard_info si;
+    int r = shard_compute(pl, rank, nranks, &si);
+    if (r != 0) return r;
+    *bytes = (size_t)si.need_rows * pl->desc.dst_w * pl->desc.channels * sizeof(float);
+    return 0;
+}
+
+int avirb200_comm_unique_id(void* id128) {
+    Nccl* nc = nccl();
+    if (!nc) return fail(AVIRB200_ERR_NCCL, "libnccl.so.2 not loadable");
+    NCCL_TRY(nc->GetUniqueId(id128));
+    return 0;
+}
+
+int avirb200_comm_create(const void* id128, int rank, int nranks, void** comm_out) {
+    Nccl* nc = nccl();
+    if (!nc) return fail(AVIRB200_ERR_NCCL, "libnccl.so.2 not loadable");
+    Id128 id;
+    std::memcpy(&id, id128, sizeof id);
+    NCCL_TRY(nc->CommInitRank(comm_out, nranks, id, rank));
+    return 0;
+}
+
+void avirb200_comm_destroy(void* comm) {
+    Nccl* nc = nccl();
+    if (nc && nc->CommDestroy && comm) nc->CommDestroy(comm);
+}
+
+int avirb200_resize_sharded(const avirb200_plan* pl, void* comm, int rank, int nranks,
+                            const void* d_src, size_t src_pitch, void* d_dst, size_t dst_pitch,
+                            void* d_ws, void* stream) {
+    if (pl == nullptr || d_src == nullptr || d_dst == nullptr || d_ws == nullptr)
+        return fail(AVIRB200_ERR_BAD_ARG, "null argument");
+    avirb200_shard_info si;
+    int r = shard_compute(pl, rank, nranks, &si);
+    if (r != 0) return r;
+    const avirb200_plan_desc& d = pl->desc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t rowf = (size_t)d.dst_w * d.channels; // floats per intermediate row
+    float* mid = static_cast<float*>(d_ws);
+    float* own = mid + (size_t)si.halo_up * rowf;
+    int launches = 0;
+    r = run_row_pass(pl, d_src, src_pitch, own, si.src_rows, st, &launches);
+    if (r != 0) return r;
+    if (nranks > 1) {
+        if (comm == nullptr) return fail(AVIRB200_ERR_BAD_ARG, "sharded resize needs a communicator");
+        Nccl* nc = nccl();
+        if (!nc) return fail(AVIRB200_ERR_NCCL, "libnccl.so.2 not loadable");
+        // What the neighbours need from this rank is symmetric information: compute theirs.
+        avirb200_shard_info up, down;
+        if (rank > 0) { r = shard_compute(pl, rank - 1, nranks, &up); if (r != 0) return r; }
+        if (rank + 1 < nranks) { r = shard_compute(pl, rank + 1, nranks, &down); if (r != 0) return r; }
+        NCCL_TRY(nc->GroupStart());
+        if (rank > 0) {
+            if (up.halo_down > 0) // my first rows go up
+                NCCL_TRY(nc->Send(own, (size_t)up.halo_down * rowf, 7, rank - 1, comm, st));
+            if (si.halo_up > 0)
+                NCCL_TRY(nc->Recv(mid, (size_t)si.halo_up * rowf, 7, rank - 1, comm, st));
+        }
+        if (rank + 1 < nranks) {
+            if (down.halo_up > 0) // my last rows go down
+                NCCL_TRY(nc->Send(own + (size_t)(si.src_rows - down.halo_up) * rowf,
+                                  (size_t)down.halo_up * rowf, 7, rank + 1, comm, st));
+            if (si.halo_down > 0)
+                NCCL_TRY(nc->Recv(own + (size_t)si.src_rows * rowf, (size_t)si.halo_down * rowf, 7,
+                                  rank + 1, comm, st));
+        }
+        NCCL_TRY(nc->GroupEnd());
+    }
+    r = run_col_pass(pl, mid, si.need_row0, d_dst, dst_pitch, si.dst_row0,
+                     si.dst_row0 + si.dst_rows, st, &launches);
+    pl->last_launches = launches;
+    return r;
+}
+
+} // extern "C"

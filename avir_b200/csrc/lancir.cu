@@ -1,0 +1,265 @@
+// lancir.cu -- LANCIR (upstream lancir.h) on sm_100a: column pass, row pass + output.
+//
+// Arithmetic to mirror (4-channel images, upstream AVX/SSE2 build; lancir.h:2466-2515):
+// per channel two interleaved partial sums over the taps -- even taps into one, odd taps
+// into the other -- added at the end.  Source reads clamp to the image (upstream pads by
+// replication: copyScanlineNv lancir.h:1406-1594, padScanlineNh 1611-1734).  Output
+// (lancir.h:1772-2056): optional multiply, clamp, round-to-nearest-even; the last
+// `(NewWidth*C) & 3` elements of a row round as (int)(v + 0.5f) instead.
+//
+// The column pass keeps threads along x (coalesced); the row pass stages a strip of the
+// fp32 intermediate in shared memory.
+
+#include <cuda_runtime.h>
+
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "avirb200.h"
+
+namespace {
+
+thread_local std::string g_lerr;
+
+int lfail(int code, const std::string& m) {
+    g_lerr = m;
+    return code;
+}
+
+#define LCUDA_TRY(expr)                                                                    \
+    do {                                                                                   \
+        cudaError_t e_ = (expr);                                                           \
+        if (e_ != cudaSuccess)                                                             \
+            return lfail(e_ == cudaErrorMemoryAllocation ? AVIRB200_ERR_ALLOC : AVIRB200_ERR_CUDA, \
+                         std::string(#expr) + ": " + cudaGetErrorString(e_));              \
+    } while (0)
+
+struct LAxis {
+    int src_len, dst_len, kl, nphases;
+    const float* taps;
+    const int* src_pos;
+    const int* phase;
+};
+
+struct LParams {
+    LAxis v, h;
+    int src_w, src_h, dst_w, dst_h, C;
+    int in_type, out_type;
+    float out_mul, clamp_max;
+    int unity;
+    const void* src; long long src_pitch;
+    float* mid;          // [dst_h][src_w*C]
+    void* dst; long long dst_pitch;
+};
+
+__device__ __forceinline__ float lload(const void* p, int type, long long i) {
+    if (type == AVIRB200_U8) return (float)((const unsigned char*)p)[i];
+    if (type == AVIRB200_U16) return (float)((const unsigned short*)p)[i];
+    return ((const float*)p)[i];
+}
+
+// Column pass: one thread per (x, c) element of an output row; grid.y = output row.
+__global__ void __launch_bounds__(256) lancir_col_kernel(const __grid_constant__ LParams p) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x; // element within a row
+    const int y = blockIdx.y;
+    const int row_elems = p.src_w * p.C;
+    if (e >= row_elems) return;
+    const int kl = p.v.kl;
+    const float* f = p.v.taps + (size_t)__ldg(p.v.phase + y) * kl;
+    const int s0 = __ldg(p.v.src_pos + y);
+    float ev = 0.0f, od = 0.0f;
+    for (int t = 0; t < kl; ++t) {
+        int sy = s0 + t;
+        sy = sy < 0 ? 0 : (sy >= p.src_h ? p.src_h - 1 : sy);
+        const float prod = __fmul_rn(__ldg(f + t), lload(p.src, p.in_type, (long long)sy * p.src_pitch + e));
+        if (t < 2) { if (t == 0) ev = prod; else od = prod; }
+        else if (t & 1) od = __fadd_rn(od, prod);
+        else ev = __fadd_rn(ev, prod);
+    }
+    p.mid[(size_t)y * row_elems + e] = __fadd_rn(ev, od);
+}
+
+// Row pass + output: one thread per output element; grid.y = row.
+__global__ void __launch_bounds__(256) lancir_row_kernel(const __grid_constant__ LParams p) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    const int out_elems = p.dst_w * p.C;
+    if (e >= out_elems) return;
+    const int x = e / p.C, c = e - x * p.C;
+    const int kl = p.h.kl;
+    const float* f = p.h.taps + (size_t)__ldg(p.h.phase + x) * kl;
+    const int s0 = __ldg(p.h.src_pos + x);
+    const float* row = p.mid + (size_t)y * p.src_w * p.C;
+    float ev = 0.0f, od = 0.0f;
+    for (int t = 0; t < kl; ++t) {
+        int sx = s0 + t;
+        sx = sx < 0 ? 0 : (sx >= p.src_w ? p.src_w - 1 : sx);
+        const float prod = __fmul_rn(__ldg(f + t), row[(size_t)sx * p.C + c]);
+        if (t < 2) { if (t == 0) ev = prod; else od = prod; }
+        else if (t & 1) od = __fadd_rn(od, prod);
+        else ev = __fadd_rn(ev, prod);
+    }
+    float v = __fadd_rn(ev, od);
+    if (!p.unity) v = __fmul_rn(v, p.out_mul);
+    const long long g = (long long)y * p.dst_pitch + e;
+    if (p.out_type == AVIRB200_F32) {
+        ((float*)p.dst)[g] = v;
+        return;
+    }
+    int iv;
+    const bool tail = e >= (out_elems & ~3);
+    if (tail) {
+        const float cv = v > p.clamp_max ? p.clamp_max : (v < 0.0f ? 0.0f : v);
+        iv = __float2int_rz(__fadd_rn(cv, 0.5f));
+    } else {
+        const float cv = fmaxf(fminf(v, p.clamp_max), 0.0f);
+        iv = __float2int_rn(cv);
+    }
+    if (p.out_type == AVIRB200_U8) ((unsigned char*)p.dst)[g] = (unsigned char)iv;
+    else ((unsigned short*)p.dst)[g] = (unsigned short)iv;
+}
+
+size_t lsize(int t) { return t == AVIRB200_U8 ? 1 : (t == AVIRB200_U16 ? 2 : 4); }
+
+} // namespace
+
+struct lancirb200_plan {
+    lancirb200_plan_desc desc;
+    void* arena = nullptr;
+    LAxis dv, dh;
+    int device = 0;
+    std::mutex mx;
+    void* d_src = nullptr;
+    void* d_dst = nullptr;
+    void* d_ws = nullptr;
+    size_t src_bytes = 0, dst_bytes = 0, ws_bytes = 0;
+    cudaStream_t stream = nullptr;
+};
+
+extern "C" {
+
+int lancirb200_plan_create(const lancirb200_plan_desc* d, lancirb200_plan** out) {
+    if (d == nullptr || out == nullptr) return lfail(AVIRB200_ERR_BAD_ARG, "null argument");
+    *out = nullptr;
+    if (d->channels != 4) return lfail(AVIRB200_ERR_UNSUPPORTED, "LANCIR GPU path is 4-channel");
+    if (d->src_w < 1 || d->src_h < 1 || d->dst_w < 1 || d->dst_h < 1)
+        return lfail(AVIRB200_ERR_BAD_ARG, "bad geometry");
+    for (int a = 0; a < 2; ++a) {
+        const lancirb200_axis_desc& ax = a ? d->h : d->v;
+        if (ax.kernel_len < 2 || ax.nphases < 1 || !ax.taps || !ax.src_pos || !ax.phase)
+            return lfail(AVIRB200_ERR_BAD_ARG, "bad axis tables");
+        for (int i = 0; i < ax.dst_len; ++i)
+            if (ax.phase[i] < 0 || ax.phase[i] >= ax.nphases)
+                return lfail(AVIRB200_ERR_BAD_ARG, "phase index out of range");
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return lfail(AVIRB200_ERR_NO_DEVICE, "no CUDA device");
+    std::unique_ptr<lancirb200_plan> pl(new (std::nothrow) lancirb200_plan());
+    if (!pl) return lfail(AVIRB200_ERR_ALLOC, "host allocation failed");
+    pl->desc = *d;
+    LCUDA_TRY(cudaGetDevice(&pl->device));
+    auto al = [](size_t v) { return (v + 255) / 256 * 256; };
+    size_t bytes = 0;
+    for (int a = 0; a < 2; ++a) {
+        const lancirb200_axis_desc& ax = a ? d->h : d->v;
+        bytes += al((size_t)ax.nphases * ax.kernel_len * 4) + 2 * al((size_t)ax.dst_len * 4);
+    }
+    LCUDA_TRY(cudaMalloc(&pl->arena, bytes));
+    std::vector<char> img(bytes, 0);
+    size_t off = 0;
+    for (int a = 0; a < 2; ++a) {
+        const lancirb200_axis_desc& ax = a ? d->h : d->v;
+        LAxis& da = a ? pl->dh : pl->dv;
+        da.src_len = ax.src_len; da.dst_len = ax.dst_len; da.kl = ax.kernel_len;
+        da.nphases = ax.nphases;
+        char* base = static_cast<char*>(pl->arena);
+        size_t n = (size_t)ax.nphases * ax.kernel_len * 4;
+        std::memcpy(img.data() + off, ax.taps, n);
+        da.taps = reinterpret_cast<const float*>(base + off); off += al(n);
+        n = (size_t)ax.dst_len * 4;
+        std::memcpy(img.data() + off, ax.src_pos, n);
+        da.src_pos = reinterpret_cast<const int*>(base + off); off += al(n);
+        std::memcpy(img.data() + off, ax.phase, n);
+        da.phase = reinterpret_cast<const int*>(base + off); off += al(n);
+    }
+    LCUDA_TRY(cudaMemcpy(pl->arena, img.data(), bytes, cudaMemcpyHostToDevice));
+    pl->desc.v.taps = nullptr; pl->desc.h.taps = nullptr;
+    *out = pl.release();
+    return 0;
+}
+
+void lancirb200_plan_destroy(lancirb200_plan* pl) {
+    if (!pl) return;
+    cudaFree(pl->arena); cudaFree(pl->d_src); cudaFree(pl->d_dst); cudaFree(pl->d_ws);
+    if (pl->stream) cudaStreamDestroy(pl->stream);
+    delete pl;
+}
+
+int lancirb200_plan_workspace_bytes(const lancirb200_plan* pl, size_t* bytes) {
+    if (!pl || !bytes) return lfail(AVIRB200_ERR_BAD_ARG, "null argument");
+    *bytes = (size_t)pl->desc.dst_h * pl->desc.src_w * pl->desc.channels * sizeof(float);
+    return 0;
+}
+
+int lancirb200_resize_device(const lancirb200_plan* pl, const void* d_src, size_t src_pitch,
+                             void* d_dst, size_t dst_pitch, void* d_ws, void* stream) {
+    if (!pl || !d_src || !d_dst || !d_ws) return lfail(AVIRB200_ERR_BAD_ARG, "null argument");
+    const lancirb200_plan_desc& d = pl->desc;
+    LParams p;
+    p.v = pl->dv; p.h = pl->dh;
+    p.src_w = d.src_w; p.src_h = d.src_h; p.dst_w = d.dst_w; p.dst_h = d.dst_h; p.C = d.channels;
+    p.in_type = d.in_type; p.out_type = d.out_type;
+    p.out_mul = d.out_mul; p.clamp_max = d.clamp_max; p.unity = d.is_unity_mul;
+    p.src = d_src; p.src_pitch = (long long)src_pitch;
+    p.mid = static_cast<float*>(d_ws);
+    p.dst = d_dst; p.dst_pitch = (long long)dst_pitch;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (d.dst_h > 65535) return lfail(AVIRB200_ERR_UNSUPPORTED, "image too tall");
+    dim3 g1((d.src_w * d.channels + 255) / 256, d.dst_h);
+    lancir_col_kernel<<<g1, 256, 0, st>>>(p);
+    dim3 g2((d.dst_w * d.channels + 255) / 256, d.dst_h);
+    lancir_row_kernel<<<g2, 256, 0, st>>>(p);
+    LCUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int lancirb200_resize_host(lancirb200_plan* pl, const void* h_src, size_t src_pitch, void* h_dst,
+                           size_t dst_pitch) {
+    if (!pl || !h_src || !h_dst) return lfail(AVIRB200_ERR_BAD_ARG, "null argument");
+    const lancirb200_plan_desc& d = pl->desc;
+    std::lock_guard<std::mutex> lk(pl->mx);
+    LCUDA_TRY(cudaSetDevice(pl->device));
+    const size_t in_row = (size_t)d.src_w * d.channels * lsize(d.in_type);
+    const size_t out_row = (size_t)d.dst_w * d.channels * lsize(d.out_type);
+    size_t ws = 0;
+    lancirb200_plan_workspace_bytes(pl, &ws);
+    if (!pl->stream) LCUDA_TRY(cudaStreamCreateWithFlags(&pl->stream, cudaStreamNonBlocking));
+    if (pl->src_bytes < in_row * d.src_h) {
+        cudaFree(pl->d_src); pl->d_src = nullptr; pl->src_bytes = 0;
+        LCUDA_TRY(cudaMalloc(&pl->d_src, in_row * d.src_h)); pl->src_bytes = in_row * d.src_h;
+    }
+    if (pl->dst_bytes < out_row * d.dst_h) {
+        cudaFree(pl->d_dst); pl->d_dst = nullptr; pl->dst_bytes = 0;
+        LCUDA_TRY(cudaMalloc(&pl->d_dst, out_row * d.dst_h)); pl->dst_bytes = out_row * d.dst_h;
+    }
+    if (pl->ws_bytes < ws) {
+        cudaFree(pl->d_ws); pl->d_ws = nullptr; pl->ws_bytes = 0;
+        LCUDA_TRY(cudaMalloc(&pl->d_ws, ws)); pl->ws_bytes = ws;
+    }
+    LCUDA_TRY(cudaMemcpy2DAsync(pl->d_src, in_row, h_src, src_pitch * lsize(d.in_type), in_row,
+                                d.src_h, cudaMemcpyHostToDevice, pl->stream));
+    int r = lancirb200_resize_device(pl, pl->d_src, (size_t)d.src_w * d.channels, pl->d_dst,
+                                     (size_t)d.dst_w * d.channels, pl->d_ws, pl->stream);
+    if (r != 0) return r;
+    LCUDA_TRY(cudaMemcpy2DAsync(h_dst, dst_pitch * lsize(d.out_type), pl->d_dst, out_row, out_row,
+                                d.dst_h, cudaMemcpyDeviceToHost, pl->stream));
+    LCUDA_TRY(cudaStreamSynchronize(pl->stream));
+    return 0;
+}
+
+} // extern "C"
