@@ -31,6 +31,7 @@ using namespace avb;
 namespace {
 
 thread_local std::string g_err;
+bool g_force_generic = false; // debug/test switch: bypass the specialised kernels
 
 int fail(int code, const std::string& msg) {
     g_err = msg;
@@ -299,7 +300,7 @@ int run_row_pass(const avirb200_plan* pl, const void* d_src, size_t src_pitch, f
                  int rows, cudaStream_t st, int* launches) {
     if (rows <= 0) return 0;
     const avirb200_plan_desc& d = pl->desc;
-    if (env_fast_enabled() && pl->fast.h_ok) {
+    if (env_fast_enabled() && !g_force_generic && pl->fast.h_ok) {
         int r = fast_row_pass(pl->fast, pl->h.dev, d, d_src, src_pitch, d_mid, rows, pl->d_lut, st);
         if (r != 0) return fail(AVIRB200_ERR_CUDA, "fast row pass launch failed");
         ++*launches;
@@ -331,7 +332,7 @@ int run_col_pass(const avirb200_plan* pl, const float* d_mid, int mid_row_base, 
                  size_t dst_pitch, int out0, int out1, cudaStream_t st, int* launches) {
     if (out1 <= out0) return 0;
     const avirb200_plan_desc& d = pl->desc;
-    if (env_fast_enabled() && pl->fast.v_ok) {
+    if (env_fast_enabled() && !g_force_generic && pl->fast.v_ok) {
         int r = fast_col_pass(pl->fast, pl->v.dev, d, d_mid, mid_row_base, d_dst, dst_pitch, out0,
                               out1, st);
         if (r != 0) return fail(AVIRB200_ERR_CUDA, "fast column pass launch failed");
@@ -414,18 +415,18 @@ Nccl* nccl() {
                                                                    : "nccl error"));     \
     } while (0)
 
-int shard_compute(const avirb200_plan* pl, int rank, int nranks, avirb200_shard_info* info) {
+int shard_compute_axis(const DevAxis& vaxis, int rank, int nranks, avirb200_shard_info* info) {
     if (nranks < 1 || rank < 0 || rank >= nranks) return fail(AVIRB200_ERR_BAD_ARG, "bad rank");
-    const avirb200_plan_desc& d = pl->desc;
-    auto src_split = [&](int r) { return (int)((long long)d.src_h * r / nranks); };
-    auto dst_split = [&](int r) { return (int)((long long)d.dst_h * r / nranks); };
+    const int src_h = vaxis.src_len, dst_h = vaxis.dst_len;
+    auto src_split = [&](int r) { return (int)((long long)src_h * r / nranks); };
+    auto dst_split = [&](int r) { return (int)((long long)dst_h * r / nranks); };
     info->src_row0 = src_split(rank);
     info->src_rows = src_split(rank + 1) - info->src_row0;
     info->dst_row0 = dst_split(rank);
     info->dst_rows = dst_split(rank + 1) - info->dst_row0;
     if (info->dst_rows <= 0 || info->src_rows <= 0)
         return fail(AVIRB200_ERR_UNSUPPORTED, "image has fewer rows than ranks");
-    Range need = chain_source_range(pl->v.hostdev,
+    Range need = chain_source_range(vaxis,
                                     Range{info->dst_row0, info->dst_row0 + info->dst_rows - 1},
                                     nullptr);
     // The band always contains the rank's own rows (they are produced locally anyway).
@@ -443,9 +444,48 @@ int shard_compute(const avirb200_plan* pl, int rank, int nranks, avirb200_shard_
     return 0;
 }
 
+int shard_compute(const avirb200_plan* pl, int rank, int nranks, avirb200_shard_info* info) {
+    return shard_compute_axis(pl->v.hostdev, rank, nranks, info);
+}
+
+// Geometry-only view of an axis descriptor (host pointers), for range arithmetic.
+DevAxis host_axis_view(const avirb200_axis_desc& ad) {
+    DevAxis d;
+    std::memset(&d, 0, sizeof d);
+    d.src_len = ad.src_len; d.dst_len = ad.dst_len; d.nsteps = ad.nsteps;
+    int lo = 0, hi = ad.src_len;
+    for (int i = 0; i < ad.nsteps && i < AVIRB200_MAX_STEPS; ++i) {
+        const avirb200_step_desc& s = ad.steps[i];
+        DevStep& ds = d.steps[i];
+        ds.kind = s.kind; ds.resample = s.resample; ds.latency = s.latency; ds.edge = s.edge;
+        ds.in_len = s.in_len; ds.out_len = s.out_len; ds.ntaps = s.ntaps; ds.order = s.order;
+        ds.upsampled = s.upsampled; ds.skip_odd = s.skip_odd; ds.zero_start = s.zero_start;
+        ds.nphases = s.nphases;
+        ds.out_prefix = s.out_prefix; ds.out_suffix = s.out_suffix;
+        ds.in_prefix = s.in_prefix; ds.in_suffix = s.in_suffix;
+        ds.n_prefix_dc = s.n_prefix_dc; ds.n_suffix_dc = s.n_suffix_dc;
+        ds.in_lo = lo; ds.in_hi = hi;
+        ds.taps = s.taps; ds.src_pos = s.src_pos; ds.phase = s.phase; ds.frac = s.frac;
+        ds.prefix_dc = s.prefix_dc; ds.suffix_dc = s.suffix_dc;
+        const Range od = step_output_domain(ds);
+        lo = od.a; hi = od.b + 1;
+    }
+    return d;
+}
+
 } // namespace
 
 extern "C" {
+
+void avirb200_debug_force_generic(int on) { g_force_generic = (on != 0); }
+
+int avirb200_shard_query_desc(const avirb200_plan_desc* desc, int rank, int nranks,
+                              avirb200_shard_info* info) {
+    if (desc == nullptr || info == nullptr) return fail(AVIRB200_ERR_BAD_ARG, "null argument");
+    if (desc->v.nsteps < 1 || desc->v.nsteps > AVIRB200_MAX_STEPS)
+        return fail(AVIRB200_ERR_BAD_ARG, "axis: nsteps out of range");
+    return shard_compute_axis(host_axis_view(desc->v), rank, nranks, info);
+}
 
 const char* avirb200_status_string(int s) {
     switch (s) {
@@ -552,6 +592,24 @@ int avirb200_resize_device(const avirb200_plan* pl, const void* d_src, size_t sr
                      &launches);
     pl->last_launches = launches;
     return r;
+}
+
+int avirb200_row_pass_device(const avirb200_plan* pl, const void* d_src, size_t src_pitch,
+                             void* d_ws, void* stream) {
+    if (pl == nullptr || d_src == nullptr || d_ws == nullptr)
+        return fail(AVIRB200_ERR_BAD_ARG, "null argument");
+    int launches = 0;
+    return run_row_pass(pl, d_src, src_pitch, static_cast<float*>(d_ws), pl->desc.src_h,
+                        static_cast<cudaStream_t>(stream), &launches);
+}
+
+int avirb200_col_pass_device(const avirb200_plan* pl, const void* d_ws, void* d_dst,
+                             size_t dst_pitch, void* stream) {
+    if (pl == nullptr || d_dst == nullptr || d_ws == nullptr)
+        return fail(AVIRB200_ERR_BAD_ARG, "null argument");
+    int launches = 0;
+    return run_col_pass(pl, static_cast<const float*>(d_ws), 0, d_dst, dst_pitch, 0,
+                        pl->desc.dst_h, static_cast<cudaStream_t>(stream), &launches);
 }
 
 int avirb200_resize_host(avirb200_plan* pl, const void* h_src, size_t src_pitch, void* h_dst,
@@ -675,6 +733,54 @@ int avirb200_resize_sharded(const avirb200_plan* pl, void* comm, int rank, int n
                      si.dst_row0 + si.dst_rows, st, &launches);
     pl->last_launches = launches;
     return r;
+}
+
+int avirb200_resize_sharded_local(const avirb200_plan* pl, int nranks, const void* d_src,
+                                  size_t src_pitch, void* d_dst, size_t dst_pitch, void* d_ws,
+                                  void* stream) {
+    if (pl == nullptr || d_src == nullptr || d_dst == nullptr || d_ws == nullptr)
+        return fail(AVIRB200_ERR_BAD_ARG, "null argument");
+    const avirb200_plan_desc& d = pl->desc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t rowf = (size_t)d.dst_w * d.channels;
+    std::vector<avirb200_shard_info> si(nranks);
+    std::vector<float*> mid(nranks);
+    float* base = static_cast<float*>(d_ws);
+    for (int r = 0; r < nranks; ++r) {
+        int e = shard_compute(pl, r, nranks, &si[r]);
+        if (e != 0) return e;
+        mid[r] = base;
+        base += (size_t)si[r].need_rows * rowf;
+    }
+    int launches = 0;
+    const size_t in_el = dtype_size(d.in_type), out_el = dtype_size(d.out_type);
+    for (int r = 0; r < nranks; ++r) { // every band's row pass
+        float* own = mid[r] + (size_t)si[r].halo_up * rowf;
+        const char* src = static_cast<const char*>(d_src) + (size_t)si[r].src_row0 * src_pitch * in_el;
+        int e = run_row_pass(pl, src, src_pitch, own, si[r].src_rows, st, &launches);
+        if (e != 0) return e;
+    }
+    for (int r = 0; r < nranks; ++r) { // the "exchange"
+        float* own = mid[r] + (size_t)si[r].halo_up * rowf;
+        if (r > 0 && si[r].halo_up > 0) {
+            const float* nb = mid[r - 1] + (size_t)(si[r - 1].halo_up + si[r - 1].src_rows - si[r].halo_up) * rowf;
+            CUDA_TRY(cudaMemcpyAsync(mid[r], nb, (size_t)si[r].halo_up * rowf * 4,
+                                     cudaMemcpyDeviceToDevice, st));
+        }
+        if (r + 1 < nranks && si[r].halo_down > 0) {
+            const float* nb = mid[r + 1] + (size_t)si[r + 1].halo_up * rowf;
+            CUDA_TRY(cudaMemcpyAsync(own + (size_t)si[r].src_rows * rowf, nb,
+                                     (size_t)si[r].halo_down * rowf * 4, cudaMemcpyDeviceToDevice, st));
+        }
+    }
+    for (int r = 0; r < nranks; ++r) {
+        char* dst = static_cast<char*>(d_dst) + (size_t)si[r].dst_row0 * dst_pitch * out_el;
+        int e = run_col_pass(pl, mid[r], si[r].need_row0, dst, dst_pitch, si[r].dst_row0,
+                             si[r].dst_row0 + si[r].dst_rows, st, &launches);
+        if (e != 0) return e;
+    }
+    pl->last_launches = launches;
+    return 0;
 }
 
 } // extern "C"

@@ -126,8 +126,10 @@ void put_axis(std::vector<double>& o, const AxisPlan& a) {
     for (const ExecStep& s : a.steps) {
         const double hd[] = {double(s.kind), double(s.resample), double(s.latency), double(s.edge),
                              double(s.in_len), double(s.out_len), double(s.ntaps), double(s.order),
-                             double(s.upsampled), double(s.skip_odd), double(s.nphases)};
-        o.insert(o.end(), hd, hd + 11);
+                             double(s.upsampled), double(s.skip_odd), double(s.nphases),
+                             double(s.out_prefix), double(s.out_suffix), double(s.in_prefix),
+                             double(s.in_suffix)};
+        o.insert(o.end(), hd, hd + 15);
         o.push_back(static_cast<double>(s.taps.size()));
         for (float f : s.taps) o.push_back(f);
         o.push_back(static_cast<double>(s.src_pos.size()));

@@ -130,6 +130,14 @@ int avirb200_plan_workspace_bytes(const avirb200_plan* plan, size_t* bytes);
 int avirb200_resize_device(const avirb200_plan* plan, const void* d_src, size_t src_pitch,
                            void* d_dst, size_t dst_pitch, void* d_workspace, void* stream);
 
+/* The two passes of avirb200_resize_device individually (same arguments, same stream
+ * semantics): row pass src -> workspace, column pass workspace -> dst.  For callers that
+ * pipeline frames, and for per-kernel timing. */
+int avirb200_row_pass_device(const avirb200_plan* plan, const void* d_src, size_t src_pitch,
+                             void* d_workspace, void* stream);
+int avirb200_col_pass_device(const avirb200_plan* plan, const void* d_workspace, void* d_dst,
+                             size_t dst_pitch, void* stream);
+
 /* Convenience used by the drop-in resizeImage(): host buffers in, host buffers out
  * (H2D, both passes, D2H, synchronise).  Device buffers are cached inside the plan. */
 int avirb200_resize_host(avirb200_plan* plan, const void* h_src, size_t src_pitch, void* h_dst,
@@ -151,6 +159,9 @@ typedef struct avirb200_shard_info {
 
 int avirb200_shard_query(const avirb200_plan* plan, int rank, int nranks,
                          avirb200_shard_info* info);
+/* Same, from a descriptor alone (pure host arithmetic, no device needed). */
+int avirb200_shard_query_desc(const avirb200_plan_desc* desc, int rank, int nranks,
+                              avirb200_shard_info* info);
 int avirb200_shard_workspace_bytes(const avirb200_plan* plan, int rank, int nranks,
                                    size_t* bytes);
 
@@ -167,6 +178,16 @@ void avirb200_comm_destroy(void* comm);
 int avirb200_resize_sharded(const avirb200_plan* plan, void* comm, int rank, int nranks,
                             const void* d_src, size_t src_pitch, void* d_dst, size_t dst_pitch,
                             void* d_workspace, void* stream);
+
+/* Validation aid: runs the `nranks` bands of the sharded schedule one after another on the
+ * CURRENT device (halo rows moved with device copies instead of NCCL).  Full-image device
+ * buffers; d_workspace must hold the sum of all ranks' avirb200_shard_workspace_bytes. */
+int avirb200_resize_sharded_local(const avirb200_plan* plan, int nranks, const void* d_src,
+                                  size_t src_pitch, void* d_dst, size_t dst_pitch,
+                                  void* d_workspace, void* stream);
+
+/* Test switch: 1 = always use the fully generic pass kernel (skip specialised kernels). */
+void avirb200_debug_force_generic(int on);
 
 /* ---- LANCIR (upstream lancir.h) ------------------------------------------------------- */
 

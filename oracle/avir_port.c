@@ -282,41 +282,47 @@ static float load_elem(const void* src, int type, size_t idx)
     }
 }
 
-/* Whole image: pack -> row pass -> fp32 intermediate -> column pass -> epilogue.
- * resizeImage: avir.h:4680-5092. */
-int avir_port_resize(const avirb200_plan_desc* d, const void* src, size_t src_pitch, void* dst,
-                     size_t dst_pitch)
+typedef struct scratch {
+    float *lin, *lout, *bufA, *bufB;
+    int guard;
+} scratch;
+
+static int scratch_init(scratch* sc, const avirb200_plan_desc* d)
 {
-    const int C = d->channels;
-    const int sw = d->src_w, sh = d->src_h, dw = d->dst_w, dh = d->dst_h;
-    int maxlen = sw > sh ? sw : sh;
+    int maxlen = d->src_w > d->src_h ? d->src_w : d->src_h;
+    sc->guard = 0;
     for (int a = 0; a < 2; a++) {
         const avirb200_axis_desc* ax = a ? &d->v : &d->h;
         for (int i = 0; i < ax->nsteps; i++) {
             const int l = ax->steps[i].out_len + ax->steps[i].out_prefix + ax->steps[i].out_suffix;
             if (l > maxlen) maxlen = l;
+            if (ax->steps[i].out_prefix > sc->guard) sc->guard = ax->steps[i].out_prefix;
         }
     }
-    int guard = 0;
-    for (int a = 0; a < 2; a++) {
-        const avirb200_axis_desc* ax = a ? &d->v : &d->h;
-        for (int i = 0; i < ax->nsteps; i++)
-            if (ax->steps[i].out_prefix > guard) guard = ax->steps[i].out_prefix;
-    }
+    sc->lin = (float*)malloc((size_t)(maxlen + 16) * sizeof(float));
+    sc->lout = (float*)malloc((size_t)(maxlen + 16) * sizeof(float));
+    sc->bufA = (float*)malloc((size_t)(maxlen + sc->guard + 16) * sizeof(float));
+    sc->bufB = (float*)malloc((size_t)(maxlen + sc->guard + 16) * sizeof(float));
+    return (sc->lin && sc->lout && sc->bufA && sc->bufB) ? 0 : AVIRB200_ERR_ALLOC;
+}
+
+static void scratch_free(scratch* sc)
+{
+    free(sc->lin); free(sc->lout); free(sc->bufA); free(sc->bufB);
+}
+
+/* Row pass over `rows` source rows starting at `src` (packScanline: avir.h:2777-2971,
+ * avir_dil.h:64-115; then the H chain) into mid[rows][dst_w*C]. */
+int avir_port_row_pass(const avirb200_plan_desc* d, const void* src, size_t src_pitch, int rows,
+                       float* mid)
+{
+    const int C = d->channels, sw = d->src_w, dw = d->dst_w;
+    scratch sc;
+    if (scratch_init(&sc, d) != 0) return AVIRB200_ERR_ALLOC;
     float lut[256];
     if ((d->use_gamma & 1) && d->in_type == AVIRB200_U8)
         for (int i = 0; i < 256; i++) lut[i] = srgb2lin_u8(i);
-
-    float* mid = (float*)malloc((size_t)dw * sh * C * sizeof(float));
-    float* res = (float*)malloc((size_t)dw * dh * C * sizeof(float));
-    float* lin = (float*)malloc((size_t)(maxlen + 16) * sizeof(float));
-    float* lout = (float*)malloc((size_t)(maxlen + 16) * sizeof(float));
-    float* bufA = (float*)malloc((size_t)(maxlen + guard + 16) * sizeof(float));
-    float* bufB = (float*)malloc((size_t)(maxlen + guard + 16) * sizeof(float));
-    if (!mid || !res || !lin || !lout || !bufA || !bufB) return AVIRB200_ERR_ALLOC;
-
-    /* row pass (packScanline: avir.h:2777-2971, avir_dil.h:64-115) */
-    for (int y = 0; y < sh; y++) {
+    for (int y = 0; y < rows; y++) {
         for (int c = 0; c < C; c++) {
             for (int x = 0; x < sw; x++) {
                 const size_t idx = (size_t)y * src_pitch + (size_t)x * C + c;
@@ -330,34 +336,44 @@ int avir_port_resize(const avirb200_plan_desc* d, const void* src, size_t src_pi
                 } else {
                     v = srgb2lin_f(load_elem(src, d->in_type, idx), d->in_gamma_mult);
                 }
-                lin[x] = v;
+                sc.lin[x] = v;
             }
-            run_chain(&d->h, d->sum_mode, lin, lout, bufA, bufB, guard);
+            run_chain(&d->h, d->sum_mode, sc.lin, sc.lout, sc.bufA, sc.bufB, sc.guard);
             for (int x = 0; x < dw; x++)
-                mid[((size_t)y * dw + x) * C + c] = lout[x];
+                mid[((size_t)y * dw + x) * C + c] = sc.lout[x];
         }
     }
-    /* column pass */
+    scratch_free(&sc);
+    return 0;
+}
+
+/* Column pass + epilogue for destination rows [out0, out1).  `mid` holds intermediate rows
+ * [mid_row0, mid_row0 + mid_rows) of the image; rows outside are poisoned with NaN, so a
+ * band that does not contain everything the outputs depend on is detected (returns
+ * the number of non-finite results, 0 = ok).  `dst` row 0 is destination row out0.
+ * Epilogue: applySRGBGamma (avir.h:2982-3068) -> dither (avir.h:4392-4419,
+ * avir_dil.h:815-859) -> unpackScanline (avir.h:3155-3215). */
+int avir_port_col_pass(const avirb200_plan_desc* d, const float* mid, int mid_row0, int mid_rows,
+                       int out0, int out1, void* dst, size_t dst_pitch)
+{
+    const int C = d->channels, sh = d->src_h, dw = d->dst_w;
+    scratch sc;
+    if (scratch_init(&sc, d) != 0) return AVIRB200_ERR_ALLOC;
+    int bad = 0;
     for (int x = 0; x < dw; x++) {
         for (int c = 0; c < C; c++) {
             for (int y = 0; y < sh; y++)
-                lin[y] = mid[((size_t)y * dw + x) * C + c];
-            run_chain(&d->v, d->sum_mode, lin, lout, bufA, bufB, guard);
-            for (int y = 0; y < dh; y++)
-                res[((size_t)y * dw + x) * C + c] = lout[y];
-        }
-    }
-    /* epilogue: applySRGBGamma (avir.h:2982-3068) -> dither (avir.h:4392-4419,
-     * avir_dil.h:815-859) -> unpackScanline (avir.h:3155-3215) */
-    for (int y = 0; y < dh; y++) {
-        for (int x = 0; x < dw; x++) {
-            for (int c = 0; c < C; c++) {
-                float v = res[((size_t)y * dw + x) * C + c];
+                sc.lin[y] = (y >= mid_row0 && y < mid_row0 + mid_rows)
+                                ? mid[((size_t)(y - mid_row0) * dw + x) * C + c] : NAN;
+            run_chain(&d->v, d->sum_mode, sc.lin, sc.lout, sc.bufA, sc.bufB, sc.guard);
+            for (int y = out0; y < out1; y++) {
+                float v = sc.lout[y];
+                if (!isfinite(v)) bad++;
                 if (d->use_gamma & 2) {
                     if (C == 4 && c == d->alpha_index) v = v * d->out_gamma_mult;
                     else v = lin2srgb(v) * d->out_gamma_mult;
                 }
-                const size_t idx = (size_t)y * dst_pitch + (size_t)x * C + c;
+                const size_t idx = (size_t)(y - out0) * dst_pitch + (size_t)x * C + c;
                 if (d->out_type == AVIRB200_F32) {
                     ((float*)dst)[idx] = v;
                     continue;
@@ -370,8 +386,23 @@ int avir_port_resize(const avirb200_plan_desc* d, const void* src, size_t src_pi
             }
         }
     }
-    free(mid); free(res); free(lin); free(lout); free(bufA); free(bufB);
-    return 0;
+    scratch_free(&sc);
+    return bad;
+}
+
+/* Whole image: row pass -> fp32 intermediate -> column pass.  resizeImage: avir.h:4680-5092. */
+int avir_port_resize(const avirb200_plan_desc* d, const void* src, size_t src_pitch, void* dst,
+                     size_t dst_pitch)
+{
+    float* mid = (float*)malloc((size_t)d->dst_w * d->src_h * d->channels * sizeof(float));
+    if (!mid) return AVIRB200_ERR_ALLOC;
+    int r = avir_port_row_pass(d, src, src_pitch, d->src_h, mid);
+    if (r == 0) {
+        r = avir_port_col_pass(d, mid, 0, d->src_h, 0, d->dst_h, dst, dst_pitch);
+        if (r > 0) r = 0; /* non-finite data is the caller's business for whole images */
+    }
+    free(mid);
+    return r;
 }
 
 /* The u8 sRGB table, for the host-logic tests. */

@@ -43,7 +43,8 @@ def host_plan(mirror, sw, sh, nw, nh, ch, in_dtype, out_dtype, k=0.0, resbits=8,
         steps = []
         for _ in range(ns):
             s = dict(zip(["kind", "R", "lat", "edge", "in_len", "out_len", "ntaps", "order",
-                          "upsampled", "skip_odd", "nphases"], [int(v) for v in take(11)]))
+                          "upsampled", "skip_odd", "nphases", "out_prefix", "out_suffix",
+                          "in_prefix", "in_suffix"], [int(v) for v in take(15)]))
             nt = int(take()[0])
             s["taps"] = take(nt).astype(np.float32)
             npos = int(take()[0])
@@ -69,10 +70,8 @@ def compare_axis(mine, refsteps):
     folded = []
     pend = None
     for s in refsteps:
-        if s["kind"] == 1:
-            if s["FltOrigLen"] == 0:
-                return ["reference used a filtered upsample (out of scope)"]
-            pend = s
+        if s["kind"] == 1 and s["FltOrigLen"] > 0:
+            pend = s  # filterless 2X upsample: folded into the next (resize) step
             continue
         s = dict(s)
         s["up_in_len"] = pend["InLen"] if pend is not None else None
@@ -82,7 +81,18 @@ def compare_axis(mine, refsteps):
         return ["step count %d vs ref %d" % (len(mine["steps"]), len(folded))]
     for i, (m, r) in enumerate(zip(mine["steps"], folded)):
         tag = "step %d: " % i
-        if r["kind"] == 0:
+        if r["kind"] == 1:
+            if m["kind"] != 1:
+                bad.append(tag + "kind")
+                continue
+            for a, b in (("R", "R"), ("lat", "lat"), ("in_len", "InLen"), ("out_len", "OutLen"),
+                         ("out_prefix", "OutPrefix"), ("out_suffix", "OutSuffix"),
+                         ("in_prefix", "InPrefix"), ("in_suffix", "InSuffix")):
+                if m[a] != r[b]:
+                    bad.append(tag + "%s %d vs %d" % (a, m[a], r[b]))
+            if len(m["taps"]) != len(r["Flt"]) or not np.array_equal(_bits(m["taps"]), _bits(r["Flt"])):
+                bad.append(tag + "upsample taps differ")
+        elif r["kind"] == 0:
             if m["kind"] != 0:
                 bad.append(tag + "kind")
                 continue

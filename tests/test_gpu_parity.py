@@ -1,0 +1,254 @@
+"""GPU parity tests proper (run with -m gpu on a B200): the product path -- C++ front-end ->
+C ABI -> sm_100a kernels -- against upstream compiled in-tree (oracle/_ref, travels prebuilt),
+the C port and the committed golden fixtures.  Bit-exact everywhere: integer output AND
+float output (0 ULP; the north-star tolerance for float is 1 ULP, the tests demand 0).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import avir_b200 as ab
+import cases as cs
+import oracle_ref as o
+
+pytestmark = pytest.mark.gpu
+
+needs_ref = pytest.mark.skipif(not o.have_ref(), reason="oracle/_ref not built")
+
+
+def expected(case, src):
+    if o.have_ref():
+        return cs.ref_output(case, src)
+    return cs.port_output(case, src)[0]
+
+
+@pytest.fixture(params=[0, 1], ids=["fast", "generic"])
+def kernel_path(request):
+    """Every parity case runs through the specialised kernels (where they apply) and
+    through the fully generic kernel."""
+    ab.lib().avirb200_debug_force_generic(request.param)
+    yield request.param
+    ab.lib().avirb200_debug_force_generic(0)
+
+
+def test_native_library_is_what_runs():
+    assert ab.device_count() >= 1
+    lib = ab.lib()
+    assert lib.avirb200_plan_last_launches  # symbol present; launches counted per call
+
+
+@pytest.mark.parametrize("case", cs.SMALL_CASES, ids=cs.case_id)
+def test_small_cases_bit_exact(case, kernel_path):
+    src = cs.make_input(case)
+    got = cs.gpu_output(case, src)
+    assert cs.count_mismatch(expected(case, src), got) == 0
+
+
+@pytest.mark.parametrize("structured", ["ramp", "impulse", "checker"])
+@pytest.mark.parametrize("case", cs.SMALL_CASES[:10], ids=cs.case_id)
+def test_structured_inputs_bit_exact(case, structured, kernel_path):
+    src = cs.make_input(case, structured=structured)
+    got = cs.gpu_output(case, src)
+    assert cs.count_mismatch(expected(case, src), got) == 0
+
+
+def test_golden_fixtures():
+    files = sorted(f for f in os.listdir(cs.GOLDEN) if f.startswith("avir_") and f.endswith(".npz"))
+    for f in files:
+        z = np.load(os.path.join(cs.GOLDEN, f), allow_pickle=True)
+        case = tuple(z["case"].tolist())
+        case = case[:6] + (np.dtype(case[6]).type, np.dtype(case[7]).type) + case[8:]
+        got = cs.gpu_output(case, z["src"])
+        assert cs.count_mismatch(z["out"], got) == 0, f
+
+
+def test_zero_size_conventions():
+    # avir.h:4686-4697: empty source -> destination zero-filled; empty destination -> no-op
+    rs = ab.CImageResizer(8, 0, 0, ab.FP_FLOAT4)
+    dst = np.full((4, 4, 4), 7, np.uint8)
+    out = rs.resizeImage(np.zeros((0, 0, 4), np.uint8).reshape(0, 0, 4), 4, 4, NewBuf=dst)
+    assert np.all(out == 0)
+
+
+# ---- medium sizes: many tiles per pass, multi-threaded upstream as the oracle --------------
+
+MEDIUM = [
+    (2, 1920, 1080, 960, 540, 4, np.float32, np.float32, 16, {}),                 # cfg3 / 4
+    (1, 1920, 1080, 960, 540, 4, np.float32, np.float32, 16, {}),
+    (1, 960, 540, 1920, 1080, 4, np.uint8, np.uint8, 8, {}),                      # cfg2 / 2
+    (1, 2048, 2048, 512, 512, 4, np.uint16, np.uint16, 16, {}),                   # cfg4 / 8
+    (2, 1920, 1080, 480, 270, 4, np.uint8, np.uint8, 8, {"gamma": True, "alpha": 3}),  # cfg5 / 4
+    (0, 1280, 720, 2000, 1125, 3, np.uint8, np.uint8, 8, {}),                     # cfg1 ratio
+    (1, 1500, 1000, 1111, 741, 4, np.uint8, np.uint8, 8, {}),                     # many phases
+    (2, 1500, 1000, 1111, 741, 4, np.float32, np.float32, 16, {}),
+]
+
+
+@needs_ref
+@pytest.mark.parametrize("case", MEDIUM, ids=cs.case_id)
+def test_medium_cases_bit_exact(case):
+    fp, sw, sh, nw, nh, ch, ti, to, rb, kw = case
+    src = cs.make_input(case, seed=11)
+    ref = o.ref_resize(src, nw, nh, to, fpclass=fp, resbits=rb, nthreads=os.cpu_count() or 8,
+                       **cs.ref_kwargs(kw))
+    got = cs.gpu_output(case, src)
+    assert cs.count_mismatch(ref, got) == 0
+
+
+@needs_ref
+def test_generic_and_fast_kernels_agree_on_medium():
+    case = MEDIUM[0]
+    src = cs.make_input(case, seed=5)
+    a = cs.gpu_output(case, src)
+    ab.lib().avirb200_debug_force_generic(1)
+    try:
+        b = cs.gpu_output(case, src)
+    finally:
+        ab.lib().avirb200_debug_force_generic(0)
+    assert cs.count_mismatch(a, b) == 0
+
+
+# ---- BASELINE.json full sizes ----------------------------------------------------------------
+
+def _device_run(case, src, sharded_local=0):
+    """Device-resident call through the C ABI with torch-managed buffers."""
+    import torch
+    fp, sw, sh, nw, nh, ch, ti, to, rb, kw = case
+    rs, v = cs.resizer_and_vars(case)
+    tmap = {np.uint8: torch.uint8, np.uint16: torch.uint16, np.float32: torch.float32}
+    d_src = torch.from_numpy(src).cuda()
+    d_dst = torch.empty((nh, nw, ch), dtype=tmap[to], device="cuda")
+    ws = rs.workspaceBytes(src.shape, ti, nw, nh, to, kw.get("k", 0.0), v)
+    d_ws = torch.empty(ws, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    rs.resizeImageDevice(d_src.data_ptr(), src.shape, ti, d_dst.data_ptr(), nw, nh, to,
+                         d_ws.data_ptr(), kw.get("k", 0.0), v, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    return d_dst.cpu().numpy()
+
+
+FULL = [
+    ("cfg2", (1, 1920, 1080, 3840, 2160, 4, np.uint8, np.uint8, 8, {})),
+    ("cfg3-dil", (2, 7680, 4320, 3840, 2160, 4, np.float32, np.float32, 16, {})),
+    ("cfg3-f4", (1, 7680, 4320, 3840, 2160, 4, np.float32, np.float32, 16, {})),
+    ("cfg5", (2, 7680, 4320, 1920, 1080, 4, np.uint8, np.uint8, 8, {"gamma": True, "alpha": 3})),
+]
+
+
+@needs_ref
+@pytest.mark.parametrize("name,case", FULL, ids=[f[0] for f in FULL])
+def test_full_size_baseline_configs_bit_exact(name, case):
+    """BASELINE.json configs at full size, device-resident path, vs multi-threaded upstream."""
+    fp, sw, sh, nw, nh, ch, ti, to, rb, kw = case
+    src = o.lcg_image(sh, sw, ch, ti, seed=12345)
+    ref = o.ref_resize(src, nw, nh, to, fpclass=fp, resbits=rb, nthreads=os.cpu_count() or 8,
+                       **cs.ref_kwargs(kw))
+    got = _device_run(case, src)
+    assert cs.count_mismatch(ref, got) == 0
+
+
+def test_full_size_properties_cfg4():
+    """16384^2 -> 4096^2 u16 (cfg4) is too slow for the CPU oracle in a test; check
+    size-independent properties instead: a constant image stays constant (unity DC gain of
+    the whole chain incl. edges), and the sharded schedule reproduces the unsharded bits."""
+    import torch
+    case = (1, 16384, 4096, 4096, 1024, 4, np.uint16, np.uint16, 16, {})  # quarter height
+    fp, sw, sh, nw, nh, ch, ti, to, rb, kw = case
+    const = np.full((sh, sw, ch), 40000, np.uint16)
+    out = _device_run(case, const)
+    assert out.min() == 40000 and out.max() == 40000
+    src = o.lcg_image(sh, sw, ch, ti, seed=99)
+    whole = _device_run(case, src)
+    # sharded-local: 8 bands on one device, halo rows moved by device copies
+    rs, v = cs.resizer_and_vars(case)
+    h, dp, _ = rs.descriptor(src.shape, ti, nw, nh, to, 0.0, v)
+    lib = ab.lib()
+    plan = C.c_void_p()
+    assert lib.avirb200_plan_create(C.c_void_p(dp), C.byref(plan)) == 0
+    total = 0
+    for r in range(8):
+        b = C.c_size_t()
+        assert lib.avirb200_shard_workspace_bytes(plan, r, 8, C.byref(b)) == 0
+        total += b.value
+    d_src = torch.from_numpy(src).cuda()
+    d_dst = torch.empty((nh, nw, ch), dtype=torch.uint16, device="cuda")
+    d_ws = torch.empty(total, dtype=torch.uint8, device="cuda")
+    lib.avirb200_resize_sharded_local.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t,
+                                                  C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
+    assert lib.avirb200_resize_sharded_local(plan, 8, d_src.data_ptr(), sw * ch, d_dst.data_ptr(),
+                                             nw * ch, d_ws.data_ptr(), None) == 0
+    torch.cuda.synchronize()
+    lib.avirb200_plan_destroy(plan)
+    rs.free_descriptor(h)
+    assert cs.count_mismatch(whole, d_dst.cpu().numpy()) == 0
+
+
+@needs_ref
+@pytest.mark.parametrize("nranks", [2, 5, 8])
+def test_sharded_local_matches_unsharded(nranks):
+    import torch
+    case = (2, 640, 720, 320, 360, 4, np.float32, np.float32, 16, {})
+    fp, sw, sh, nw, nh, ch, ti, to, rb, kw = case
+    src = cs.make_input(case, seed=21)
+    ref = cs.ref_output(case, src)
+    rs, v = cs.resizer_and_vars(case)
+    h, dp, _ = rs.descriptor(src.shape, ti, nw, nh, to, 0.0, v)
+    lib = ab.lib()
+    plan = C.c_void_p()
+    assert lib.avirb200_plan_create(C.c_void_p(dp), C.byref(plan)) == 0
+    total = 0
+    for r in range(nranks):
+        b = C.c_size_t()
+        assert lib.avirb200_shard_workspace_bytes(plan, r, nranks, C.byref(b)) == 0
+        total += b.value
+    d_src = torch.from_numpy(src).cuda()
+    d_dst = torch.zeros((nh, nw, ch), dtype=torch.float32, device="cuda")
+    d_ws = torch.empty(total, dtype=torch.uint8, device="cuda")
+    lib.avirb200_resize_sharded_local.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t,
+                                                  C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
+    assert lib.avirb200_resize_sharded_local(plan, nranks, d_src.data_ptr(), sw * ch,
+                                             d_dst.data_ptr(), nw * ch, d_ws.data_ptr(), None) == 0
+    torch.cuda.synchronize()
+    lib.avirb200_plan_destroy(plan)
+    rs.free_descriptor(h)
+    assert cs.count_mismatch(ref, d_dst.cpu().numpy()) == 0
+
+
+# ---- LANCIR ---------------------------------------------------------------------------------
+
+LANCIR = [
+    (96, 54, 48, 27, np.uint8, np.uint8, {}),
+    (64, 48, 103, 77, np.uint8, np.uint8, {}),
+    (64, 64, 16, 16, np.uint16, np.uint16, {}),
+    (60, 40, 40, 27, np.uint8, np.uint16, {}),
+    (50, 30, 33, 17, np.float32, np.float32, {}),
+    (50, 30, 33, 17, np.float32, np.uint8, {}),
+    (50, 30, 70, 45, np.uint8, np.float32, {"kx": 0.7, "ky": -0.66, "ox": 0.25, "oy": 0.1}),
+    (640, 480, 1024, 768, np.uint8, np.uint8, {}),       # BASELINE cfg1 geometry (RGBA)
+    (1920, 1080, 960, 540, np.uint8, np.uint8, {}),
+]
+
+
+@pytest.mark.parametrize("sw,sh,nw,nh,ti,to,kw", LANCIR)
+def test_lancir_bit_exact(sw, sh, nw, nh, ti, to, kw):
+    src = o.lcg_image(sh, sw, 4, ti, seed=3)
+    if o.have_ref():
+        r, ref = o.lancir_ref(src, nw, nh, to, **kw)
+        assert r == nh
+    else:
+        pytest.skip("needs oracle/_ref")
+    r, got = ab.CLancIR().resizeImage(src, nw, nh, ab.CLancIRParams(**kw), out_dtype=to)
+    assert r == nh
+    assert cs.count_mismatch(ref, got) == 0
+
+
+def test_lancir_golden_fixtures():
+    files = sorted(f for f in os.listdir(cs.GOLDEN) if f.startswith("lancir_"))
+    assert files
+    for f in files:
+        z = np.load(os.path.join(cs.GOLDEN, f))
+        sw, sh, nw, nh = [int(v) for v in z["geom"]]
+        r, got = ab.CLancIR().resizeImage(z["src"], nw, nh, out_dtype=z["out"].dtype)
+        assert r == nh and cs.count_mismatch(z["out"], got) == 0, f
