@@ -69,7 +69,8 @@ def test_zero_size_conventions():
     rs = ab.CImageResizer(8, 0, 0, ab.FP_FLOAT4)
     dst = np.full((4, 4, 4), 7, np.uint8)
     out = rs.resizeImage(np.zeros((0, 0, 4), np.uint8).reshape(0, 0, 4), 4, 4, NewBuf=dst)
-    assert np.all(out == 0)
+    # upstream clears NewWidth*NewHeight ELEMENTS (not pixels): avir.h:4688-4689
+    assert np.all(out.ravel()[:16] == 0) and np.all(out.ravel()[16:] == 7)
 
 
 # ---- medium sizes: many tiles per pass, multi-threaded upstream as the oracle --------------
