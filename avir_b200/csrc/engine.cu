@@ -301,10 +301,9 @@ int run_row_pass(const avirb200_plan* pl, const void* d_src, size_t src_pitch, f
     if (rows <= 0) return 0;
     const avirb200_plan_desc& d = pl->desc;
     if (env_fast_enabled() && !g_force_generic && pl->fast.h_ok) {
-        int r = fast_row_pass(pl->fast, pl->h.dev, d, d_src, src_pitch, d_mid, rows, pl->d_lut, st);
-        if (r != 0) return fail(AVIRB200_ERR_CUDA, "fast row pass launch failed");
-        ++*launches;
-        return 0;
+        const int r = fast_row_pass(pl->fast, d, d_src, src_pitch, d_mid, rows, pl->d_lut, st);
+        if (r == -1) return fail(AVIRB200_ERR_CUDA, "fast row pass launch failed");
+        if (r == 0) { ++*launches; return 0; }
     }
     PassParams p;
     std::memset(&p, 0, sizeof p);
@@ -333,11 +332,10 @@ int run_col_pass(const avirb200_plan* pl, const float* d_mid, int mid_row_base, 
     if (out1 <= out0) return 0;
     const avirb200_plan_desc& d = pl->desc;
     if (env_fast_enabled() && !g_force_generic && pl->fast.v_ok) {
-        int r = fast_col_pass(pl->fast, pl->v.dev, d, d_mid, mid_row_base, d_dst, dst_pitch, out0,
-                              out1, st);
-        if (r != 0) return fail(AVIRB200_ERR_CUDA, "fast column pass launch failed");
-        ++*launches;
-        return 0;
+        const int r = fast_col_pass(pl->fast, d, d_mid, mid_row_base, d_dst, dst_pitch, out0, out1,
+                                    pl->d_lut, st);
+        if (r == -1) return fail(AVIRB200_ERR_CUDA, "fast column pass launch failed");
+        if (r == 0) { ++*launches; return 0; }
     }
     PassParams p;
     std::memset(&p, 0, sizeof p);
@@ -552,7 +550,7 @@ int avirb200_plan_create(const avirb200_plan_desc* desc, avirb200_plan** out) {
 
     pl->cfg_h = choose_generic_config(pl->h.hostdev, desc->channels, 0, desc->dst_w);
     pl->cfg_v = choose_generic_config(pl->v.hostdev, desc->channels, 0, desc->dst_h);
-    fast_plan_init(pl->fast, pl->h.hostdev, pl->v.hostdev, pl->h.dev, pl->v.dev, *desc);
+    fast_plan_init(pl->fast, pl->h.hostdev, pl->v.hostdev, *desc);
     *out = pl.release();
     return 0;
 }
