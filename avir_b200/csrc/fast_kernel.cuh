@@ -1,0 +1,599 @@
+// fast_kernel.cuh -- specialised pass kernel for 4-channel images (sm_100a), device side.
+//
+// Same job as generic_pass.cuh (one kernel = one whole 1-D filtering chain for a tile of
+// lines, every intermediate in shared memory) with the structure the FP32 pipe needs to be
+// the limiter, because the bit-exact contract forbids FMA: each tap costs a separate
+// multiply and add, so every other instruction in the inner loops competes for issue slots.
+//
+//   * lane = one channel PAIR (float2) of one line; a warp = the 32 lanes (16 lines) of ONE
+//     position, so positions/taps/phases are warp-uniform: no divergence, tap reads are
+//     shared-memory broadcasts, input reads are conflict-free 256-byte rows;
+//   * register blocking: a thread produces 4 consecutive outputs from one register window
+//     of inputs (window loads amortised over 4 x taps products) -- fully unrolled templates
+//     for the chains of the BASELINE configs, plain loops for everything else; the variant
+//     is dispatched once per step per warp, not per output;
+//   * order-1 interpolation taps c0 + c1*x are row/column-invariant: they are formed once on
+//     the host (same two float operations upstream performs) into an "effective phase"
+//     table, so the kernels always run order-0 arithmetic;
+//   * edge replication is materialised: a tile covers the UNCLAMPED index range its
+//     consumer reads, out-of-domain positions hold the clamped sample, so inner loops
+//     carry no index clamps;
+//   * the source tile is staged with cp.async (16-byte LDGSTS, no register round trip, all
+//     of a thread's copies in flight at once) while the tap rows of every step are staged
+//     alongside.
+//
+// Arithmetic order is upstream's (see generic_pass.cuh / oracle/avir_port.c); tests run
+// every case through both kernels.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "device_plan.h"
+#include "generic_pass.cuh"
+
+namespace avb {
+
+constexpr int kFastLanes = 32;      // lane pairs per position = 16 lines x 2
+constexpr int kFastLines = 16;
+constexpr int kFastThreads = 256;
+constexpr int kFastWarps = kFastThreads / 32;
+constexpr int kFastMaxSteps = 4;
+constexpr int kFastPitch = kFastLanes + 2; // float2 units: 272 bytes (16-byte aligned rows)
+
+enum FastVariant : int {
+    kVarSimple = 0,
+    kVarResizeDil24D2,   // float8_dil, FL 24, source step 2            (cfg3 mirror dil)
+    kVarResizeDil56D4,   // float8_dil, FL 56, source step 4            (cfg5)
+    kVarResizeDil32D2,
+    kVarResizeInl18D2,   // interleaved, FL 18, source step 2           (cfg3 float4, cfg4)
+    kVarResizeInl24D2,
+    kVarFirDil8R1,       // float8_dil 8-tap (7 + pad) correction       (cfg3/cfg5 dil)
+    kVarFirInl7R1,       // interleaved 7-tap (L = 3), R = 1            (LPF k=2, correction)
+    kVarFirInl15R2,      // interleaved 15-tap (L = 7), R = 2           (cfg4 decimator)
+};
+
+struct FastStep {
+    int kind, variant;
+    int resample, latency, edge, ntaps, ntaps_pad;
+    int out_len;
+    int in_lo, in_hi;    // valid domain of the input line
+    int upsampled, skip_odd, zero_start;
+    const float* taps;   // FIR: ntaps floats; RESIZE: [n_eff][ntaps_pad]
+    const int* src_pos;  // RESIZE
+    const int* eff;      // RESIZE: per-output row of `taps`
+};
+
+struct FastAxis {
+    int nsteps, src_len, dst_len;
+    FastStep s[kFastMaxSteps];
+};
+
+struct FastParams {
+    FastAxis ax;
+    int is_v;
+    int n_lines;          // rows (H) or pixel columns (V) in this launch
+    int tile_out;
+    int out0, out1;
+    int span_a, span_b;   // shared rows of the two ping-pong buffers
+    int tap_off[kFastMaxSteps]; // float offset of each step's staged taps
+    const int* tile_ranges;     // per tile: (a, b) of the source tile and of every step's output
+    const void* src;
+    long long src_pitch;  // elements
+    int src_type;
+    int src_row_base;
+    void* dst;
+    long long dst_pitch;
+    int dst_type;
+    int dst_row_base;
+    int gamma_in, gamma_out, alpha_index;
+    float in_gamma_mult, out_gamma_mult;
+    const float* srgb_lut;
+    int round_mode;
+    float tr_mul, tr_mul_inv, pk_out;
+};
+
+// ---- host+device range arithmetic (unclamped: tiles materialise edge replicas) ----------------
+
+AVB_HD Range fast_input_range(const FastStep& s, Range o, const int* src_pos) {
+    // o must lie inside the step's output domain
+    Range r;
+    if (s.kind == AVIRB200_STEP_FIR) {
+        r.a = (o.a - s.edge) * s.resample - s.latency;
+        r.b = (o.b - s.edge) * s.resample - s.latency + s.ntaps - 1;
+    } else {
+        const int d21 = s.ntaps / 2 - 1;
+        r.a = src_pos[o.a] - d21;
+        r.b = src_pos[o.b] - d21 + s.ntaps - 1;
+        if (s.upsampled) {
+            r.a >>= 1;
+            r.b >>= 1;
+        }
+    }
+    return r;
+}
+
+AVB_HD Range clampr(Range r, int lo, int hi) {
+    Range c;
+    c.a = imin(imax(r.a, lo), hi - 1);
+    c.b = imin(imax(r.b, lo), hi - 1);
+    return c;
+}
+
+#if defined(__CUDACC__)
+
+// ---- small device helpers ------------------------------------------------------------------------
+
+__device__ __forceinline__ float2 f2mul(float t, float2 x) {
+    return make_float2(__fmul_rn(t, x.x), __fmul_rn(t, x.y));
+}
+__device__ __forceinline__ float2 f2add(float2 a, float2 b) {
+    return make_float2(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y));
+}
+__device__ __forceinline__ float2 f2hadd8(const float2* v) {
+    return f2add(f2add(f2add(v[0], v[4]), f2add(v[1], v[5])),
+                 f2add(f2add(v[2], v[6]), f2add(v[3], v[7])));
+}
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
+
+// Output stage for one element (gamma -> round -> clamp), 4-channel images.
+__device__ __forceinline__ float epilogue_value_c4(const FastParams& p, float v, int c) {
+    if (p.gamma_out) {
+        if (c == p.alpha_index) v = __fmul_rn(v, p.out_gamma_mult);
+        else v = __fmul_rn(lin2srgb(v), p.out_gamma_mult);
+    }
+    if (p.dst_type != AVIRB200_F32) {
+        if (p.tr_mul == 1.0f) v = round_out(v, p.round_mode);
+        else v = __fmul_rn(round_out(__fmul_rn(v, p.tr_mul_inv), p.round_mode), p.tr_mul);
+        v = v < 0.0f ? 0.0f : (v > p.pk_out ? p.pk_out : v);
+    }
+    return v;
+}
+
+// ---- blocked step routines: M outputs from one register window ----------------------------------
+// `x0` points at the thread's lane in the row of the first input position of output 0; rows
+// are kFastPitch float2 apart.  `tp` = staged taps of output 0 (FLP floats per output).
+
+template <int SUM, int FL, int FLP, int D, int M>
+__device__ __forceinline__ void resize_blocked(const float2* x0, const float* tp, int zero_start,
+                                               float2* out) {
+    constexpr int W = FL + (M - 1) * D;
+    float2 x[W];
+#pragma unroll
+    for (int w = 0; w < W; ++w) x[w] = x0[w * kFastPitch];
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+        const float* t = tp + m * FLP;
+        float2 r;
+        if (SUM == AVIRB200_SUM_DIL8) {
+            float2 ln[8];
+#pragma unroll
+            for (int g = 0; g < FL / 8; ++g) {
+                const float4 ta = *reinterpret_cast<const float4*>(t + g * 8);
+                const float4 tb = *reinterpret_cast<const float4*>(t + g * 8 + 4);
+                const float tt[8] = {ta.x, ta.y, ta.z, ta.w, tb.x, tb.y, tb.z, tb.w};
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const float2 v = f2mul(tt[q], x[m * D + g * 8 + q]);
+                    ln[q] = (g == 0) ? v : f2add(ln[q], v);
+                }
+            }
+            r = f2hadd8(ln);
+        } else {
+#pragma unroll
+            for (int i = 0; i < FL; i += 2) {
+                const float2 t2 = *reinterpret_cast<const float2*>(t + i);
+                const float2 v0 = f2mul(t2.x, x[m * D + i]);
+                r = (i == 0) ? v0 : f2add(r, v0);
+                r = f2add(r, f2mul(t2.y, x[m * D + i + 1]));
+            }
+        }
+        if (zero_start) r = f2add(r, make_float2(0.0f, 0.0f));
+        out[m] = r;
+    }
+}
+
+// De-interleaved RESIZE with long filters: group-major so that only 8 + (M-1)*D inputs and
+// M x 8 lane accumulators are live at a time (a full register window would not fit).
+template <int FL, int FLP, int D, int M>
+__device__ __forceinline__ void resize_dil_groupmajor(const float2* x0, const float* tp,
+                                                      int zero_start, float2* out) {
+    constexpr int W = 8 + (M - 1) * D;
+    float2 ln[M][8];
+#pragma unroll
+    for (int g = 0; g < FL / 8; ++g) {
+        float2 x[W];
+#pragma unroll
+        for (int w = 0; w < W; ++w) x[w] = x0[(g * 8 + w) * kFastPitch];
+#pragma unroll
+        for (int m = 0; m < M; ++m) {
+            const float* t = tp + m * FLP + g * 8;
+            const float4 ta = *reinterpret_cast<const float4*>(t);
+            const float4 tb = *reinterpret_cast<const float4*>(t + 4);
+            const float tt[8] = {ta.x, ta.y, ta.z, ta.w, tb.x, tb.y, tb.z, tb.w};
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const float2 v = f2mul(tt[q], x[m * D + q]);
+                ln[m][q] = (g == 0) ? v : f2add(ln[m][q], v);
+            }
+        }
+    }
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+        float2 r = f2hadd8(ln[m]);
+        if (zero_start) r = f2add(r, make_float2(0.0f, 0.0f));
+        out[m] = r;
+    }
+}
+
+// FIR.  INL: folded symmetric form around the centre tap; DIL: full padded filter.
+// `tt` = the NT taps in registers.
+template <int SUM, int NT, int R, int M>
+__device__ __forceinline__ void fir_blocked(const float2* x0, const float* tt, float2* out) {
+    constexpr int W = NT + (M - 1) * R;
+    float2 x[W];
+#pragma unroll
+    for (int w = 0; w < W; ++w) x[w] = x0[w * kFastPitch];
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+        if (SUM == AVIRB200_SUM_DIL8) {
+            float2 ln[8];
+#pragma unroll
+            for (int g = 0; g < NT / 8; ++g) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const float2 v = f2mul(tt[g * 8 + q], x[m * R + g * 8 + q]);
+                    ln[q] = (g == 0) ? v : f2add(ln[q], v);
+                }
+            }
+            out[m] = f2hadd8(ln);
+        } else {
+            constexpr int L = NT / 2;
+            float2 s = f2mul(tt[L], x[m * R + L]);
+#pragma unroll
+            for (int i = 1; i <= L; ++i)
+                s = f2add(s, f2mul(tt[L + i], f2add(x[m * R + L + i], x[m * R + L - i])));
+            out[m] = s;
+        }
+    }
+}
+
+// ---- plain-loop step routine: any geometry, one output ------------------------------------------
+// `xb` = the thread's lane in the row of input position 0 of the tile-relative frame, i.e.
+// xb[(n - tile_a) * kFastPitch] is sample n.
+
+template <int SUM>
+__device__ float2 step_simple(const FastStep& s, const float2* xb, int tile_a, int j, const float* tp) {
+    if (s.kind == AVIRB200_STEP_FIR) {
+        if (SUM == AVIRB200_SUM_INL) {
+            const int L = s.latency;
+            const float2* c = xb + ((j - s.edge) * s.resample - tile_a) * kFastPitch;
+            float2 sum = f2mul(tp[L], c[0]);
+            for (int i = 1; i <= L; ++i)
+                sum = f2add(sum, f2mul(tp[L + i], f2add(c[i * kFastPitch], c[-i * kFastPitch])));
+            return sum;
+        }
+        const float2* c = xb + ((j - s.edge) * s.resample - s.latency - tile_a) * kFastPitch;
+        float2 ln[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) ln[q] = f2mul(tp[q], c[q * kFastPitch]);
+        for (int i = 8; i < s.ntaps; i += 8) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) ln[q] = f2add(ln[q], f2mul(tp[i + q], c[(i + q) * kFastPitch]));
+        }
+        return f2hadd8(ln);
+    }
+    const int FL = s.ntaps;
+    const int p = __ldg(s.src_pos + j) - (FL / 2 - 1);
+    float2 r = make_float2(0.0f, 0.0f);
+    if (SUM == AVIRB200_SUM_INL) {
+        bool first = true;
+        if (s.upsampled) {
+            // only even virtual positions hold samples; upstream's doResize2 skips the rest
+            for (int i = (p & 1); i < FL; i += 2) {
+                const float2 v = f2mul(tp[i], xb[(((p + i) >> 1) - tile_a) * kFastPitch]);
+                r = first ? v : f2add(r, v);
+                first = false;
+            }
+        } else {
+            const float2* c = xb + (p - tile_a) * kFastPitch;
+            for (int i = 0; i < FL; ++i) {
+                const float2 v = f2mul(tp[i], c[i * kFastPitch]);
+                r = first ? v : f2add(r, v);
+                first = false;
+            }
+        }
+    } else {
+        const float2* c = xb + (p - tile_a) * kFastPitch;
+        float2 ln[8];
+        for (int i = 0; i < FL; i += 8) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const float2 v = f2mul(tp[i + q], c[(i + q) * kFastPitch]);
+                ln[q] = (i == 0) ? v : f2add(ln[q], v);
+            }
+        }
+        r = f2hadd8(ln);
+    }
+    if (s.zero_start) r = f2add(r, make_float2(0.0f, 0.0f));
+    return r;
+}
+
+// ---- where a step's outputs go -----------------------------------------------------------------------
+
+struct Sink {
+    float2* ob;          // shared tile of the step's output: row (j - oa), this thread's lane
+    int oa;
+    bool to_global;      // last step of the column pass: epilogue + store to the image
+    unsigned char* gp;   // image element (dst row 0, this thread's pixel/channel pair)
+    size_t grow;         // bytes between image rows
+    int grow_base;       // dst_row_base
+    bool gok;
+};
+
+__device__ __forceinline__ void sink_store(const FastParams& p, const Sink& k, int j, float2 v, int c0) {
+    if (!k.to_global) {
+        k.ob[(j - k.oa) * kFastPitch] = v;
+        return;
+    }
+    v.x = epilogue_value_c4(p, v.x, c0);
+    v.y = epilogue_value_c4(p, v.y, c0 + 1);
+    if (!k.gok) return;
+    unsigned char* g = k.gp + (size_t)(j - k.grow_base) * k.grow;
+    if (p.dst_type == AVIRB200_F32) *reinterpret_cast<float2*>(g) = v;
+    else if (p.dst_type == AVIRB200_U8)
+        *reinterpret_cast<uchar2*>(g) = make_uchar2((unsigned char)v.x, (unsigned char)v.y);
+    else
+        *reinterpret_cast<ushort2*>(g) = make_ushort2((unsigned short)v.x, (unsigned short)v.y);
+}
+
+// ---- one step for one warp ------------------------------------------------------------------------------
+
+template <int SUM>
+__device__ __forceinline__ void run_step(const FastParams& p, const FastStep& s, const float2* xb,
+                                         int tile_a, const Range out, const Range dom,
+                                         const float* stp, const Sink& k, int warp, int c0) {
+    // balanced split of the tile's outputs over the warps, in units of 4
+    const int on = out.b - out.a + 1;
+    const int units = (on + 3) >> 2;
+    const int jb = out.a + 4 * ((units * warp) / kFastWarps);
+    const int je = imin(out.a + 4 * ((units * (warp + 1)) / kFastWarps), out.a + on);
+    if (jb >= je) return;
+
+    // region [bl, bh) the blocked routine may cover: in-domain, whole quads, right geometry
+    int bl = imax(jb, dom.a), bh = imin(je, dom.b + 1);
+    int nq = 0, p0 = 0, D = 0;
+    if (s.variant != kVarSimple && bh - bl >= 4) {
+        nq = (bh - bl) >> 2;
+        if (s.kind == AVIRB200_STEP_RESIZE) {
+            D = (s.variant == kVarResizeDil56D4) ? 4 : 2;
+            const int last = bl + 4 * nq - 1;
+            const int spl = __ldg(s.src_pos + bl), sph = __ldg(s.src_pos + last);
+            if (sph - spl != D * (last - bl)) nq = 0; // not the uniform spacing the template assumes
+            p0 = spl - (s.ntaps / 2 - 1);
+        } else {
+            D = s.resample;
+            p0 = (bl - s.edge) * s.resample - s.latency; // first input of output bl (both forms)
+        }
+    }
+    const float* tp_of_dom = stp; // RESIZE: row (j - dom.a); FIR: the filter itself
+
+    auto simple_one = [&](int j) {
+        const int jj = imin(imax(j, dom.a), dom.b); // edge replica: value of the clamped output
+        const float* tp = (s.kind == AVIRB200_STEP_FIR) ? stp : stp + (size_t)(jj - dom.a) * s.ntaps_pad;
+        sink_store(p, k, j, step_simple<SUM>(s, xb, tile_a, jj, tp), c0);
+    };
+
+    int j = jb;
+    const int head_end = (nq > 0) ? bl : je;
+    for (; j < head_end; ++j) simple_one(j);
+    if (nq > 0) {
+        const float2* x0 = xb + (p0 - tile_a) * kFastPitch;
+        const float* tp = tp_of_dom + (size_t)(bl - dom.a) * s.ntaps_pad;
+        float2 o4[4];
+#define AVB_QUAD_LOOP(CALL, XSTEP, TSTEP)                                           \
+    for (int q = 0; q < nq; ++q) {                                                  \
+        CALL;                                                                       \
+        _Pragma("unroll") for (int m = 0; m < 4; ++m) sink_store(p, k, j + m, o4[m], c0); \
+        j += 4;                                                                     \
+        x0 += (XSTEP) * kFastPitch;                                                 \
+        tp += (TSTEP);                                                              \
+    }
+        switch (s.variant) {
+        case kVarResizeDil24D2:
+            AVB_QUAD_LOOP((resize_blocked<AVIRB200_SUM_DIL8, 24, 24, 2, 4>(x0, tp, s.zero_start, o4)), 8, 4 * 24)
+            break;
+        case kVarResizeDil32D2:
+            AVB_QUAD_LOOP((resize_blocked<AVIRB200_SUM_DIL8, 32, 32, 2, 4>(x0, tp, s.zero_start, o4)), 8, 4 * 32)
+            break;
+        case kVarResizeInl18D2:
+            AVB_QUAD_LOOP((resize_blocked<AVIRB200_SUM_INL, 18, 20, 2, 4>(x0, tp, s.zero_start, o4)), 8, 4 * 20)
+            break;
+        case kVarResizeInl24D2:
+            AVB_QUAD_LOOP((resize_blocked<AVIRB200_SUM_INL, 24, 24, 2, 4>(x0, tp, s.zero_start, o4)), 8, 4 * 24)
+            break;
+        case kVarResizeDil56D4:
+            AVB_QUAD_LOOP((resize_dil_groupmajor<56, 56, 4, 2>(x0, tp, s.zero_start, o4),
+                           resize_dil_groupmajor<56, 56, 4, 2>(x0 + 8 * kFastPitch, tp + 2 * 56, s.zero_start, o4 + 2)),
+                          16, 4 * 56)
+            break;
+        case kVarFirDil8R1: {
+            float tt[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) tt[i] = stp[i];
+            AVB_QUAD_LOOP((fir_blocked<AVIRB200_SUM_DIL8, 8, 1, 4>(x0, tt, o4)), 4, 0)
+            break;
+        }
+        case kVarFirInl7R1: {
+            float tt[7];
+#pragma unroll
+            for (int i = 0; i < 7; ++i) tt[i] = stp[i];
+            AVB_QUAD_LOOP((fir_blocked<AVIRB200_SUM_INL, 7, 1, 4>(x0, tt, o4)), 4, 0)
+            break;
+        }
+        case kVarFirInl15R2: {
+            float tt[15];
+#pragma unroll
+            for (int i = 0; i < 15; ++i) tt[i] = stp[i];
+            AVB_QUAD_LOOP((fir_blocked<AVIRB200_SUM_INL, 15, 2, 4>(x0, tt, o4)), 8, 0)
+            break;
+        }
+        default:
+            break;
+        }
+#undef AVB_QUAD_LOOP
+        for (; j < je; ++j) simple_one(j);
+    }
+}
+
+// ---- the kernel ------------------------------------------------------------------------------------------
+
+template <int SUM>
+__global__ void __launch_bounds__(kFastThreads, 2)
+fast_pass_kernel(const __grid_constant__ FastParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* bufA = reinterpret_cast<float2*>(smem_raw);
+    float2* bufB = bufA + (size_t)p.span_a * kFastPitch;
+    float* stap = reinterpret_cast<float*>(bufB + (size_t)p.span_b * kFastPitch);
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    const int line0 = blockIdx.y * kFastLines;
+    const int nlines = imin(kFastLines, p.n_lines - line0);
+    const int j0 = p.out0 + blockIdx.x * p.tile_out;
+    const int j1 = imin(j0 + p.tile_out, p.out1) - 1;
+    const int ns = p.ax.nsteps;
+
+    // rng[i] = unclamped positions of step i's INPUT held in shared memory; rng[ns] = outputs
+    // The host tabulated them per tile (kFastMaxSteps + 1 ranges = 10 ints per tile), so a
+    // block starts with one uniform load instead of a dependent chain of position look-ups.
+    const int* tr = p.tile_ranges + (size_t)blockIdx.x * (2 * (kFastMaxSteps + 1));
+    auto rng = [&](int i) { return Range{__ldg(tr + 2 * i), __ldg(tr + 2 * i + 1)}; };
+
+    // ---- stage the source tile (edge replicas materialised)
+    {
+        const Range r0g = rng(0);
+        const int a = r0g.a, n = r0g.b - r0g.a + 1;
+        if (p.is_v) {
+            // a "line" is a pixel column; 16 pixels = 64 contiguous floats of a row
+            const float* src = static_cast<const float*>(p.src);
+            const int q = imin(tid & 15, nlines - 1); // pixel within the strip (float4)
+            const int r0 = tid >> 4;                  // 16 rows per sweep
+            for (int pos = r0; pos < n; pos += kFastThreads / 16) {
+                const int y = imin(imax(a + pos, 0), p.ax.src_len - 1) - p.src_row_base;
+                cp_async16(bufA + pos * kFastPitch + (tid & 15) * 2,
+                           reinterpret_cast<const float4*>(src + (size_t)y * p.src_pitch) + line0 + q);
+            }
+        } else {
+            const int px = tid & 31; // 32 consecutive positions per sweep
+            const int r0 = tid >> 5; // 8 rows per sweep
+#pragma unroll
+            for (int rr = 0; rr < kFastLines / (kFastThreads / 32); ++rr) {
+                const int r = r0 + rr * (kFastThreads / 32);
+                const size_t rowoff = (size_t)(line0 + imin(r, nlines - 1)) * p.src_pitch;
+                if (p.src_type == AVIRB200_F32) {
+                    const float4* srow = reinterpret_cast<const float4*>(static_cast<const float*>(p.src) + rowoff);
+                    for (int pos = px; pos < n; pos += 32) {
+                        const int x = imin(imax(a + pos, 0), p.ax.src_len - 1);
+                        cp_async16(bufA + pos * kFastPitch + r * 2, srow + x);
+                    }
+                } else {
+                    for (int pos = px; pos < n; pos += 32) {
+                        const int x = imin(imax(a + pos, 0), p.ax.src_len - 1);
+                        float4 v;
+                        if (p.src_type == AVIRB200_U8) {
+                            const uchar4 b = __ldg(reinterpret_cast<const uchar4*>(static_cast<const unsigned char*>(p.src) + rowoff) + x);
+                            v = make_float4((float)b.x, (float)b.y, (float)b.z, (float)b.w);
+                            if (p.gamma_in) {
+                                const int ai = p.alpha_index;
+                                v.x = (ai == 0) ? __fmul_rn(v.x, p.in_gamma_mult) : p.srgb_lut[b.x];
+                                v.y = p.srgb_lut[b.y];
+                                v.z = p.srgb_lut[b.z];
+                                v.w = (ai == 3) ? __fmul_rn(v.w, p.in_gamma_mult) : p.srgb_lut[b.w];
+                            }
+                        } else {
+                            const ushort4 b = __ldg(reinterpret_cast<const ushort4*>(static_cast<const unsigned short*>(p.src) + rowoff) + x);
+                            v = make_float4((float)b.x, (float)b.y, (float)b.z, (float)b.w);
+                            if (p.gamma_in) {
+                                const int ai = p.alpha_index;
+                                v.x = (ai == 0) ? __fmul_rn(v.x, p.in_gamma_mult) : srgb2lin(v.x, p.in_gamma_mult);
+                                v.y = srgb2lin(v.y, p.in_gamma_mult);
+                                v.z = srgb2lin(v.z, p.in_gamma_mult);
+                                v.w = (ai == 3) ? __fmul_rn(v.w, p.in_gamma_mult) : srgb2lin(v.w, p.in_gamma_mult);
+                            }
+                        }
+                        *reinterpret_cast<float4*>(bufA + pos * kFastPitch + r * 2) = v;
+                    }
+                }
+            }
+        }
+    }
+
+    // ---- stage the taps of every step while the source tile is in flight
+    for (int i = 0; i < ns; ++i) {
+        const FastStep& s = p.ax.s[i];
+        float* st = stap + p.tap_off[i];
+        if (s.kind == AVIRB200_STEP_FIR) {
+            for (int t = tid; t < s.ntaps; t += kFastThreads) st[t] = __ldg(s.taps + t);
+        } else {
+            const Range dom = clampr(rng(i + 1), 0, s.out_len);
+            const int rows = dom.b - dom.a + 1;
+            const int fl4 = s.ntaps_pad >> 2;
+            for (int t = tid; t < rows * fl4; t += kFastThreads) {
+                const int rr = t / fl4, c4 = t - rr * fl4;
+                const int e = __ldg(s.eff + dom.a + rr);
+                reinterpret_cast<float4*>(st)[t] =
+                    __ldg(reinterpret_cast<const float4*>(s.taps + (size_t)e * s.ntaps_pad) + c4);
+            }
+        }
+    }
+    if (p.src_type == AVIRB200_F32) cp_async_wait_all();
+    __syncthreads();
+
+    // ---- the chain
+    const int c0 = (lane & 1) * 2; // first channel of this lane's pair
+    Sink gk;
+    gk.to_global = false;
+    gk.gok = (lane >> 1) < nlines;
+    const size_t esz = (p.dst_type == AVIRB200_F32 ? 4 : (p.dst_type == AVIRB200_U16 ? 2 : 1));
+    gk.grow = (size_t)p.dst_pitch * esz;
+    gk.grow_base = p.dst_row_base;
+    gk.gp = static_cast<unsigned char*>(p.dst) + ((size_t)(line0 + (lane >> 1)) * 4 + c0) * esz;
+    for (int i = 0; i < ns; ++i) {
+        const FastStep& s = p.ax.s[i];
+        const float2* xb = ((i & 1) ? bufB : bufA) + lane;
+        const Range ro = rng(i + 1);
+        Sink k = gk;
+        k.ob = ((i & 1) ? bufA : bufB) + lane;
+        k.oa = ro.a;
+        k.to_global = (i == ns - 1) && p.is_v;
+        run_step<SUM>(p, s, xb, __ldg(tr + 2 * i), ro, clampr(ro, 0, s.out_len),
+                      stap + p.tap_off[i], k, warp, c0);
+        __syncthreads();
+    }
+
+    if (!p.is_v) {
+        // coalesced store of the row-pass tile: [pos][row] in shared -> rows of float4 pixels
+        const float2* ob = (ns & 1) ? bufB : bufA;
+        const int oa = j0, on = j1 - j0 + 1;
+        const int px = tid & 31, r0 = tid >> 5;
+        for (int r = r0; r < nlines; r += kFastThreads / 32) {
+            float4* drow = reinterpret_cast<float4*>(static_cast<float*>(p.dst) +
+                                                     (size_t)(line0 + r) * p.dst_pitch);
+            for (int pos = px; pos < on; pos += 32)
+                drow[oa + pos] = *reinterpret_cast<const float4*>(ob + pos * kFastPitch + r * 2);
+        }
+    }
+}
+
+#endif // __CUDACC__
+
+} // namespace avb
