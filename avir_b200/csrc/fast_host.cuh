@@ -35,7 +35,12 @@ inline bool env_fast_enabled() {
     return on;
 }
 
-const size_t kFastSmemBudget = 110 * 1024; // two resident blocks per SM
+const size_t kFastSmemBudget = (227 * 1024) / kFastBlocksPerSM - 2048; // per block
+
+// A resize step all of whose outputs use effective phase 0 (the only one): integer ratios.
+inline bool hax_uniform(const FastAxis& hax, int i) {
+    return hax.s[i].kind == AVIRB200_STEP_RESIZE && hax.s[i].n_eff == 1;
+}
 
 // Shared-memory footprint of one tile [j0, j1]: rows of the two ping-pong buffers and the
 // staged taps of every step.  Accumulates maxima into `f`; returns a relative cost of the
@@ -52,7 +57,7 @@ inline double fast_tile_footprint(const FastAxis& hax, int j0, int j1, FastFootp
         if (i & 1) f.span_a = imax(f.span_a, on); else f.span_b = imax(f.span_b, on);
         const Range dom = clampr(r, 0, s.out_len);
         const int need = (s.kind == AVIRB200_STEP_FIR) ? ((s.ntaps + 3) & ~3)
-                                                       : (dom.b - dom.a + 1) * s.ntaps_pad;
+                         : (hax_uniform(hax, i) ? s.ntaps_pad : (dom.b - dom.a + 1) * s.ntaps_pad);
         tap_need[i] = imax(tap_need[i], need);
         const int quads = (on + 3) / 4;
         const int crit = 4 * ((quads + kFastWarps - 1) / kFastWarps); // outputs on the busiest warp
@@ -64,7 +69,7 @@ inline double fast_tile_footprint(const FastAxis& hax, int j0, int j1, FastFootp
     }
     const int src_rows = r.b - r.a + 1;
     f.span_a = imax(f.span_a, src_rows); // source tile in A
-    cost += src_rows * 6.0;              // staging: 16 lines x 16 bytes per row over 256 threads
+    cost += src_rows * 2.0;              // staging instructions (the copies themselves are asynchronous)
     return cost;
 }
 
@@ -131,7 +136,7 @@ inline bool fast_build_axis(FastPass& fp, const DevAxis& host, int sum_mode) {
         s.ntaps = d.ntaps; s.ntaps_pad = (d.ntaps + 3) & ~3;
         s.out_len = d.out_len; s.in_lo = d.in_lo; s.in_hi = d.in_hi;
         s.upsampled = d.upsampled; s.skip_odd = d.skip_odd; s.zero_start = d.zero_start;
-        s.taps = nullptr; s.src_pos = nullptr; s.eff = nullptr;
+        s.taps = nullptr; s.src_pos = nullptr; s.eff = nullptr; s.n_eff = 0;
         if (d.kind == AVIRB200_STEP_UPSAMPLE) return false;
         if (d.in_lo != 0) return false;
         if (d.kind == AVIRB200_STEP_FIR) {
@@ -173,6 +178,7 @@ inline bool fast_build_axis(FastPass& fp, const DevAxis& host, int sum_mode) {
                 }
                 fp.eff_idx[i][j] = it->second;
             }
+            s.n_eff = (int)seen.size();
             if (!d.upsampled) {
                 if (sum_mode == AVIRB200_SUM_DIL8 && FL == 24) s.variant = kVarResizeDil24D2;
                 if (sum_mode == AVIRB200_SUM_DIL8 && FL == 32) s.variant = kVarResizeDil32D2;
@@ -259,21 +265,35 @@ inline void fast_fill_common(FastParams& p, const avirb200_plan_desc& d, const f
     p.pk_out = d.pk_out;
 }
 
+inline int fast_sm_count() {
+    static const int sms = [] {
+        int d = 0, n = 0;
+        cudaGetDevice(&d);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d);
+        return n > 0 ? n : 1;
+    }();
+    return sms;
+}
+
+// One block per tile; blockIdx.x walks along the line.
 inline int fast_launch(const FastParams& p, size_t smem, int sum_mode, cudaStream_t st) {
     dim3 grid((p.out1 - p.out0 + p.tile_out - 1) / p.tile_out, (p.n_lines + kFastLines - 1) / kFastLines);
-    if (grid.y > 65535) return -1;
-    cudaError_t e;
+    if (grid.x == 0 || grid.y == 0) return 0;
+    if (grid.y > 65535) return -2;
+    cudaError_t e = cudaSuccess;
+#define AVB_LAUNCH(SUMM, ISV)                                                                      \
+    do {                                                                                           \
+        e = cudaFuncSetAttribute(fast_pass_kernel<SUMM, ISV>,                                      \
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);          \
+        if (e == cudaSuccess) fast_pass_kernel<SUMM, ISV><<<grid, kFastThreads, smem, st>>>(p);    \
+    } while (0)
     if (sum_mode == AVIRB200_SUM_DIL8) {
-        e = cudaFuncSetAttribute(fast_pass_kernel<AVIRB200_SUM_DIL8>,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return -1;
-        fast_pass_kernel<AVIRB200_SUM_DIL8><<<grid, kFastThreads, smem, st>>>(p);
+        if (p.is_v) AVB_LAUNCH(AVIRB200_SUM_DIL8, true); else AVB_LAUNCH(AVIRB200_SUM_DIL8, false);
     } else {
-        e = cudaFuncSetAttribute(fast_pass_kernel<AVIRB200_SUM_INL>,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return -1;
-        fast_pass_kernel<AVIRB200_SUM_INL><<<grid, kFastThreads, smem, st>>>(p);
+        if (p.is_v) AVB_LAUNCH(AVIRB200_SUM_INL, true); else AVB_LAUNCH(AVIRB200_SUM_INL, false);
     }
+#undef AVB_LAUNCH
+    if (e != cudaSuccess) return -1;
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
@@ -286,15 +306,25 @@ inline const int* fast_tile_table(const FastPass& fp, int out0, int out1) {
     if (it != fp.range_tabs.end()) return it->second;
     const int ns = fp.hax.nsteps, t = fp.tile_out;
     const int ntiles = (out1 - out0 + t - 1) / t;
-    std::vector<int> tab((size_t)ntiles * 2 * (kFastMaxSteps + 1));
+    std::vector<int> tab((size_t)ntiles * kTileRec, 0);
     for (int k = 0; k < ntiles; ++k) {
-        int* e = &tab[(size_t)k * 2 * (kFastMaxSteps + 1)];
+        int* e = &tab[(size_t)k * kTileRec];
         const int j0 = out0 + k * t, j1 = imin(j0 + t, out1) - 1;
         for (int i = 0; i <= kFastMaxSteps; ++i) { e[2 * i] = j0; e[2 * i + 1] = j1; }
         Range r{j0, j1};
         for (int i = ns - 1; i >= 0; --i) {
             const FastStep& s = fp.hax.s[i];
-            r = fast_input_range(s, clampr(r, 0, s.out_len), s.src_pos);
+            const Range dom = clampr(r, 0, s.out_len);
+            if (s.kind == AVIRB200_STEP_RESIZE) {
+                // first position and (if regular) the source step of the in-domain outputs
+                const int* sp = s.src_pos;
+                e[10 + i] = sp[dom.a];
+                int step = (dom.b > dom.a) ? sp[dom.a + 1] - sp[dom.a] : 0;
+                for (int j = dom.a + 1; j <= dom.b && step != 0; ++j)
+                    if (sp[j] - sp[j - 1] != step) step = 0;
+                e[14 + i] = step;
+            }
+            r = fast_input_range(s, dom, s.src_pos);
             e[2 * i] = r.a; e[2 * i + 1] = r.b;
         }
     }
@@ -310,7 +340,23 @@ inline const int* fast_tile_table(const FastPass& fp, int out0, int out1) {
 
 inline size_t fast_elsize(int t) { return t == AVIRB200_U8 ? 1 : (t == AVIRB200_U16 ? 2 : 4); }
 
+// Picks the (single) resize step whose one effective phase goes into the kernel parameters.
+inline void fast_set_const_taps(FastParams& p, const FastPass& fp) {
+    p.rtaps_step = -1;
+    for (int i = 0; i < fp.hax.nsteps; ++i) {
+        const FastStep& s = fp.hax.s[i];
+        if (s.kind == AVIRB200_STEP_RESIZE && s.n_eff == 1 && s.ntaps <= 64 && s.variant != kVarSimple &&
+            s.variant != kVarResizeDil56D4) {
+            p.rtaps_step = i;
+            for (int t = 0; t < s.ntaps; ++t) p.rtaps[t] = fp.eff_taps[i][t];
+            break;
+        }
+    }
+}
+
 inline void fast_set_footprint(FastParams& p, const FastFootprint& f) {
+    for (int i = 0; i < p.ax.nsteps; ++i)
+        p.uniform_taps[i] = (p.ax.s[i].kind == AVIRB200_STEP_RESIZE && p.ax.s[i].n_eff == 1) ? 1 : 0;
     p.span_a = f.span_a;
     p.span_b = f.span_b;
     for (int i = 0; i < kFastMaxSteps; ++i) p.tap_off[i] = f.tap_off[i];
@@ -332,6 +378,7 @@ inline int fast_row_pass(const FastPlan& f, const avirb200_plan_desc& d, const v
     p.tile_out = f.h.tile_out;
     p.out0 = 0; p.out1 = d.dst_w;
     fast_set_footprint(p, f.h.fpnt);
+    fast_set_const_taps(p, f.h);
     p.tile_ranges = fast_tile_table(f.h, 0, d.dst_w);
     if (p.tile_ranges == nullptr) return -1;
     p.src = d_src; p.src_pitch = (long long)src_pitch; p.src_type = d.in_type;
@@ -354,11 +401,12 @@ inline int fast_col_pass(const FastPlan& f, const avirb200_plan_desc& d, const f
     FastFootprint fpnt = f.v.fpnt;
     if (out0 != 0 || out1 != d.dst_h) { // a shard: footprint of its own tiles
         fpnt = fast_footprint_all(f.v.hax, f.v.tile_out, out0, out1);
-        if (fpnt.smem > 200 * 1024) return -2;
+        if (fpnt.smem > 220 * 1024) return -2;
     }
     p.tile_out = f.v.tile_out;
     p.out0 = out0; p.out1 = out1;
     fast_set_footprint(p, fpnt);
+    fast_set_const_taps(p, f.v);
     p.tile_ranges = fast_tile_table(f.v, out0, out1);
     if (p.tile_ranges == nullptr) return -1;
     p.src = d_mid; p.src_pitch = (long long)d.dst_w * 4; p.src_type = AVIRB200_F32;

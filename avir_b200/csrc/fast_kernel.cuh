@@ -37,6 +37,8 @@ namespace avb {
 constexpr int kFastLanes = 32;      // lane pairs per position = 16 lines x 2
 constexpr int kFastLines = 16;
 constexpr int kFastThreads = 256;
+constexpr int kFastBlocksPerSM = 2;
+constexpr int kTileRec = 20; // ints per host-built tile record (see fast_host.cuh)
 constexpr int kFastWarps = kFastThreads / 32;
 constexpr int kFastMaxSteps = 4;
 constexpr int kFastPitch = kFastLanes + 2; // float2 units: 272 bytes (16-byte aligned rows)
@@ -59,6 +61,7 @@ struct FastStep {
     int out_len;
     int in_lo, in_hi;    // valid domain of the input line
     int upsampled, skip_odd, zero_start;
+    int n_eff;           // RESIZE: rows in `taps` (distinct effective phases)
     const float* taps;   // FIR: ntaps floats; RESIZE: [n_eff][ntaps_pad]
     const int* src_pos;  // RESIZE
     const int* eff;      // RESIZE: per-output row of `taps`
@@ -78,6 +81,9 @@ struct FastParams {
     int span_a, span_b;   // shared rows of the two ping-pong buffers
     int tap_off[kFastMaxSteps]; // float offset of each step's staged taps
     const int* tile_ranges;     // per tile: (a, b) of the source tile and of every step's output
+    int uniform_taps[kFastMaxSteps]; // resize step whose outputs all share one effective phase
+    int rtaps_step;                  // the step whose single effective phase is in rtaps (-1: none)
+    float rtaps[64];                 // that phase: constant-bank operands for the blocked loops
     const void* src;
     long long src_pitch;  // elements
     int src_type;
@@ -161,24 +167,33 @@ __device__ __forceinline__ float epilogue_value_c4(const FastParams& p, float v,
 // `x0` points at the thread's lane in the row of the first input position of output 0; rows
 // are kFastPitch float2 apart.  `tp` = staged taps of output 0 (FLP floats per output).
 
-template <int SUM, int FL, int FLP, int D, int M>
-__device__ __forceinline__ void resize_blocked(const float2* x0, const float* tp, int zero_start,
-                                               float2* out) {
+template <int SUM, int FL, int FLP, int D, int M, bool UNI>
+__device__ __forceinline__ void resize_blocked(const FastParams& p, const float2* x0, const float* tp,
+                                               int tstride, int zero_start, float2* out) {
     constexpr int W = FL + (M - 1) * D;
     float2 x[W];
 #pragma unroll
     for (int w = 0; w < W; ++w) x[w] = x0[w * kFastPitch];
 #pragma unroll
     for (int m = 0; m < M; ++m) {
-        const float* t = tp + m * FLP;
+        const float* t = tp + m * tstride;
         float2 r;
         if (SUM == AVIRB200_SUM_DIL8) {
             float2 ln[8];
 #pragma unroll
             for (int g = 0; g < FL / 8; ++g) {
-                const float4 ta = *reinterpret_cast<const float4*>(t + g * 8);
-                const float4 tb = *reinterpret_cast<const float4*>(t + g * 8 + 4);
-                const float tt[8] = {ta.x, ta.y, ta.z, ta.w, tb.x, tb.y, tb.z, tb.w};
+                float tt[8];
+                if (UNI) {
+                    // one effective phase for the whole axis: taps are kernel parameters, i.e.
+                    // constant-bank operands of the multiplies (no loads, no registers)
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) tt[q] = p.rtaps[g * 8 + q];
+                } else {
+                    const float4 ta = *reinterpret_cast<const float4*>(t + g * 8);
+                    const float4 tb = *reinterpret_cast<const float4*>(t + g * 8 + 4);
+                    tt[0] = ta.x; tt[1] = ta.y; tt[2] = ta.z; tt[3] = ta.w;
+                    tt[4] = tb.x; tt[5] = tb.y; tt[6] = tb.z; tt[7] = tb.w;
+                }
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
                     const float2 v = f2mul(tt[q], x[m * D + g * 8 + q]);
@@ -189,7 +204,9 @@ __device__ __forceinline__ void resize_blocked(const float2* x0, const float* tp
         } else {
 #pragma unroll
             for (int i = 0; i < FL; i += 2) {
-                const float2 t2 = *reinterpret_cast<const float2*>(t + i);
+                float2 t2;
+                if (UNI) t2 = make_float2(p.rtaps[i], p.rtaps[i + 1]);
+                else t2 = *reinterpret_cast<const float2*>(t + i);
                 const float2 v0 = f2mul(t2.x, x[m * D + i]);
                 r = (i == 0) ? v0 : f2add(r, v0);
                 r = f2add(r, f2mul(t2.y, x[m * D + i + 1]));
@@ -203,7 +220,7 @@ __device__ __forceinline__ void resize_blocked(const float2* x0, const float* tp
 // De-interleaved RESIZE with long filters: group-major so that only 8 + (M-1)*D inputs and
 // M x 8 lane accumulators are live at a time (a full register window would not fit).
 template <int FL, int FLP, int D, int M>
-__device__ __forceinline__ void resize_dil_groupmajor(const float2* x0, const float* tp,
+__device__ __forceinline__ void resize_dil_groupmajor(const float2* x0, const float* tp, int tstride,
                                                       int zero_start, float2* out) {
     constexpr int W = 8 + (M - 1) * D;
     float2 ln[M][8];
@@ -214,7 +231,7 @@ __device__ __forceinline__ void resize_dil_groupmajor(const float2* x0, const fl
         for (int w = 0; w < W; ++w) x[w] = x0[(g * 8 + w) * kFastPitch];
 #pragma unroll
         for (int m = 0; m < M; ++m) {
-            const float* t = tp + m * FLP + g * 8;
+            const float* t = tp + m * tstride + g * 8;
             const float4 ta = *reinterpret_cast<const float4*>(t);
             const float4 tb = *reinterpret_cast<const float4*>(t + 4);
             const float tt[8] = {ta.x, ta.y, ta.z, ta.w, tb.x, tb.y, tb.z, tb.w};
@@ -327,19 +344,21 @@ __device__ float2 step_simple(const FastStep& s, const float2* xb, int tile_a, i
 }
 
 // ---- where a step's outputs go -----------------------------------------------------------------------
+// TO_GLOBAL = last step of the column pass: output stage + store to the destination image;
+// otherwise the shared tile of the step's output.
 
 struct Sink {
-    float2* ob;          // shared tile of the step's output: row (j - oa), this thread's lane
+    float2* ob;          // shared tile: row (j - oa), this thread's lane
     int oa;
-    bool to_global;      // last step of the column pass: epilogue + store to the image
-    unsigned char* gp;   // image element (dst row 0, this thread's pixel/channel pair)
+    unsigned char* gp;   // image element (dst row 0, this thread's pixel / channel pair)
     size_t grow;         // bytes between image rows
     int grow_base;       // dst_row_base
     bool gok;
 };
 
+template <bool TO_GLOBAL>
 __device__ __forceinline__ void sink_store(const FastParams& p, const Sink& k, int j, float2 v, int c0) {
-    if (!k.to_global) {
+    if (!TO_GLOBAL) {
         k.ob[(j - k.oa) * kFastPitch] = v;
         return;
     }
@@ -356,10 +375,11 @@ __device__ __forceinline__ void sink_store(const FastParams& p, const Sink& k, i
 
 // ---- one step for one warp ------------------------------------------------------------------------------
 
-template <int SUM>
+template <int SUM, bool TO_GLOBAL>
 __device__ __forceinline__ void run_step(const FastParams& p, const FastStep& s, const float2* xb,
                                          int tile_a, const Range out, const Range dom,
-                                         const float* stp, const Sink& k, int warp, int c0) {
+                                         const float* stp, int uni, bool const_taps, int sp_first,
+                                         int spacing_ok, const Sink& k, int warp, int c0) {
     // balanced split of the tile's outputs over the warps, in units of 4
     const int on = out.b - out.a + 1;
     const int units = (on + 3) >> 2;
@@ -368,27 +388,27 @@ __device__ __forceinline__ void run_step(const FastParams& p, const FastStep& s,
     if (jb >= je) return;
 
     // region [bl, bh) the blocked routine may cover: in-domain, whole quads, right geometry
-    int bl = imax(jb, dom.a), bh = imin(je, dom.b + 1);
-    int nq = 0, p0 = 0, D = 0;
+    const int bl = imax(jb, dom.a), bh = imin(je, dom.b + 1);
+    int nq = 0, p0 = 0;
     if (s.variant != kVarSimple && bh - bl >= 4) {
         nq = (bh - bl) >> 2;
         if (s.kind == AVIRB200_STEP_RESIZE) {
-            D = (s.variant == kVarResizeDil56D4) ? 4 : 2;
-            const int last = bl + 4 * nq - 1;
-            const int spl = __ldg(s.src_pos + bl), sph = __ldg(s.src_pos + last);
-            if (sph - spl != D * (last - bl)) nq = 0; // not the uniform spacing the template assumes
-            p0 = spl - (s.ntaps / 2 - 1);
+            // the host checked the tile's in-domain outputs for the uniform source step the
+            // templates assume (spacing_ok = that step, 0 = irregular) and tabulated the first
+            // position, so no position look-ups are needed here
+            const int D = (s.variant == kVarResizeDil56D4) ? 4 : 2;
+            if (spacing_ok != D) nq = 0;
+            p0 = sp_first + (bl - dom.a) * D - (s.ntaps / 2 - 1);
         } else {
-            D = s.resample;
             p0 = (bl - s.edge) * s.resample - s.latency; // first input of output bl (both forms)
         }
     }
-    const float* tp_of_dom = stp; // RESIZE: row (j - dom.a); FIR: the filter itself
+    const int tstr = uni ? 0 : s.ntaps_pad; // RESIZE: staged row (j - dom.a), or one shared row
 
     auto simple_one = [&](int j) {
         const int jj = imin(imax(j, dom.a), dom.b); // edge replica: value of the clamped output
-        const float* tp = (s.kind == AVIRB200_STEP_FIR) ? stp : stp + (size_t)(jj - dom.a) * s.ntaps_pad;
-        sink_store(p, k, j, step_simple<SUM>(s, xb, tile_a, jj, tp), c0);
+        const float* tp = (s.kind == AVIRB200_STEP_FIR) ? stp : stp + (size_t)(jj - dom.a) * tstr;
+        sink_store<TO_GLOBAL>(p, k, j, step_simple<SUM>(s, xb, tile_a, jj, tp), c0);
     };
 
     int j = jb;
@@ -396,33 +416,31 @@ __device__ __forceinline__ void run_step(const FastParams& p, const FastStep& s,
     for (; j < head_end; ++j) simple_one(j);
     if (nq > 0) {
         const float2* x0 = xb + (p0 - tile_a) * kFastPitch;
-        const float* tp = tp_of_dom + (size_t)(bl - dom.a) * s.ntaps_pad;
+        const float* tp = stp + (size_t)(bl - dom.a) * tstr;
         float2 o4[4];
-#define AVB_QUAD_LOOP(CALL, XSTEP, TSTEP)                                           \
-    for (int q = 0; q < nq; ++q) {                                                  \
-        CALL;                                                                       \
-        _Pragma("unroll") for (int m = 0; m < 4; ++m) sink_store(p, k, j + m, o4[m], c0); \
-        j += 4;                                                                     \
-        x0 += (XSTEP) * kFastPitch;                                                 \
-        tp += (TSTEP);                                                              \
+#define AVB_QUAD_LOOP(CALL, XSTEP, TSTEP)                                                         \
+    for (int q = 0; q < nq; ++q) {                                                                \
+        CALL;                                                                                     \
+        _Pragma("unroll") for (int m = 0; m < 4; ++m) sink_store<TO_GLOBAL>(p, k, j + m, o4[m], c0); \
+        j += 4;                                                                                   \
+        x0 += (XSTEP) * kFastPitch;                                                               \
+        tp += (TSTEP);                                                                            \
+    }
+#define AVB_RESIZE_CASE(SUMM, FL, FLP)                                                                          \
+    if (const_taps) {                                                                                           \
+        AVB_QUAD_LOOP((resize_blocked<SUMM, FL, FLP, 2, 4, true>(p, x0, tp, 0, s.zero_start, o4)), 8, 0)        \
+    } else {                                                                                                    \
+        AVB_QUAD_LOOP((resize_blocked<SUMM, FL, FLP, 2, 4, false>(p, x0, tp, tstr, s.zero_start, o4)), 8, 4 * tstr) \
     }
         switch (s.variant) {
-        case kVarResizeDil24D2:
-            AVB_QUAD_LOOP((resize_blocked<AVIRB200_SUM_DIL8, 24, 24, 2, 4>(x0, tp, s.zero_start, o4)), 8, 4 * 24)
-            break;
-        case kVarResizeDil32D2:
-            AVB_QUAD_LOOP((resize_blocked<AVIRB200_SUM_DIL8, 32, 32, 2, 4>(x0, tp, s.zero_start, o4)), 8, 4 * 32)
-            break;
-        case kVarResizeInl18D2:
-            AVB_QUAD_LOOP((resize_blocked<AVIRB200_SUM_INL, 18, 20, 2, 4>(x0, tp, s.zero_start, o4)), 8, 4 * 20)
-            break;
-        case kVarResizeInl24D2:
-            AVB_QUAD_LOOP((resize_blocked<AVIRB200_SUM_INL, 24, 24, 2, 4>(x0, tp, s.zero_start, o4)), 8, 4 * 24)
-            break;
+        case kVarResizeDil24D2: AVB_RESIZE_CASE(AVIRB200_SUM_DIL8, 24, 24) break;
+        case kVarResizeDil32D2: AVB_RESIZE_CASE(AVIRB200_SUM_DIL8, 32, 32) break;
+        case kVarResizeInl18D2: AVB_RESIZE_CASE(AVIRB200_SUM_INL, 18, 20) break;
+        case kVarResizeInl24D2: AVB_RESIZE_CASE(AVIRB200_SUM_INL, 24, 24) break;
         case kVarResizeDil56D4:
-            AVB_QUAD_LOOP((resize_dil_groupmajor<56, 56, 4, 2>(x0, tp, s.zero_start, o4),
-                           resize_dil_groupmajor<56, 56, 4, 2>(x0 + 8 * kFastPitch, tp + 2 * 56, s.zero_start, o4 + 2)),
-                          16, 4 * 56)
+            AVB_QUAD_LOOP((resize_dil_groupmajor<56, 56, 4, 2>(x0, tp, tstr, s.zero_start, o4),
+                           resize_dil_groupmajor<56, 56, 4, 2>(x0 + 8 * kFastPitch, tp + 2 * tstr, tstr, s.zero_start, o4 + 2)),
+                          16, 4 * tstr)
             break;
         case kVarFirDil8R1: {
             float tt[8];
@@ -448,148 +466,166 @@ __device__ __forceinline__ void run_step(const FastParams& p, const FastStep& s,
         default:
             break;
         }
+#undef AVB_RESIZE_CASE
 #undef AVB_QUAD_LOOP
         for (; j < je; ++j) simple_one(j);
     }
 }
 
-// ---- the kernel ------------------------------------------------------------------------------------------
+// ---- source tile staging ----
 
-template <int SUM>
-__global__ void __launch_bounds__(kFastThreads, 2)
+template <bool IS_V>
+__device__ __forceinline__ void stage_source(const FastParams& p, float2* buf, const int* tr,
+                                             int line0, int nlines, int tid) {
+    const int a = tr[0], n = tr[1] - a + 1; // tile record (shared memory)
+    if (IS_V) {
+        // a "line" is a pixel column; 16 pixels = 64 contiguous floats of a row
+        const float* src = static_cast<const float*>(p.src);
+        const int q = imin(tid & 15, nlines - 1); // pixel within the strip (float4)
+        const int r0 = tid >> 4;                  // 16 rows per sweep
+        for (int pos = r0; pos < n; pos += kFastThreads / 16) {
+            const int y = imin(imax(a + pos, 0), p.ax.src_len - 1) - p.src_row_base;
+            cp_async16(buf + pos * kFastPitch + (tid & 15) * 2,
+                       reinterpret_cast<const float4*>(src + (size_t)y * p.src_pitch) + line0 + q);
+        }
+        return;
+    }
+    const int px = tid & 31; // 32 consecutive positions per sweep
+    const int r0 = tid >> 5; // 8 rows per sweep
+#pragma unroll
+    for (int rr = 0; rr < kFastLines / (kFastThreads / 32); ++rr) {
+        const int r = r0 + rr * (kFastThreads / 32);
+        const size_t rowoff = (size_t)(line0 + imin(r, nlines - 1)) * p.src_pitch;
+        if (p.src_type == AVIRB200_F32) {
+            const float4* srow = reinterpret_cast<const float4*>(static_cast<const float*>(p.src) + rowoff);
+            for (int pos = px; pos < n; pos += 32) {
+                const int x = imin(imax(a + pos, 0), p.ax.src_len - 1);
+                cp_async16(buf + pos * kFastPitch + r * 2, srow + x);
+            }
+        } else {
+            for (int pos = px; pos < n; pos += 32) {
+                const int x = imin(imax(a + pos, 0), p.ax.src_len - 1);
+                float4 v;
+                if (p.src_type == AVIRB200_U8) {
+                    const uchar4 b = __ldg(reinterpret_cast<const uchar4*>(static_cast<const unsigned char*>(p.src) + rowoff) + x);
+                    v = make_float4((float)b.x, (float)b.y, (float)b.z, (float)b.w);
+                    if (p.gamma_in) {
+                        const int ai = p.alpha_index;
+                        v.x = (ai == 0) ? __fmul_rn(v.x, p.in_gamma_mult) : p.srgb_lut[b.x];
+                        v.y = p.srgb_lut[b.y];
+                        v.z = p.srgb_lut[b.z];
+                        v.w = (ai == 3) ? __fmul_rn(v.w, p.in_gamma_mult) : p.srgb_lut[b.w];
+                    }
+                } else {
+                    const ushort4 b = __ldg(reinterpret_cast<const ushort4*>(static_cast<const unsigned short*>(p.src) + rowoff) + x);
+                    v = make_float4((float)b.x, (float)b.y, (float)b.z, (float)b.w);
+                    if (p.gamma_in) {
+                        const int ai = p.alpha_index;
+                        v.x = (ai == 0) ? __fmul_rn(v.x, p.in_gamma_mult) : srgb2lin(v.x, p.in_gamma_mult);
+                        v.y = srgb2lin(v.y, p.in_gamma_mult);
+                        v.z = srgb2lin(v.z, p.in_gamma_mult);
+                        v.w = (ai == 3) ? __fmul_rn(v.w, p.in_gamma_mult) : srgb2lin(v.w, p.in_gamma_mult);
+                    }
+                }
+                *reinterpret_cast<float4*>(buf + pos * kFastPitch + r * 2) = v;
+            }
+        }
+    }
+}
+
+// ---- the kernel ------------------------------------------------------------------------------------------
+// One block = one tile: 16 lines x tile_out final outputs.  blockIdx.x walks along the line so
+// that concurrently resident blocks share their halo reads through L2.
+//
+// Tile record (host-built, kTileRec ints):
+//   [0..9]   (a, b) of the source tile and of every step's output tile
+//   [10..13] first source position of each resize step's in-domain outputs
+//   [14..17] uniform source step of those outputs (0 = irregular)
+
+template <int SUM, bool IS_V>
+__global__ void __launch_bounds__(kFastThreads, kFastBlocksPerSM)
 fast_pass_kernel(const __grid_constant__ FastParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* bufA = reinterpret_cast<float2*>(smem_raw);
     float2* bufB = bufA + (size_t)p.span_a * kFastPitch;
     float* stap = reinterpret_cast<float*>(bufB + (size_t)p.span_b * kFastPitch);
+    __shared__ __align__(16) int tr[kTileRec];
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
     const int line0 = blockIdx.y * kFastLines;
     const int nlines = imin(kFastLines, p.n_lines - line0);
-    const int j0 = p.out0 + blockIdx.x * p.tile_out;
-    const int j1 = imin(j0 + p.tile_out, p.out1) - 1;
     const int ns = p.ax.nsteps;
 
-    // rng[i] = unclamped positions of step i's INPUT held in shared memory; rng[ns] = outputs
-    // The host tabulated them per tile (kFastMaxSteps + 1 ranges = 10 ints per tile), so a
-    // block starts with one uniform load instead of a dependent chain of position look-ups.
-    const int* tr = p.tile_ranges + (size_t)blockIdx.x * (2 * (kFastMaxSteps + 1));
-    auto rng = [&](int i) { return Range{__ldg(tr + 2 * i), __ldg(tr + 2 * i + 1)}; };
-
-    // ---- stage the source tile (edge replicas materialised)
-    {
-        const Range r0g = rng(0);
-        const int a = r0g.a, n = r0g.b - r0g.a + 1;
-        if (p.is_v) {
-            // a "line" is a pixel column; 16 pixels = 64 contiguous floats of a row
-            const float* src = static_cast<const float*>(p.src);
-            const int q = imin(tid & 15, nlines - 1); // pixel within the strip (float4)
-            const int r0 = tid >> 4;                  // 16 rows per sweep
-            for (int pos = r0; pos < n; pos += kFastThreads / 16) {
-                const int y = imin(imax(a + pos, 0), p.ax.src_len - 1) - p.src_row_base;
-                cp_async16(bufA + pos * kFastPitch + (tid & 15) * 2,
-                           reinterpret_cast<const float4*>(src + (size_t)y * p.src_pitch) + line0 + q);
-            }
-        } else {
-            const int px = tid & 31; // 32 consecutive positions per sweep
-            const int r0 = tid >> 5; // 8 rows per sweep
-#pragma unroll
-            for (int rr = 0; rr < kFastLines / (kFastThreads / 32); ++rr) {
-                const int r = r0 + rr * (kFastThreads / 32);
-                const size_t rowoff = (size_t)(line0 + imin(r, nlines - 1)) * p.src_pitch;
-                if (p.src_type == AVIRB200_F32) {
-                    const float4* srow = reinterpret_cast<const float4*>(static_cast<const float*>(p.src) + rowoff);
-                    for (int pos = px; pos < n; pos += 32) {
-                        const int x = imin(imax(a + pos, 0), p.ax.src_len - 1);
-                        cp_async16(bufA + pos * kFastPitch + r * 2, srow + x);
-                    }
-                } else {
-                    for (int pos = px; pos < n; pos += 32) {
-                        const int x = imin(imax(a + pos, 0), p.ax.src_len - 1);
-                        float4 v;
-                        if (p.src_type == AVIRB200_U8) {
-                            const uchar4 b = __ldg(reinterpret_cast<const uchar4*>(static_cast<const unsigned char*>(p.src) + rowoff) + x);
-                            v = make_float4((float)b.x, (float)b.y, (float)b.z, (float)b.w);
-                            if (p.gamma_in) {
-                                const int ai = p.alpha_index;
-                                v.x = (ai == 0) ? __fmul_rn(v.x, p.in_gamma_mult) : p.srgb_lut[b.x];
-                                v.y = p.srgb_lut[b.y];
-                                v.z = p.srgb_lut[b.z];
-                                v.w = (ai == 3) ? __fmul_rn(v.w, p.in_gamma_mult) : p.srgb_lut[b.w];
-                            }
-                        } else {
-                            const ushort4 b = __ldg(reinterpret_cast<const ushort4*>(static_cast<const unsigned short*>(p.src) + rowoff) + x);
-                            v = make_float4((float)b.x, (float)b.y, (float)b.z, (float)b.w);
-                            if (p.gamma_in) {
-                                const int ai = p.alpha_index;
-                                v.x = (ai == 0) ? __fmul_rn(v.x, p.in_gamma_mult) : srgb2lin(v.x, p.in_gamma_mult);
-                                v.y = srgb2lin(v.y, p.in_gamma_mult);
-                                v.z = srgb2lin(v.z, p.in_gamma_mult);
-                                v.w = (ai == 3) ? __fmul_rn(v.w, p.in_gamma_mult) : srgb2lin(v.w, p.in_gamma_mult);
-                            }
-                        }
-                        *reinterpret_cast<float4*>(bufA + pos * kFastPitch + r * 2) = v;
-                    }
-                }
-            }
-        }
-    }
-
-    // ---- stage the taps of every step while the source tile is in flight
+    if (tid < kTileRec) tr[tid] = __ldg(p.tile_ranges + (size_t)blockIdx.x * kTileRec + tid);
+    // taps that do not depend on the tile: FIR filters, single-phase resize steps
     for (int i = 0; i < ns; ++i) {
         const FastStep& s = p.ax.s[i];
         float* st = stap + p.tap_off[i];
         if (s.kind == AVIRB200_STEP_FIR) {
-            for (int t = tid; t < s.ntaps; t += kFastThreads) st[t] = __ldg(s.taps + t);
-        } else {
-            const Range dom = clampr(rng(i + 1), 0, s.out_len);
-            const int rows = dom.b - dom.a + 1;
-            const int fl4 = s.ntaps_pad >> 2;
-            for (int t = tid; t < rows * fl4; t += kFastThreads) {
-                const int rr = t / fl4, c4 = t - rr * fl4;
-                const int e = __ldg(s.eff + dom.a + rr);
-                reinterpret_cast<float4*>(st)[t] =
-                    __ldg(reinterpret_cast<const float4*>(s.taps + (size_t)e * s.ntaps_pad) + c4);
-            }
+            for (int q = tid; q < s.ntaps; q += kFastThreads) st[q] = __ldg(s.taps + q);
+        } else if (p.uniform_taps[i]) {
+            for (int q = tid; q < s.ntaps_pad; q += kFastThreads) st[q] = __ldg(s.taps + q);
         }
     }
-    if (p.src_type == AVIRB200_F32) cp_async_wait_all();
+    __syncthreads();
+    auto rng = [&](int i) { return Range{tr[2 * i], tr[2 * i + 1]}; };
+
+    // ---- stage the source tile (edge replicas materialised) and the per-tile tap rows
+    stage_source<IS_V>(p, bufA, tr, line0, nlines, tid);
+    for (int i = 0; i < ns; ++i) {
+        const FastStep& s = p.ax.s[i];
+        if (s.kind == AVIRB200_STEP_FIR || p.uniform_taps[i]) continue;
+        float* st = stap + p.tap_off[i];
+        const Range dom = clampr(rng(i + 1), 0, s.out_len);
+        const int rows = dom.b - dom.a + 1;
+        const int fl4 = s.ntaps_pad >> 2;
+        for (int q = tid; q < rows * fl4; q += kFastThreads) {
+            const int rr = q / fl4, c4 = q - rr * fl4;
+            const int e = __ldg(s.eff + dom.a + rr);
+            reinterpret_cast<float4*>(st)[q] =
+                __ldg(reinterpret_cast<const float4*>(s.taps + (size_t)e * s.ntaps_pad) + c4);
+        }
+    }
+    cp_async_wait_all();
     __syncthreads();
 
-    // ---- the chain
+    // ---- the chain: source(A) -> B -> A -> B ...
     const int c0 = (lane & 1) * 2; // first channel of this lane's pair
-    Sink gk;
-    gk.to_global = false;
-    gk.gok = (lane >> 1) < nlines;
     const size_t esz = (p.dst_type == AVIRB200_F32 ? 4 : (p.dst_type == AVIRB200_U16 ? 2 : 1));
-    gk.grow = (size_t)p.dst_pitch * esz;
-    gk.grow_base = p.dst_row_base;
-    gk.gp = static_cast<unsigned char*>(p.dst) + ((size_t)(line0 + (lane >> 1)) * 4 + c0) * esz;
+    Sink k;
+    k.gok = (lane >> 1) < nlines;
+    k.grow = (size_t)p.dst_pitch * esz;
+    k.grow_base = p.dst_row_base;
+    k.gp = static_cast<unsigned char*>(p.dst) + ((size_t)(line0 + (lane >> 1)) * 4 + c0) * esz;
     for (int i = 0; i < ns; ++i) {
         const FastStep& s = p.ax.s[i];
         const float2* xb = ((i & 1) ? bufB : bufA) + lane;
         const Range ro = rng(i + 1);
-        Sink k = gk;
         k.ob = ((i & 1) ? bufA : bufB) + lane;
         k.oa = ro.a;
-        k.to_global = (i == ns - 1) && p.is_v;
-        run_step<SUM>(p, s, xb, __ldg(tr + 2 * i), ro, clampr(ro, 0, s.out_len),
-                      stap + p.tap_off[i], k, warp, c0);
+        const bool ct = (p.rtaps_step == i);
+        if (IS_V && i == ns - 1)
+            run_step<SUM, true>(p, s, xb, tr[2 * i], ro, clampr(ro, 0, s.out_len), stap + p.tap_off[i],
+                                p.uniform_taps[i], ct, tr[10 + i], tr[14 + i], k, warp, c0);
+        else
+            run_step<SUM, false>(p, s, xb, tr[2 * i], ro, clampr(ro, 0, s.out_len), stap + p.tap_off[i],
+                                 p.uniform_taps[i], ct, tr[10 + i], tr[14 + i], k, warp, c0);
         __syncthreads();
     }
 
-    if (!p.is_v) {
+    if (!IS_V) {
         // coalesced store of the row-pass tile: [pos][row] in shared -> rows of float4 pixels
         const float2* ob = (ns & 1) ? bufB : bufA;
-        const int oa = j0, on = j1 - j0 + 1;
+        const Range ro = rng(ns);
+        const int on = ro.b - ro.a + 1;
         const int px = tid & 31, r0 = tid >> 5;
         for (int r = r0; r < nlines; r += kFastThreads / 32) {
             float4* drow = reinterpret_cast<float4*>(static_cast<float*>(p.dst) +
                                                      (size_t)(line0 + r) * p.dst_pitch);
             for (int pos = px; pos < on; pos += 32)
-                drow[oa + pos] = *reinterpret_cast<const float4*>(ob + pos * kFastPitch + r * 2);
+                drow[ro.a + pos] = *reinterpret_cast<const float4*>(ob + pos * kFastPitch + r * 2);
         }
     }
 }
