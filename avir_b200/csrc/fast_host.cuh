@@ -80,7 +80,7 @@ inline void fast_finish_footprint(FastFootprint& f, const int* tap_need, int ns)
         off += (tap_need[i] + 3) & ~3;
     }
     f.taps_floats = off;
-    f.smem = ((size_t)f.span_a + f.span_b) * kFastPitch * sizeof(float2) + (size_t)off * sizeof(float);
+    f.smem = ((size_t)2 * f.span_a + f.span_b) * kFastPitch * sizeof(float2) + (size_t)off * sizeof(float);
 }
 
 // Worst-case footprint over all tiles of [out0, out1) for tile size t.
@@ -275,24 +275,57 @@ inline int fast_sm_count() {
     return sms;
 }
 
-// One block per tile; blockIdx.x walks along the line.
+// Persistent launch: kFastBlocksPerSM blocks per SM (or fewer when there are fewer tiles).
 inline int fast_launch(const FastParams& p, size_t smem, int sum_mode, cudaStream_t st) {
-    dim3 grid((p.out1 - p.out0 + p.tile_out - 1) / p.tile_out, (p.n_lines + kFastLines - 1) / kFastLines);
-    if (grid.x == 0 || grid.y == 0) return 0;
-    if (grid.y > 65535) return -2;
+    const long long tiles = (long long)((p.out1 - p.out0 + p.tile_out - 1) / p.tile_out) *
+                            ((p.n_lines + kFastLines - 1) / kFastLines);
+    if (tiles <= 0) return 0;
+    if (tiles > 0x7fffffffLL) return -2;
+    const long long slots = (long long)fast_sm_count() * kFastBlocksPerSM;
+    const int grid = (int)(tiles < slots ? tiles : slots);
     cudaError_t e = cudaSuccess;
-#define AVB_LAUNCH(SUMM, ISV)                                                                      \
+#define AVB_LAUNCH_K(...)                                                                          \
     do {                                                                                           \
-        e = cudaFuncSetAttribute(fast_pass_kernel<SUMM, ISV>,                                      \
+        e = cudaFuncSetAttribute(fast_pass_kernel<__VA_ARGS__>,                                    \
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);          \
-        if (e == cudaSuccess) fast_pass_kernel<SUMM, ISV><<<grid, kFastThreads, smem, st>>>(p);    \
+        if (e == cudaSuccess) fast_pass_kernel<__VA_ARGS__><<<grid, kFastThreads, smem, st>>>(p);  \
     } while (0)
-    if (sum_mode == AVIRB200_SUM_DIL8) {
-        if (p.is_v) AVB_LAUNCH(AVIRB200_SUM_DIL8, true); else AVB_LAUNCH(AVIRB200_SUM_DIL8, false);
-    } else {
-        if (p.is_v) AVB_LAUNCH(AVIRB200_SUM_INL, true); else AVB_LAUNCH(AVIRB200_SUM_INL, false);
+#define AVB_LAUNCH_HV(...)                                                                         \
+    do {                                                                                           \
+        if (p.is_v) AVB_LAUNCH_K(__VA_ARGS__); else AVB_LAUNCH_K(__VA_ARGS__);                      \
+    } while (0)
+    // chain-specialised instantiations (the BASELINE configs); anything else runs the
+    // chain-generic instantiation
+    const FastAxis& a = p.ax;
+    const int v0 = a.s[0].variant, v1 = a.nsteps > 1 ? a.s[1].variant : -1,
+              v2 = a.nsteps > 2 ? a.s[2].variant : -1;
+    const int cs = p.rtaps_step;
+    const bool generic_only = [] { const char* g = getenv("AVIRB200_NO_CHAIN_KERNELS"); return g && g[0] == '1'; }();
+#define AVB_TRY(SUMM, NSS, A0, A1, A2, CSS)                                                         \
+    if (!launched && !generic_only && sum_mode == SUMM && a.nsteps == NSS && v0 == A0 &&           \
+        (NSS < 2 || v1 == A1) && (NSS < 3 || v2 == A2) && cs == CSS) {                             \
+        if (p.is_v) AVB_LAUNCH_K(SUMM, true, NSS, A0, A1, A2, CSS);                                 \
+        else AVB_LAUNCH_K(SUMM, false, NSS, A0, A1, A2, CSS);                                       \
+        launched = true;                                                                           \
     }
-#undef AVB_LAUNCH
+    bool launched = false;
+    AVB_TRY(AVIRB200_SUM_DIL8, 2, kVarResizeDil24D2, kVarFirDil8R1, -1, 0)        // cfg3 (float8_dil)
+    AVB_TRY(AVIRB200_SUM_DIL8, 2, kVarResizeDil56D4, kVarFirDil8R1, -1, -1)       // cfg5
+    AVB_TRY(AVIRB200_SUM_INL, 3, kVarFirInl7R1, kVarResizeInl18D2, kVarFirInl7R1, 1)   // cfg3 (float4)
+    AVB_TRY(AVIRB200_SUM_INL, 3, kVarFirInl15R2, kVarResizeInl18D2, kVarFirInl7R1, 1)  // cfg4
+    AVB_TRY(AVIRB200_SUM_INL, 2, kVarResizeInl24D2, kVarFirInl7R1, -1, 0)         // k = 2, mode 1
+    if (!launched) {
+        if (sum_mode == AVIRB200_SUM_DIL8) {
+            if (p.is_v) AVB_LAUNCH_K(AVIRB200_SUM_DIL8, true, -1, -1, -1, -1, -2);
+            else AVB_LAUNCH_K(AVIRB200_SUM_DIL8, false, -1, -1, -1, -1, -2);
+        } else {
+            if (p.is_v) AVB_LAUNCH_K(AVIRB200_SUM_INL, true, -1, -1, -1, -1, -2);
+            else AVB_LAUNCH_K(AVIRB200_SUM_INL, false, -1, -1, -1, -1, -2);
+        }
+    }
+#undef AVB_TRY
+#undef AVB_LAUNCH_HV
+#undef AVB_LAUNCH_K
     if (e != cudaSuccess) return -1;
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
@@ -342,6 +375,7 @@ inline size_t fast_elsize(int t) { return t == AVIRB200_U8 ? 1 : (t == AVIRB200_
 
 // Picks the (single) resize step whose one effective phase goes into the kernel parameters.
 inline void fast_set_const_taps(FastParams& p, const FastPass& fp) {
+    { const char* e = getenv("AVIRB200_DEBUG"); p.debug = e ? atoi(e) : 0; }
     p.rtaps_step = -1;
     for (int i = 0; i < fp.hax.nsteps; ++i) {
         const FastStep& s = fp.hax.s[i];

@@ -84,6 +84,7 @@ struct FastParams {
     int uniform_taps[kFastMaxSteps]; // resize step whose outputs all share one effective phase
     int rtaps_step;                  // the step whose single effective phase is in rtaps (-1: none)
     float rtaps[64];                 // that phase: constant-bank operands for the blocked loops
+    int debug;                       // perf experiments: 1 = skip the arithmetic, 2 = skip source staging
     const void* src;
     long long src_pitch;  // elements
     int src_type;
@@ -375,11 +376,15 @@ __device__ __forceinline__ void sink_store(const FastParams& p, const Sink& k, i
 
 // ---- one step for one warp ------------------------------------------------------------------------------
 
-template <int SUM, bool TO_GLOBAL>
+// VAR / CT: compile-time step variant and constant-tap flag of the chain-specialised kernels
+// (-1 = decide at run time from the step record: the chain-generic kernel).
+template <int SUM, bool TO_GLOBAL, int VAR, int CT>
 __device__ __forceinline__ void run_step(const FastParams& p, const FastStep& s, const float2* xb,
                                          int tile_a, const Range out, const Range dom,
-                                         const float* stp, int uni, bool const_taps, int sp_first,
+                                         const float* stp, int uni, bool const_taps_rt, int sp_first,
                                          int spacing_ok, const Sink& k, int warp, int c0) {
+    const int variant = (VAR >= 0) ? VAR : s.variant;
+    const bool const_taps = (CT >= 0) ? (CT == 1) : const_taps_rt;
     // balanced split of the tile's outputs over the warps, in units of 4
     const int on = out.b - out.a + 1;
     const int units = (on + 3) >> 2;
@@ -390,13 +395,13 @@ __device__ __forceinline__ void run_step(const FastParams& p, const FastStep& s,
     // region [bl, bh) the blocked routine may cover: in-domain, whole quads, right geometry
     const int bl = imax(jb, dom.a), bh = imin(je, dom.b + 1);
     int nq = 0, p0 = 0;
-    if (s.variant != kVarSimple && bh - bl >= 4) {
+    if (variant != kVarSimple && bh - bl >= 4) {
         nq = (bh - bl) >> 2;
         if (s.kind == AVIRB200_STEP_RESIZE) {
             // the host checked the tile's in-domain outputs for the uniform source step the
             // templates assume (spacing_ok = that step, 0 = irregular) and tabulated the first
             // position, so no position look-ups are needed here
-            const int D = (s.variant == kVarResizeDil56D4) ? 4 : 2;
+            const int D = (variant == kVarResizeDil56D4) ? 4 : 2;
             if (spacing_ok != D) nq = 0;
             p0 = sp_first + (bl - dom.a) * D - (s.ntaps / 2 - 1);
         } else {
@@ -432,7 +437,7 @@ __device__ __forceinline__ void run_step(const FastParams& p, const FastStep& s,
     } else {                                                                                                    \
         AVB_QUAD_LOOP((resize_blocked<SUMM, FL, FLP, 2, 4, false>(p, x0, tp, tstr, s.zero_start, o4)), 8, 4 * tstr) \
     }
-        switch (s.variant) {
+        switch (variant) {
         case kVarResizeDil24D2: AVB_RESIZE_CASE(AVIRB200_SUM_DIL8, 24, 24) break;
         case kVarResizeDil32D2: AVB_RESIZE_CASE(AVIRB200_SUM_DIL8, 32, 32) break;
         case kVarResizeInl18D2: AVB_RESIZE_CASE(AVIRB200_SUM_INL, 18, 20) break;
@@ -542,23 +547,37 @@ __device__ __forceinline__ void stage_source(const FastParams& p, float2* buf, c
 //   [10..13] first source position of each resize step's in-domain outputs
 //   [14..17] uniform source step of those outputs (0 = irregular)
 
-template <int SUM, bool IS_V>
+// NS/V0..V2/CTS: chain known at compile time (steps, their variants, which step has its taps
+// in the kernel parameters); NS = -1 is the chain-generic kernel.  Specialising removes the
+// per-step variant dispatch, the indexed parameter loads and most of the code the generic
+// kernel drags through the instruction cache.
+template <int SUM, bool IS_V, int NS, int V0, int V1, int V2, int CTS>
 __global__ void __launch_bounds__(kFastThreads, kFastBlocksPerSM)
 fast_pass_kernel(const __grid_constant__ FastParams p) {
+    // Persistent: a block walks over tiles (tile index = line block * tiles_per_line + tile
+    // along the line, strided by the grid, so concurrently running blocks work on neighbouring
+    // tiles and share halos through L2).  The source of the NEXT tile streams into the second
+    // source buffer (cp.async) while the current tile computes, so HBM stays busy during the
+    // arithmetic instead of the whole GPU alternating between a load phase and a math phase.
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float2* bufA = reinterpret_cast<float2*>(smem_raw);
-    float2* bufB = bufA + (size_t)p.span_a * kFastPitch;
+    float2* bufA0 = reinterpret_cast<float2*>(smem_raw);
+    float2* bufA1 = bufA0 + (size_t)p.span_a * kFastPitch;
+    float2* bufB = bufA1 + (size_t)p.span_a * kFastPitch;
     float* stap = reinterpret_cast<float*>(bufB + (size_t)p.span_b * kFastPitch);
-    __shared__ __align__(16) int tr[kTileRec];
+    __shared__ __align__(16) int srec[3][kTileRec];
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
-    const int line0 = blockIdx.y * kFastLines;
-    const int nlines = imin(kFastLines, p.n_lines - line0);
-    const int ns = p.ax.nsteps;
+    const int ns = (NS > 0) ? NS : p.ax.nsteps;
+    const int tiles_x = (p.out1 - p.out0 + p.tile_out - 1) / p.tile_out;
+    const int total = tiles_x * ((p.n_lines + kFastLines - 1) / kFastLines);
+    const bool async_src = IS_V || (p.src_type == AVIRB200_F32);
+    const int G = gridDim.x;
 
-    if (tid < kTileRec) tr[tid] = __ldg(p.tile_ranges + (size_t)blockIdx.x * kTileRec + tid);
+    int t = blockIdx.x;
+    if (t >= total) return;
+
     // taps that do not depend on the tile: FIR filters, single-phase resize steps
     for (int i = 0; i < ns; ++i) {
         const FastStep& s = p.ax.s[i];
@@ -569,64 +588,103 @@ fast_pass_kernel(const __grid_constant__ FastParams p) {
             for (int q = tid; q < s.ntaps_pad; q += kFastThreads) st[q] = __ldg(s.taps + q);
         }
     }
-    __syncthreads();
-    auto rng = [&](int i) { return Range{tr[2 * i], tr[2 * i + 1]}; };
-
-    // ---- stage the source tile (edge replicas materialised) and the per-tile tap rows
-    stage_source<IS_V>(p, bufA, tr, line0, nlines, tid);
-    for (int i = 0; i < ns; ++i) {
-        const FastStep& s = p.ax.s[i];
-        if (s.kind == AVIRB200_STEP_FIR || p.uniform_taps[i]) continue;
-        float* st = stap + p.tap_off[i];
-        const Range dom = clampr(rng(i + 1), 0, s.out_len);
-        const int rows = dom.b - dom.a + 1;
-        const int fl4 = s.ntaps_pad >> 2;
-        for (int q = tid; q < rows * fl4; q += kFastThreads) {
-            const int rr = q / fl4, c4 = q - rr * fl4;
-            const int e = __ldg(s.eff + dom.a + rr);
-            reinterpret_cast<float4*>(st)[q] =
-                __ldg(reinterpret_cast<const float4*>(s.taps + (size_t)e * s.ntaps_pad) + c4);
-        }
+    // records of the first two tiles
+    if (tid < kTileRec) {
+        srec[0][tid] = __ldg(p.tile_ranges + (size_t)(t % tiles_x) * kTileRec + tid);
+        if (t + G < total) srec[1][tid] = __ldg(p.tile_ranges + (size_t)((t + G) % tiles_x) * kTileRec + tid);
     }
-    cp_async_wait_all();
     __syncthreads();
-
-    // ---- the chain: source(A) -> B -> A -> B ...
+    if (async_src && p.debug != 2) {
+        const int lb = t / tiles_x;
+        stage_source<IS_V>(p, bufA0, srec[0], lb * kFastLines, imin(kFastLines, p.n_lines - lb * kFastLines), tid);
+    }
     const int c0 = (lane & 1) * 2; // first channel of this lane's pair
     const size_t esz = (p.dst_type == AVIRB200_F32 ? 4 : (p.dst_type == AVIRB200_U16 ? 2 : 1));
-    Sink k;
-    k.gok = (lane >> 1) < nlines;
-    k.grow = (size_t)p.dst_pitch * esz;
-    k.grow_base = p.dst_row_base;
-    k.gp = static_cast<unsigned char*>(p.dst) + ((size_t)(line0 + (lane >> 1)) * 4 + c0) * esz;
-    for (int i = 0; i < ns; ++i) {
-        const FastStep& s = p.ax.s[i];
-        const float2* xb = ((i & 1) ? bufB : bufA) + lane;
-        const Range ro = rng(i + 1);
-        k.ob = ((i & 1) ? bufA : bufB) + lane;
-        k.oa = ro.a;
-        const bool ct = (p.rtaps_step == i);
-        if (IS_V && i == ns - 1)
-            run_step<SUM, true>(p, s, xb, tr[2 * i], ro, clampr(ro, 0, s.out_len), stap + p.tap_off[i],
-                                p.uniform_taps[i], ct, tr[10 + i], tr[14 + i], k, warp, c0);
-        else
-            run_step<SUM, false>(p, s, xb, tr[2 * i], ro, clampr(ro, 0, s.out_len), stap + p.tap_off[i],
-                                 p.uniform_taps[i], ct, tr[10 + i], tr[14 + i], k, warp, c0);
-        __syncthreads();
-    }
 
-    if (!IS_V) {
-        // coalesced store of the row-pass tile: [pos][row] in shared -> rows of float4 pixels
-        const float2* ob = (ns & 1) ? bufB : bufA;
-        const Range ro = rng(ns);
-        const int on = ro.b - ro.a + 1;
-        const int px = tid & 31, r0 = tid >> 5;
-        for (int r = r0; r < nlines; r += kFastThreads / 32) {
-            float4* drow = reinterpret_cast<float4*>(static_cast<float*>(p.dst) +
-                                                     (size_t)(line0 + r) * p.dst_pitch);
-            for (int pos = px; pos < on; pos += 32)
-                drow[ro.a + pos] = *reinterpret_cast<const float4*>(ob + pos * kFastPitch + r * 2);
+    for (int it = 0; t < total; t += G, ++it) {
+        const int lb = t / tiles_x;
+        const int line0 = lb * kFastLines;
+        const int nlines = imin(kFastLines, p.n_lines - line0);
+        const int* tr = srec[it % 3];
+        float2* bufA = (it & 1) ? bufA1 : bufA0;
+        auto rng = [&](int i) { return Range{tr[2 * i], tr[2 * i + 1]}; };
+
+        // per-tile tap rows of resize steps with varying phases
+        for (int i = 0; i < ns; ++i) {
+            const FastStep& s = p.ax.s[i];
+            if (s.kind == AVIRB200_STEP_FIR || p.uniform_taps[i]) continue;
+            float* st = stap + p.tap_off[i];
+            const Range dom = clampr(rng(i + 1), 0, s.out_len);
+            const int rows = dom.b - dom.a + 1;
+            const int fl4 = s.ntaps_pad >> 2;
+            for (int q = tid; q < rows * fl4; q += kFastThreads) {
+                const int rr = q / fl4, c4 = q - rr * fl4;
+                const int e = __ldg(s.eff + dom.a + rr);
+                reinterpret_cast<float4*>(st)[q] =
+                    __ldg(reinterpret_cast<const float4*>(s.taps + (size_t)e * s.ntaps_pad) + c4);
+            }
         }
+        if (!async_src) stage_source<IS_V>(p, bufA, tr, line0, nlines, tid);
+        cp_async_wait_all(); // this tile's source and the next tile's record have landed
+        __syncthreads();
+
+        // prefetch: record of the tile after next, source of the next tile
+        if (t + 2 * G < total && tid < kTileRec / 4)
+            cp_async16(&srec[(it + 2) % 3][tid * 4],
+                       p.tile_ranges + (size_t)((t + 2 * G) % tiles_x) * kTileRec + tid * 4);
+        if (async_src && t + G < total && p.debug != 2) {
+            const int lbn = (t + G) / tiles_x;
+            stage_source<IS_V>(p, (it & 1) ? bufA0 : bufA1, srec[(it + 1) % 3], lbn * kFastLines,
+                               imin(kFastLines, p.n_lines - lbn * kFastLines), tid);
+        }
+
+        // ---- the chain: source(A) -> B -> A -> B ...
+        Sink k;
+        k.gok = (lane >> 1) < nlines;
+        k.grow = (size_t)p.dst_pitch * esz;
+        k.grow_base = p.dst_row_base;
+        k.gp = static_cast<unsigned char*>(p.dst) + ((size_t)(line0 + (lane >> 1)) * 4 + c0) * esz;
+#define AVB_CHAIN_STEP(I, VARI, CTI)                                                                      \
+    {                                                                                                  \
+        const FastStep& s = p.ax.s[I];                                                                 \
+        const float2* xb = (((I) & 1) ? bufB : bufA) + lane;                                           \
+        const Range ro = rng((I) + 1);                                                                 \
+        k.ob = (((I) & 1) ? bufA : bufB) + lane;                                                       \
+        k.oa = ro.a;                                                                                   \
+        if (p.debug == 1) {                                                                            \
+        } else if (IS_V && (I) == ns - 1)                                                              \
+            run_step<SUM, true, VARI, CTI>(                                                            \
+                p, s, xb, tr[2 * (I)], ro, clampr(ro, 0, s.out_len), stap + p.tap_off[I],              \
+                p.uniform_taps[I], p.rtaps_step == (I), tr[10 + (I)], tr[14 + (I)], k, warp, c0);      \
+        else                                                                                           \
+            run_step<SUM, false, VARI, CTI>(                                                           \
+                p, s, xb, tr[2 * (I)], ro, clampr(ro, 0, s.out_len), stap + p.tap_off[I],              \
+                p.uniform_taps[I], p.rtaps_step == (I), tr[10 + (I)], tr[14 + (I)], k, warp, c0);      \
+        __syncthreads();                                                                               \
+    }
+        if (NS > 0) {
+            AVB_CHAIN_STEP(0, V0, (CTS == 0 ? 1 : 0))
+            if (NS > 1) AVB_CHAIN_STEP(1, V1, (CTS == 1 ? 1 : 0))
+            if (NS > 2) AVB_CHAIN_STEP(2, V2, (CTS == 2 ? 1 : 0))
+        } else {
+            for (int i = 0; i < ns; ++i) AVB_CHAIN_STEP(i, -1, -1)
+        }
+#undef AVB_CHAIN_STEP
+
+        if (!IS_V) {
+            // coalesced store of the row-pass tile: [pos][row] in shared -> rows of float4 pixels
+            const float2* ob = (ns & 1) ? bufB : bufA;
+            const Range ro = rng(ns);
+            const int on = ro.b - ro.a + 1;
+            const int px = tid & 31, r0 = tid >> 5;
+            for (int r = r0; r < nlines; r += kFastThreads / 32) {
+                float4* drow = reinterpret_cast<float4*>(static_cast<float*>(p.dst) +
+                                                         (size_t)(line0 + r) * p.dst_pitch);
+                for (int pos = px; pos < on; pos += 32)
+                    drow[ro.a + pos] = *reinterpret_cast<const float4*>(ob + pos * kFastPitch + r * 2);
+            }
+        }
+        // (the next iteration's first barrier orders these reads before the buffer's reuse)
     }
 }
 
