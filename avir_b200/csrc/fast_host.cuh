@@ -237,6 +237,9 @@ inline void fast_plan_init(FastPlan& f, const DevAxis& h_host, const DevAxis& v_
         if (fast_upload(fp) != 0) continue;
         fast_choose_tile(fp, 0, hs[a]->dst_len);
         fp.ok = true;
+        if (getenv("AVIRB200_VERBOSE"))
+            fprintf(stderr, "[avirb200] fast %s pass: tile_out %d, span_a %d, span_b %d, taps %d floats, smem %zu B\n",
+                    a ? "column" : "row", fp.tile_out, fp.fpnt.span_a, fp.fpnt.span_b, fp.fpnt.taps_floats, fp.fpnt.smem);
     }
     f.h_ok = f.h.ok;
     f.v_ok = f.v.ok;
@@ -304,11 +307,13 @@ inline int fast_launch(const FastParams& p, size_t smem, int sum_mode, cudaStrea
 #define AVB_TRY(SUMM, NSS, A0, A1, A2, CSS)                                                         \
     if (!launched && !generic_only && sum_mode == SUMM && a.nsteps == NSS && v0 == A0 &&           \
         (NSS < 2 || v1 == A1) && (NSS < 3 || v2 == A2) && cs == CSS) {                             \
-        if (p.is_v) AVB_LAUNCH_K(SUMM, true, NSS, A0, A1, A2, CSS);                                 \
-        else AVB_LAUNCH_K(SUMM, false, NSS, A0, A1, A2, CSS);                                       \
+        if (p.is_v && plain_f32) AVB_LAUNCH_K(SUMM, true, NSS, A0, A1, A2, CSS, 1);                 \
+        else if (p.is_v) AVB_LAUNCH_K(SUMM, true, NSS, A0, A1, A2, CSS, 0);                         \
+        else AVB_LAUNCH_K(SUMM, false, NSS, A0, A1, A2, CSS, 0);                                    \
         launched = true;                                                                           \
     }
     bool launched = false;
+    const bool plain_f32 = (p.dst_type == AVIRB200_F32 && !p.gamma_out);
     AVB_TRY(AVIRB200_SUM_DIL8, 2, kVarResizeDil24D2, kVarFirDil8R1, -1, 0)        // cfg3 (float8_dil)
     AVB_TRY(AVIRB200_SUM_DIL8, 2, kVarResizeDil56D4, kVarFirDil8R1, -1, -1)       // cfg5
     AVB_TRY(AVIRB200_SUM_INL, 3, kVarFirInl7R1, kVarResizeInl18D2, kVarFirInl7R1, 1)   // cfg3 (float4)
@@ -316,11 +321,11 @@ inline int fast_launch(const FastParams& p, size_t smem, int sum_mode, cudaStrea
     AVB_TRY(AVIRB200_SUM_INL, 2, kVarResizeInl24D2, kVarFirInl7R1, -1, 0)         // k = 2, mode 1
     if (!launched) {
         if (sum_mode == AVIRB200_SUM_DIL8) {
-            if (p.is_v) AVB_LAUNCH_K(AVIRB200_SUM_DIL8, true, -1, -1, -1, -1, -2);
-            else AVB_LAUNCH_K(AVIRB200_SUM_DIL8, false, -1, -1, -1, -1, -2);
+            if (p.is_v) AVB_LAUNCH_K(AVIRB200_SUM_DIL8, true, -1, -1, -1, -1, -2, 0);
+            else AVB_LAUNCH_K(AVIRB200_SUM_DIL8, false, -1, -1, -1, -1, -2, 0);
         } else {
-            if (p.is_v) AVB_LAUNCH_K(AVIRB200_SUM_INL, true, -1, -1, -1, -1, -2);
-            else AVB_LAUNCH_K(AVIRB200_SUM_INL, false, -1, -1, -1, -1, -2);
+            if (p.is_v) AVB_LAUNCH_K(AVIRB200_SUM_INL, true, -1, -1, -1, -1, -2, 0);
+            else AVB_LAUNCH_K(AVIRB200_SUM_INL, false, -1, -1, -1, -1, -2, 0);
         }
     }
 #undef AVB_TRY

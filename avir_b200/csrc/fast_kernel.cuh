@@ -357,10 +357,15 @@ struct Sink {
     bool gok;
 };
 
-template <bool TO_GLOBAL>
+// EPI 1 = destination is float and there is no output gamma: the value is stored as is.
+template <bool TO_GLOBAL, int EPI>
 __device__ __forceinline__ void sink_store(const FastParams& p, const Sink& k, int j, float2 v, int c0) {
     if (!TO_GLOBAL) {
         k.ob[(j - k.oa) * kFastPitch] = v;
+        return;
+    }
+    if (EPI == 1) {
+        if (k.gok) *reinterpret_cast<float2*>(k.gp + (size_t)(j - k.grow_base) * k.grow) = v;
         return;
     }
     v.x = epilogue_value_c4(p, v.x, c0);
@@ -378,7 +383,7 @@ __device__ __forceinline__ void sink_store(const FastParams& p, const Sink& k, i
 
 // VAR / CT: compile-time step variant and constant-tap flag of the chain-specialised kernels
 // (-1 = decide at run time from the step record: the chain-generic kernel).
-template <int SUM, bool TO_GLOBAL, int VAR, int CT>
+template <int SUM, bool TO_GLOBAL, int VAR, int CT, int EPI>
 __device__ __forceinline__ void run_step(const FastParams& p, const FastStep& s, const float2* xb,
                                          int tile_a, const Range out, const Range dom,
                                          const float* stp, int uni, bool const_taps_rt, int sp_first,
@@ -413,7 +418,7 @@ __device__ __forceinline__ void run_step(const FastParams& p, const FastStep& s,
     auto simple_one = [&](int j) {
         const int jj = imin(imax(j, dom.a), dom.b); // edge replica: value of the clamped output
         const float* tp = (s.kind == AVIRB200_STEP_FIR) ? stp : stp + (size_t)(jj - dom.a) * tstr;
-        sink_store<TO_GLOBAL>(p, k, j, step_simple<SUM>(s, xb, tile_a, jj, tp), c0);
+        sink_store<TO_GLOBAL, EPI>(p, k, j, step_simple<SUM>(s, xb, tile_a, jj, tp), c0);
     };
 
     int j = jb;
@@ -426,7 +431,7 @@ __device__ __forceinline__ void run_step(const FastParams& p, const FastStep& s,
 #define AVB_QUAD_LOOP(CALL, XSTEP, TSTEP)                                                         \
     for (int q = 0; q < nq; ++q) {                                                                \
         CALL;                                                                                     \
-        _Pragma("unroll") for (int m = 0; m < 4; ++m) sink_store<TO_GLOBAL>(p, k, j + m, o4[m], c0); \
+        _Pragma("unroll") for (int m = 0; m < 4; ++m) sink_store<TO_GLOBAL, EPI>(p, k, j + m, o4[m], c0); \
         j += 4;                                                                                   \
         x0 += (XSTEP) * kFastPitch;                                                               \
         tp += (TSTEP);                                                                            \
@@ -488,10 +493,22 @@ __device__ __forceinline__ void stage_source(const FastParams& p, float2* buf, c
         const float* src = static_cast<const float*>(p.src);
         const int q = imin(tid & 15, nlines - 1); // pixel within the strip (float4)
         const int r0 = tid >> 4;                  // 16 rows per sweep
-        for (int pos = r0; pos < n; pos += kFastThreads / 16) {
-            const int y = imin(imax(a + pos, 0), p.ax.src_len - 1) - p.src_row_base;
-            cp_async16(buf + pos * kFastPitch + (tid & 15) * 2,
-                       reinterpret_cast<const float4*>(src + (size_t)y * p.src_pitch) + line0 + q);
+        float2* d = buf + r0 * kFastPitch + (tid & 15) * 2;
+        if (a >= 0 && a + n <= p.ax.src_len) {
+            // interior tile: no edge replication, pointers advance by constants
+            const float4* g = reinterpret_cast<const float4*>(src + (size_t)(a + r0 - p.src_row_base) * p.src_pitch) + line0 + q;
+            const size_t gstep = (size_t)(kFastThreads / 16) * (p.src_pitch / 4);
+            for (int pos = r0; pos < n; pos += kFastThreads / 16) {
+                cp_async16(d, g);
+                d += (kFastThreads / 16) * kFastPitch;
+                g += gstep;
+            }
+        } else {
+            for (int pos = r0; pos < n; pos += kFastThreads / 16) {
+                const int y = imin(imax(a + pos, 0), p.ax.src_len - 1) - p.src_row_base;
+                cp_async16(d, reinterpret_cast<const float4*>(src + (size_t)y * p.src_pitch) + line0 + q);
+                d += (kFastThreads / 16) * kFastPitch;
+            }
         }
         return;
     }
@@ -503,9 +520,20 @@ __device__ __forceinline__ void stage_source(const FastParams& p, float2* buf, c
         const size_t rowoff = (size_t)(line0 + imin(r, nlines - 1)) * p.src_pitch;
         if (p.src_type == AVIRB200_F32) {
             const float4* srow = reinterpret_cast<const float4*>(static_cast<const float*>(p.src) + rowoff);
-            for (int pos = px; pos < n; pos += 32) {
-                const int x = imin(imax(a + pos, 0), p.ax.src_len - 1);
-                cp_async16(buf + pos * kFastPitch + r * 2, srow + x);
+            float2* d = buf + px * kFastPitch + r * 2;
+            if (a >= 0 && a + n <= p.ax.src_len) {
+                const float4* g = srow + a + px; // interior tile: constant strides
+                for (int pos = px; pos < n; pos += 32) {
+                    cp_async16(d, g);
+                    d += 32 * kFastPitch;
+                    g += 32;
+                }
+            } else {
+                for (int pos = px; pos < n; pos += 32) {
+                    const int x = imin(imax(a + pos, 0), p.ax.src_len - 1);
+                    cp_async16(d, srow + x);
+                    d += 32 * kFastPitch;
+                }
             }
         } else {
             for (int pos = px; pos < n; pos += 32) {
@@ -551,7 +579,7 @@ __device__ __forceinline__ void stage_source(const FastParams& p, float2* buf, c
 // in the kernel parameters); NS = -1 is the chain-generic kernel.  Specialising removes the
 // per-step variant dispatch, the indexed parameter loads and most of the code the generic
 // kernel drags through the instruction cache.
-template <int SUM, bool IS_V, int NS, int V0, int V1, int V2, int CTS>
+template <int SUM, bool IS_V, int NS, int V0, int V1, int V2, int CTS, int EPI>
 __global__ void __launch_bounds__(kFastThreads, kFastBlocksPerSM)
 fast_pass_kernel(const __grid_constant__ FastParams p) {
     // Persistent: a block walks over tiles (tile index = line block * tiles_per_line + tile
@@ -653,11 +681,11 @@ fast_pass_kernel(const __grid_constant__ FastParams p) {
         k.oa = ro.a;                                                                                   \
         if (p.debug == 1) {                                                                            \
         } else if (IS_V && (I) == ns - 1)                                                              \
-            run_step<SUM, true, VARI, CTI>(                                                            \
+            run_step<SUM, true, VARI, CTI, EPI>(                                                            \
                 p, s, xb, tr[2 * (I)], ro, clampr(ro, 0, s.out_len), stap + p.tap_off[I],              \
                 p.uniform_taps[I], p.rtaps_step == (I), tr[10 + (I)], tr[14 + (I)], k, warp, c0);      \
         else                                                                                           \
-            run_step<SUM, false, VARI, CTI>(                                                           \
+            run_step<SUM, false, VARI, CTI, 0>(                                                           \
                 p, s, xb, tr[2 * (I)], ro, clampr(ro, 0, s.out_len), stap + p.tap_off[I],              \
                 p.uniform_taps[I], p.rtaps_step == (I), tr[10 + (I)], tr[14 + (I)], k, warp, c0);      \
         __syncthreads();                                                                               \

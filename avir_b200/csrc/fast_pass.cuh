@@ -3,6 +3,7 @@
 #pragma once
 
 #include <cuda_runtime.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
