@@ -36,8 +36,8 @@ namespace avb {
 
 constexpr int kFastLanes = 32;      // lane pairs per position = 16 lines x 2
 constexpr int kFastLines = 16;
-constexpr int kFastThreads = 256;
-constexpr int kFastBlocksPerSM = 2;
+constexpr int kFastThreads = 384;
+constexpr int kFastBlocksPerSM = 1;
 constexpr int kTileRec = 20; // ints per host-built tile record (see fast_host.cuh)
 constexpr int kFastWarps = kFastThreads / 32;
 constexpr int kFastMaxSteps = 4;
@@ -514,9 +514,7 @@ __device__ __forceinline__ void stage_source(const FastParams& p, float2* buf, c
     }
     const int px = tid & 31; // 32 consecutive positions per sweep
     const int r0 = tid >> 5; // 8 rows per sweep
-#pragma unroll
-    for (int rr = 0; rr < kFastLines / (kFastThreads / 32); ++rr) {
-        const int r = r0 + rr * (kFastThreads / 32);
+    for (int r = r0; r < kFastLines; r += kFastThreads / 32) {
         const size_t rowoff = (size_t)(line0 + imin(r, nlines - 1)) * p.src_pitch;
         if (p.src_type == AVIRB200_F32) {
             const float4* srow = reinterpret_cast<const float4*>(static_cast<const float*>(p.src) + rowoff);
@@ -699,7 +697,7 @@ fast_pass_kernel(const __grid_constant__ FastParams p) {
         }
 #undef AVB_CHAIN_STEP
 
-        if (!IS_V) {
+        if (!IS_V && p.debug != 3) {
             // coalesced store of the row-pass tile: [pos][row] in shared -> rows of float4 pixels
             const float2* ob = (ns & 1) ? bufB : bufA;
             const Range ro = rng(ns);
