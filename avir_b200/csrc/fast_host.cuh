@@ -3,6 +3,7 @@
 
 struct FastFootprint {
     int span_a = 0, span_b = 0;
+    bool raw = false; // row pass with an integer source: two raw pixel tiles in addition
     int tap_off[kFastMaxSteps] = {0, 0, 0, 0};
     int taps_floats = 0;
     size_t smem = 0;
@@ -13,6 +14,7 @@ struct FastPass {
     FastAxis ax;        // device pointers
     FastAxis hax;       // host pointers (range arithmetic)
     int tile_out = 0;
+    bool raw = false;   // row pass with an integer source
     FastFootprint fpnt;
     std::vector<std::vector<float> > eff_taps;
     std::vector<std::vector<int> > eff_idx, src_pos;
@@ -80,12 +82,14 @@ inline void fast_finish_footprint(FastFootprint& f, const int* tap_need, int ns)
         off += (tap_need[i] + 3) & ~3;
     }
     f.taps_floats = off;
-    f.smem = ((size_t)2 * f.span_a + f.span_b) * kFastPitch * sizeof(float2) + (size_t)off * sizeof(float);
+    f.smem = ((size_t)2 * f.span_a + f.span_b) * kFastPitch * sizeof(float2) + (size_t)off * sizeof(float) +
+             (f.raw ? (size_t)2 * f.span_a * kFastLines * 8 : 0);
 }
 
 // Worst-case footprint over all tiles of [out0, out1) for tile size t.
-inline FastFootprint fast_footprint_all(const FastAxis& hax, int t, int out0, int out1) {
+inline FastFootprint fast_footprint_all(const FastAxis& hax, int t, int out0, int out1, bool raw = false) {
     FastFootprint f;
+    f.raw = raw;
     int need[kFastMaxSteps] = {0, 0, 0, 0};
     for (int j0 = out0; j0 < out1; j0 += t)
         fast_tile_footprint(hax, j0, imin(j0 + t, out1) - 1, f, need);
@@ -103,6 +107,7 @@ inline void fast_choose_tile(FastPass& fp, int out0, int out1) {
         // a representative interior tile
         const int mid = out0 + ((len / 2) / t) * t;
         FastFootprint f;
+        f.raw = fp.raw;
         int need[kFastMaxSteps] = {0, 0, 0, 0};
         const double c = fast_tile_footprint(fp.hax, mid, imin(mid + t, out1) - 1, f, need);
         fast_finish_footprint(f, need, fp.hax.nsteps);
@@ -111,7 +116,7 @@ inline void fast_choose_tile(FastPass& fp, int out0, int out1) {
         if (per < best) { best = per; best_t = t; }
     }
     for (;;) {
-        fp.fpnt = fast_footprint_all(fp.hax, best_t, out0, out1);
+        fp.fpnt = fast_footprint_all(fp.hax, best_t, out0, out1, fp.raw);
         if (fp.fpnt.smem <= kFastSmemBudget || best_t <= 4) break;
         best_t = imax(4, best_t - 4);
     }
@@ -235,6 +240,7 @@ inline void fast_plan_init(FastPlan& f, const DevAxis& h_host, const DevAxis& v_
         for (int i = 0; i < fp.hax.nsteps; ++i)
             fp.hax.s[i].src_pos = fp.src_pos[i].empty() ? nullptr : fp.src_pos[i].data();
         if (fast_upload(fp) != 0) continue;
+        fp.raw = (a == 0 && d.in_type != AVIRB200_F32);
         fast_choose_tile(fp, 0, hs[a]->dst_len);
         fp.ok = true;
         if (getenv("AVIRB200_VERBOSE"))
@@ -399,6 +405,7 @@ inline void fast_set_footprint(FastParams& p, const FastFootprint& f) {
     p.span_a = f.span_a;
     p.span_b = f.span_b;
     for (int i = 0; i < kFastMaxSteps; ++i) p.tap_off[i] = f.tap_off[i];
+    p.taps_floats = f.taps_floats;
 }
 
 // Returns 0 = launched, -2 = not applicable (alignment: the caller runs the generic kernel),

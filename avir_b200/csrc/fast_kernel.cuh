@@ -80,6 +80,7 @@ struct FastParams {
     int out0, out1;
     int span_a, span_b;   // shared rows of the two ping-pong buffers
     int tap_off[kFastMaxSteps]; // float offset of each step's staged taps
+    int taps_floats;            // total staged tap floats (integer-source raw tiles start behind)
     const int* tile_ranges;     // per tile: (a, b) of the source tile and of every step's output
     int uniform_taps[kFastMaxSteps]; // resize step whose outputs all share one effective phase
     int rtaps_step;                  // the step whose single effective phase is in rtaps (-1: none)
@@ -564,6 +565,63 @@ __device__ __forceinline__ void stage_source(const FastParams& p, float2* buf, c
     }
 }
 
+// ---- integer sources (row pass): raw pixels stream in asynchronously, converted in shared memory --
+// Raw layout: [position][line] of one pixel (uchar4 / ushort4).
+
+template <int BYTES>
+__device__ __forceinline__ void cp_async_small(void* smem, const void* gmem) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(sa), "l"(gmem), "n"(BYTES));
+}
+
+__device__ __forceinline__ void stage_raw(const FastParams& p, unsigned char* raw, const int* tr, int line0,
+                                          int nlines, int tid) {
+    const int a = tr[0], n = tr[1] - a + 1;
+    const int px = tid & 31, r0 = tid >> 5;
+    const int pb = (p.src_type == AVIRB200_U8) ? 4 : 8; // bytes per pixel
+    for (int r = r0; r < kFastLines; r += kFastThreads / 32) {
+        const unsigned char* srow = static_cast<const unsigned char*>(p.src) +
+                                    (size_t)(line0 + imin(r, nlines - 1)) * p.src_pitch * (pb / 4);
+        for (int pos = px; pos < n; pos += 32) {
+            const int x = imin(imax(a + pos, 0), p.ax.src_len - 1);
+            unsigned char* d = raw + ((size_t)pos * kFastLines + r) * pb;
+            if (pb == 4) cp_async_small<4>(d, srow + (size_t)x * 4);
+            else cp_async_small<8>(d, srow + (size_t)x * 8);
+        }
+    }
+}
+
+// packScanline on the staged raw tile (avir.h:2777-2971): (float) cast, or sRGB linearisation.
+__device__ __forceinline__ void convert_raw(const FastParams& p, const unsigned char* raw, float2* buf,
+                                            const float* lut, int n, int tid) {
+    for (int idx = tid; idx < n * kFastLines; idx += kFastThreads) {
+        const int pos = idx >> 4, r = idx & (kFastLines - 1);
+        float4 v;
+        if (p.src_type == AVIRB200_U8) {
+            const uchar4 b = reinterpret_cast<const uchar4*>(raw)[idx];
+            v = make_float4((float)b.x, (float)b.y, (float)b.z, (float)b.w);
+            if (p.gamma_in) {
+                const int ai = p.alpha_index;
+                v.x = (ai == 0) ? __fmul_rn(v.x, p.in_gamma_mult) : lut[b.x];
+                v.y = lut[b.y];
+                v.z = lut[b.z];
+                v.w = (ai == 3) ? __fmul_rn(v.w, p.in_gamma_mult) : lut[b.w];
+            }
+        } else {
+            const ushort4 b = reinterpret_cast<const ushort4*>(raw)[idx];
+            v = make_float4((float)b.x, (float)b.y, (float)b.z, (float)b.w);
+            if (p.gamma_in) {
+                const int ai = p.alpha_index;
+                v.x = (ai == 0) ? __fmul_rn(v.x, p.in_gamma_mult) : srgb2lin(v.x, p.in_gamma_mult);
+                v.y = srgb2lin(v.y, p.in_gamma_mult);
+                v.z = srgb2lin(v.z, p.in_gamma_mult);
+                v.w = (ai == 3) ? __fmul_rn(v.w, p.in_gamma_mult) : srgb2lin(v.w, p.in_gamma_mult);
+            }
+        }
+        *reinterpret_cast<float4*>(buf + pos * kFastPitch + r * 2) = v;
+    }
+}
+
 // ---- the kernel ------------------------------------------------------------------------------------------
 // One block = one tile: 16 lines x tile_out final outputs.  blockIdx.x walks along the line so
 // that concurrently resident blocks share their halo reads through L2.
@@ -590,7 +648,11 @@ fast_pass_kernel(const __grid_constant__ FastParams p) {
     float2* bufA1 = bufA0 + (size_t)p.span_a * kFastPitch;
     float2* bufB = bufA1 + (size_t)p.span_a * kFastPitch;
     float* stap = reinterpret_cast<float*>(bufB + (size_t)p.span_b * kFastPitch);
+    // integer sources: two raw pixel tiles behind the taps (16-byte aligned: taps are padded)
+    unsigned char* raw0 = reinterpret_cast<unsigned char*>(stap + p.taps_floats);
+    unsigned char* raw1 = raw0 + (size_t)p.span_a * kFastLines * 8;
     __shared__ __align__(16) int srec[3][kTileRec];
+    __shared__ float slut[256];
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
@@ -599,6 +661,7 @@ fast_pass_kernel(const __grid_constant__ FastParams p) {
     const int tiles_x = (p.out1 - p.out0 + p.tile_out - 1) / p.tile_out;
     const int total = tiles_x * ((p.n_lines + kFastLines - 1) / kFastLines);
     const bool async_src = IS_V || (p.src_type == AVIRB200_F32);
+    const bool raw_src = !IS_V && (p.src_type != AVIRB200_F32);
     const int G = gridDim.x;
 
     int t = blockIdx.x;
@@ -614,6 +677,8 @@ fast_pass_kernel(const __grid_constant__ FastParams p) {
             for (int q = tid; q < s.ntaps_pad; q += kFastThreads) st[q] = __ldg(s.taps + q);
         }
     }
+    if (raw_src && p.gamma_in && p.src_type == AVIRB200_U8)
+        for (int q = tid; q < 256; q += kFastThreads) slut[q] = __ldg(p.srgb_lut + q);
     // records of the first two tiles
     if (tid < kTileRec) {
         srec[0][tid] = __ldg(p.tile_ranges + (size_t)(t % tiles_x) * kTileRec + tid);
@@ -623,6 +688,10 @@ fast_pass_kernel(const __grid_constant__ FastParams p) {
     if (async_src && p.debug != 2) {
         const int lb = t / tiles_x;
         stage_source<IS_V>(p, bufA0, srec[0], lb * kFastLines, imin(kFastLines, p.n_lines - lb * kFastLines), tid);
+    }
+    if (raw_src) {
+        const int lb = t / tiles_x;
+        stage_raw(p, raw0, srec[0], lb * kFastLines, imin(kFastLines, p.n_lines - lb * kFastLines), tid);
     }
     const int c0 = (lane & 1) * 2; // first channel of this lane's pair
     const size_t esz = (p.dst_type == AVIRB200_F32 ? 4 : (p.dst_type == AVIRB200_U16 ? 2 : 1));
@@ -650,7 +719,6 @@ fast_pass_kernel(const __grid_constant__ FastParams p) {
                     __ldg(reinterpret_cast<const float4*>(s.taps + (size_t)e * s.ntaps_pad) + c4);
             }
         }
-        if (!async_src) stage_source<IS_V>(p, bufA, tr, line0, nlines, tid);
         cp_async_wait_all(); // this tile's source and the next tile's record have landed
         __syncthreads();
 
@@ -662,6 +730,16 @@ fast_pass_kernel(const __grid_constant__ FastParams p) {
             const int lbn = (t + G) / tiles_x;
             stage_source<IS_V>(p, (it & 1) ? bufA0 : bufA1, srec[(it + 1) % 3], lbn * kFastLines,
                                imin(kFastLines, p.n_lines - lbn * kFastLines), tid);
+        }
+
+        if (raw_src) {
+            if (t + G < total) {
+                const int lbn = (t + G) / tiles_x;
+                stage_raw(p, (it & 1) ? raw0 : raw1, srec[(it + 1) % 3], lbn * kFastLines,
+                          imin(kFastLines, p.n_lines - lbn * kFastLines), tid);
+            }
+            convert_raw(p, (it & 1) ? raw1 : raw0, bufA, slut, tr[1] - tr[0] + 1, tid);
+            __syncthreads();
         }
 
         // ---- the chain: source(A) -> B -> A -> B ...
