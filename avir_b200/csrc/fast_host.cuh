@@ -184,6 +184,8 @@ inline bool fast_build_axis(FastPass& fp, const DevAxis& host, int sum_mode) {
                 fp.eff_idx[i][j] = it->second;
             }
             s.n_eff = (int)seen.size();
+            if (d.upsampled && d.skip_odd && sum_mode == AVIRB200_SUM_INL && FL == 24 && seen.size() == 1)
+                s.variant = kVarResize2Inl24;
             if (!d.upsampled) {
                 if (sum_mode == AVIRB200_SUM_DIL8 && FL == 24) s.variant = kVarResizeDil24D2;
                 if (sum_mode == AVIRB200_SUM_DIL8 && FL == 32) s.variant = kVarResizeDil32D2;
@@ -325,6 +327,7 @@ inline int fast_launch(const FastParams& p, size_t smem, int sum_mode, cudaStrea
     AVB_TRY(AVIRB200_SUM_INL, 3, kVarFirInl7R1, kVarResizeInl18D2, kVarFirInl7R1, 1)   // cfg3 (float4)
     AVB_TRY(AVIRB200_SUM_INL, 3, kVarFirInl15R2, kVarResizeInl18D2, kVarFirInl7R1, 1)  // cfg4
     AVB_TRY(AVIRB200_SUM_INL, 2, kVarResizeInl24D2, kVarFirInl7R1, -1, 0)         // k = 2, mode 1
+    AVB_TRY(AVIRB200_SUM_INL, 2, kVarFirInl7R1, kVarResize2Inl24, -1, 1)          // cfg2 (k = 0.5)
     if (!launched) {
         if (sum_mode == AVIRB200_SUM_DIL8) {
             if (p.is_v) AVB_LAUNCH_K(AVIRB200_SUM_DIL8, true, -1, -1, -1, -1, -2, 0);

@@ -53,6 +53,7 @@ enum FastVariant : int {
     kVarFirDil8R1,       // float8_dil 8-tap (7 + pad) correction       (cfg3/cfg5 dil)
     kVarFirInl7R1,       // interleaved 7-tap (L = 3), R = 1            (LPF k=2, correction)
     kVarFirInl15R2,      // interleaved 15-tap (L = 7), R = 2           (cfg4 decimator)
+    kVarResize2Inl24,    // interleaved FL 24 over the virtual 2X line, skip-odd (cfg2, k = 0.5)
 };
 
 struct FastStep {
@@ -252,6 +253,32 @@ __device__ __forceinline__ void resize_dil_groupmajor(const float2* x0, const fl
     }
 }
 
+// Interleaved RESIZE over the virtual 2X zero-stuffed line, upstream's doResize2
+// (avir.h:4114-4328): only the 12 taps that land on real samples are accumulated; consecutive
+// outputs advance by one virtual position, i.e. alternate between the even and the odd taps.
+// ODD = parity of output 0's first virtual position; x0 = sample (p0 + parity) / 2.  Taps are
+// the kernel-parameter constants (single effective phase).
+template <bool ODD>
+__device__ __forceinline__ void resize2_blocked(const FastParams& p, const float2* x0, int zero_start,
+                                                float2* out) {
+    constexpr int W = ODD ? 13 : 14;
+    float2 x[W];
+#pragma unroll
+    for (int w = 0; w < W; ++w) x[w] = x0[w * kFastPitch];
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+        constexpr int dummy = 0;
+        (void)dummy;
+        const int fo = ODD ? ((m & 1) ? 0 : 1) : (m & 1);
+        const int base = ODD ? (m >> 1) : ((m + 1) >> 1);
+        float2 r = f2mul(p.rtaps[fo], x[base]);
+#pragma unroll
+        for (int t = 1; t < 12; ++t) r = f2add(r, f2mul(p.rtaps[fo + 2 * t], x[base + t]));
+        if (zero_start) r = f2add(r, make_float2(0.0f, 0.0f));
+        out[m] = r;
+    }
+}
+
 // FIR.  INL: folded symmetric form around the centre tap; DIL: full padded filter.
 // `tt` = the NT taps in registers.
 template <int SUM, int NT, int R, int M>
@@ -407,7 +434,8 @@ __device__ __forceinline__ void run_step(const FastParams& p, const FastStep& s,
             // the host checked the tile's in-domain outputs for the uniform source step the
             // templates assume (spacing_ok = that step, 0 = irregular) and tabulated the first
             // position, so no position look-ups are needed here
-            const int D = (variant == kVarResizeDil56D4) ? 4 : 2;
+            const int D = (variant == kVarResizeDil56D4) ? 4 : (variant == kVarResize2Inl24 ? 1 : 2);
+            if (variant == kVarResize2Inl24 && !const_taps) nq = 0;
             if (spacing_ok != D) nq = 0;
             p0 = sp_first + (bl - dom.a) * D - (s.ntaps / 2 - 1);
         } else {
@@ -427,6 +455,7 @@ __device__ __forceinline__ void run_step(const FastParams& p, const FastStep& s,
     for (; j < head_end; ++j) simple_one(j);
     if (nq > 0) {
         const float2* x0 = xb + (p0 - tile_a) * kFastPitch;
+        if (variant == kVarResize2Inl24) x0 = xb + (((p0 + (p0 & 1)) >> 1) - tile_a) * kFastPitch;
         const float* tp = stp + (size_t)(bl - dom.a) * tstr;
         float2 o4[4];
 #define AVB_QUAD_LOOP(CALL, XSTEP, TSTEP)                                                         \
@@ -448,6 +477,13 @@ __device__ __forceinline__ void run_step(const FastParams& p, const FastStep& s,
         case kVarResizeDil32D2: AVB_RESIZE_CASE(AVIRB200_SUM_DIL8, 32, 32) break;
         case kVarResizeInl18D2: AVB_RESIZE_CASE(AVIRB200_SUM_INL, 18, 20) break;
         case kVarResizeInl24D2: AVB_RESIZE_CASE(AVIRB200_SUM_INL, 24, 24) break;
+        case kVarResize2Inl24:
+            if (p0 & 1) {
+                AVB_QUAD_LOOP((resize2_blocked<true>(p, x0, s.zero_start, o4)), 2, 0)
+            } else {
+                AVB_QUAD_LOOP((resize2_blocked<false>(p, x0, s.zero_start, o4)), 2, 0)
+            }
+            break;
         case kVarResizeDil56D4:
             AVB_QUAD_LOOP((resize_dil_groupmajor<56, 56, 4, 2>(x0, tp, tstr, s.zero_start, o4),
                            resize_dil_groupmajor<56, 56, 4, 2>(x0 + 8 * kFastPitch, tp + 2 * tstr, tstr, s.zero_start, o4 + 2)),
