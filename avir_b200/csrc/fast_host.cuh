@@ -82,8 +82,8 @@ inline void fast_finish_footprint(FastFootprint& f, const int* tap_need, int ns)
         off += (tap_need[i] + 3) & ~3;
     }
     f.taps_floats = off;
-    f.smem = ((size_t)2 * f.span_a + f.span_b) * kFastPitch * sizeof(float2) + (size_t)off * sizeof(float) +
-             (f.raw ? (size_t)2 * f.span_a * kFastLines * 8 : 0);
+    f.smem = ((size_t)(f.raw ? 1 : 2) * f.span_a + f.span_b) * kFastPitch * sizeof(float2) +
+             (size_t)off * sizeof(float) + (f.raw ? (size_t)2 * f.span_a * kFastLines * 8 : 0);
 }
 
 // Worst-case footprint over all tiles of [out0, out1) for tile size t.

@@ -680,8 +680,11 @@ fast_pass_kernel(const __grid_constant__ FastParams p) {
     // source buffer (cp.async) while the current tile computes, so HBM stays busy during the
     // arithmetic instead of the whole GPU alternating between a load phase and a math phase.
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    // integer sources are converted into the float tile every iteration, so only their raw
+    // pixel tiles are double-buffered and one float source buffer suffices
+    const bool one_a = !IS_V && (p.src_type != AVIRB200_F32);
     float2* bufA0 = reinterpret_cast<float2*>(smem_raw);
-    float2* bufA1 = bufA0 + (size_t)p.span_a * kFastPitch;
+    float2* bufA1 = one_a ? bufA0 : bufA0 + (size_t)p.span_a * kFastPitch;
     float2* bufB = bufA1 + (size_t)p.span_a * kFastPitch;
     float* stap = reinterpret_cast<float*>(bufB + (size_t)p.span_b * kFastPitch);
     // integer sources: two raw pixel tiles behind the taps (16-byte aligned: taps are padded)
