@@ -54,20 +54,43 @@ def _sources(dirs, exts):
     return out
 
 
+def _obj_stale(obj, src):
+    """Per-object staleness from the dependency file nvcc wrote beside it (-MD)."""
+    dep = obj + ".d"
+    if not os.path.exists(obj) or not os.path.exists(dep):
+        return True
+    t = os.path.getmtime(obj)
+    words = open(dep).read().replace("\\\n", " ").split()
+    deps = [w for w in words[1:] if not w.endswith(":")] + [src, os.path.abspath(__file__)]
+    for d in deps:
+        if d.startswith("/usr/") or d.startswith("/opt/"):
+            continue
+        if not os.path.exists(d) or os.path.getmtime(d) > t:
+            return True
+    return False
+
+
 def build_cuda(force=False, verbose=False):
+    """One object per .cu (compiled in parallel, only when one of its own includes changed),
+    linked into libavirb200.so."""
+    from concurrent.futures import ThreadPoolExecutor
     target = os.path.join(PKG, "libavirb200.so")
-    cus = [os.path.join(CSRC, "engine.cu"), os.path.join(CSRC, "lancir.cu")]
-    deps = _sources([CSRC, INC], (".cu", ".cuh", ".h", ".hpp"))
-    if not force and not _newer(target, deps):
-        return target
-    objs = []
-    for cu in cus:
-        obj = os.path.join(PKG, os.path.basename(cu)[:-3] + ".o")
-        out = _run([_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", cu, "-o", obj])
-        if verbose:
-            print(out)
-        objs.append(obj)
-    _run([_nvcc(), "-shared", "-o", target] + objs + ["-lcudart_static", "-ldl", "-lpthread", "-lrt"])
+    cus = [os.path.join(CSRC, "engine.cu"), os.path.join(CSRC, "lancir.cu"),
+           os.path.join(CSRC, "stream_pass.cu")]
+    objs = [os.path.join(PKG, os.path.basename(cu)[:-3] + ".o") for cu in cus]
+    todo = [(cu, ob) for cu, ob in zip(cus, objs) if force or _obj_stale(ob, cu)]
+
+    def compile_one(job):
+        cu, obj = job
+        return _run([_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) +
+                    ["-MD", "-MF", obj + ".d", "-c", cu, "-o", obj])
+
+    with ThreadPoolExecutor(max_workers=4) as ex:
+        for out in ex.map(compile_one, todo):
+            if verbose:
+                print(out)
+    if todo or not os.path.exists(target):
+        _run([_nvcc(), "-shared", "-o", target] + objs + ["-lcudart_static", "-ldl", "-lpthread", "-lrt"])
     return target
 
 
@@ -87,10 +110,25 @@ def build_oracles():
     _run(["make", "-C", os.path.join(ROOT, "oracle"), "all"])
 
 
+def build_emul(force=False):
+    """TEST INFRASTRUCTURE: host lockstep emulation of the streaming kernel (tests/emul)."""
+    d = os.path.join(ROOT, "tests", "emul")
+    target = os.path.join(d, "libstream_emul.so")
+    src = os.path.join(d, "stream_emul.cpp")
+    deps = [src] + _sources([CSRC, INC], (".cuh", ".h"))
+    if not force and not _newer(target, deps):
+        return target
+    cuda_inc = os.path.join(os.path.dirname(os.path.dirname(_nvcc())), "include")
+    _run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-I" + INC, "-I" + CSRC,
+          "-I" + cuda_inc, "-o", target, src, "-pthread"])
+    return target
+
+
 def build_all(force=False, verbose=False):
     build_cuda(force, verbose)
     build_host(force)
     build_oracles()
+    build_emul(force)
 
 
 if __name__ == "__main__":

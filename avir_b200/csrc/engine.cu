@@ -25,13 +25,26 @@
 #include "device_plan.h"
 #include "fast_pass.cuh"
 #include "generic_pass.cuh"
+#include "stream_types.h"
+#include "stream_launch.h"
 
 using namespace avb;
 
 namespace {
 
 thread_local std::string g_err;
-bool g_force_generic = false; // debug/test switch: bypass the specialised kernels
+// debug/test switch: 0 = streaming kernel, else tile kernel, else generic kernel (product
+// order); 1 = generic kernel only; 2 = tile kernel, else generic (no streaming kernel)
+int g_kernel_mode = 0;
+#define g_force_generic (g_kernel_mode == 1)
+
+bool env_stream_enabled() {
+    static const bool on = [] {
+        const char* e = getenv("AVIRB200_DISABLE_STREAM");
+        return !(e && e[0] == '1');
+    }();
+    return on;
+}
 
 int fail(int code, const std::string& msg) {
     g_err = msg;
@@ -102,6 +115,7 @@ struct avirb200_plan {
     int device = 0;
     PassConfig cfg_h, cfg_v;
     FastPlan fast;
+    avs::StreamAxisPlan stream_h, stream_v; // chain != 0: the pass runs on the streaming kernel
     // resize_host cache
     std::mutex mx;
     void* d_src = nullptr;
@@ -300,6 +314,22 @@ int run_row_pass(const avirb200_plan* pl, const void* d_src, size_t src_pitch, f
                  int rows, cudaStream_t st, int* launches) {
     if (rows <= 0) return 0;
     const avirb200_plan_desc& d = pl->desc;
+    if (g_kernel_mode == 0 && env_stream_enabled() && pl->stream_h.chain != 0 &&
+        ((uintptr_t)d_src % 16) == 0 && (src_pitch % 4) == 0 && ((uintptr_t)d_mid % 16) == 0) {
+        avs::StreamParams sp;
+        avs::stream_fill_params(sp, pl->stream_h, d);
+        sp.n_lines = rows;
+        sp.out0 = 0;
+        sp.out1 = d.dst_w;
+        sp.src = d_src;
+        sp.src_pitch = (long long)src_pitch;
+        sp.dst = d_mid;
+        sp.dst_pitch = (long long)d.dst_w * 4;
+        sp.dst_type = AVIRB200_F32;
+        const int r = avs::stream_launch(pl->stream_h.chain, false, false, sp, st);
+        if (r == -1) return fail(AVIRB200_ERR_CUDA, "streaming row pass launch failed");
+        if (r == 0) { ++*launches; return 0; }
+    }
     if (env_fast_enabled() && !g_force_generic && pl->fast.h_ok) {
         const int r = fast_row_pass(pl->fast, d, d_src, src_pitch, d_mid, rows, pl->d_lut, st);
         if (r == -1) return fail(AVIRB200_ERR_CUDA, "fast row pass launch failed");
@@ -331,6 +361,28 @@ int run_col_pass(const avirb200_plan* pl, const float* d_mid, int mid_row_base, 
                  size_t dst_pitch, int out0, int out1, cudaStream_t st, int* launches) {
     if (out1 <= out0) return 0;
     const avirb200_plan_desc& d = pl->desc;
+    {
+        const size_t es = fast_elsize(d.out_type);
+        if (g_kernel_mode == 0 && env_stream_enabled() && pl->stream_v.chain != 0 &&
+            ((uintptr_t)d_dst % (2 * es)) == 0 && (dst_pitch % 2) == 0 && ((uintptr_t)d_mid % 16) == 0) {
+            avs::StreamParams sp;
+            avs::stream_fill_params(sp, pl->stream_v, d);
+            sp.n_lines = d.dst_w;
+            sp.out0 = out0;
+            sp.out1 = out1;
+            sp.src = d_mid;
+            sp.src_pitch = (long long)d.dst_w * 4;
+            sp.src_row_base = mid_row_base;
+            sp.dst = d_dst;
+            sp.dst_pitch = (long long)dst_pitch;
+            sp.dst_type = d.out_type;
+            sp.dst_row_base = out0;
+            const bool plain = (d.out_type == AVIRB200_F32) && !(d.use_gamma & 2);
+            const int r = avs::stream_launch(pl->stream_v.chain, true, plain, sp, st);
+            if (r == -1) return fail(AVIRB200_ERR_CUDA, "streaming column pass launch failed");
+            if (r == 0) { ++*launches; return 0; }
+        }
+    }
     if (env_fast_enabled() && !g_force_generic && pl->fast.v_ok) {
         const int r = fast_col_pass(pl->fast, d, d_mid, mid_row_base, d_dst, dst_pitch, out0, out1,
                                     pl->d_lut, st);
@@ -475,7 +527,13 @@ DevAxis host_axis_view(const avirb200_axis_desc& ad) {
 
 extern "C" {
 
-void avirb200_debug_force_generic(int on) { g_force_generic = (on != 0); }
+void avirb200_debug_force_generic(int mode) { g_kernel_mode = (mode == 1 || mode == 2) ? mode : 0; }
+
+int avirb200_plan_kernel_paths(const avirb200_plan* pl) {
+    if (pl == nullptr) return 0;
+    return (pl->stream_h.chain != 0 ? 1 : 0) | (pl->stream_v.chain != 0 ? 2 : 0) |
+           (pl->fast.h_ok ? 4 : 0) | (pl->fast.v_ok ? 8 : 0);
+}
 
 int avirb200_shard_query_desc(const avirb200_plan_desc* desc, int rank, int nranks,
                               avirb200_shard_info* info) {
@@ -551,6 +609,8 @@ int avirb200_plan_create(const avirb200_plan_desc* desc, avirb200_plan** out) {
     pl->cfg_h = choose_generic_config(pl->h.hostdev, desc->channels, 0, desc->dst_w);
     pl->cfg_v = choose_generic_config(pl->v.hostdev, desc->channels, 0, desc->dst_h);
     fast_plan_init(pl->fast, pl->h.hostdev, pl->v.hostdev, *desc);
+    if (avs::stream_row_source_ok(*desc)) avs::stream_plan_axis(desc->h, desc->sum_mode, desc->channels, pl->stream_h);
+    avs::stream_plan_axis(desc->v, desc->sum_mode, desc->channels, pl->stream_v);
     *out = pl.release();
     return 0;
 }

@@ -1,0 +1,561 @@
+// stream_kernel.cuh -- warp-streaming pass kernel for regular 4-channel chains (sm_100a).
+//
+// The tile kernel (fast_kernel.cuh) gives every block a tile of 16 lines, runs one step of
+// the chain at a time over the whole tile and separates the steps with block barriers.  With
+// the shared memory a chain needs, a tile holds ~130 outputs, i.e. 2-3 inner-loop trips per
+// warp between barriers: the FP32 pipe idles half of the time.  This kernel removes the
+// barriers altogether:
+//
+//   * a WARP owns a run: 16 lines (lane = one channel pair of one line, as in the tile
+//     kernel) times a long contiguous range of positions, and streams along it;
+//   * every step of the chain works in batches of 8 outputs from a register window of its
+//     input (38 shared loads per 752 FP instructions for the 24-tap resize) and appends the
+//     batch to a small per-warp ring in shared memory; the next step consumes that ring a
+//     fixed number of rounds later (software pipeline, all offsets compile-time);
+//   * a lane only ever reads back what it wrote itself ([position][lane] layout), so the
+//     intermediate rings need no synchronisation at all; only the source ring (filled by
+//     16-byte cp.async copies, transposing rows into lanes in the row pass, three rounds
+//     ahead of use) and the row pass's output staging use __syncwarp;
+//   * taps are kernel parameters (constant-bank operands of the multiplies): only chains
+//     whose resize step has one effective phase and a constant source step -- all integer
+//     ratios, i.e. every BASELINE configuration -- run here, everything else stays on the
+//     tile kernel;
+//   * edges: the source ring materialises the replicated border (the loader clamps the
+//     global coordinate); a batch whose window leaves its input line, or that is cut by the
+//     end of its own output line, takes a per-output path that clamps every tap position
+//     (upstream replicates edges per step, avir.h:3227-3239) -- 2 batches per line and step.
+//
+// Arithmetic (order of the separate multiplies and adds) is the tile kernel's, i.e.
+// upstream's; tests compare all three kernels against the oracle.  The same source compiles
+// for the host (tests/emul/stream_emul.cpp: 32 threads in lockstep per warp) so that the
+// index logic is checked against the oracle on machines without a GPU.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string.h>
+
+#include "avirb200.h"
+#include "pixel_ops.cuh"
+#include "stream_types.h"
+
+#if defined(__CUDACC__)
+#define AVS_FN __device__ __forceinline__
+#define AVS_SYNCWARP() __syncwarp()
+#else
+#define AVS_FN inline __attribute__((always_inline))
+void avs_emul_syncwarp(); // the emulator's lockstep barrier
+#define AVS_SYNCWARP() avs_emul_syncwarp()
+#endif
+
+namespace avs {
+
+using avb::lin2srgb;
+using avb::round_out;
+
+constexpr int kLines = 16;      // lines per warp (2 lanes per line)
+constexpr int kPitchT = 34;     // float2 units: 272-byte rows, conflict-free transposed access
+constexpr int kPitchL = 32;     // 256-byte rows where only the owning lane touches a column
+
+// Compile-time description of one step.  NT = taps (FIR: stored taps, 2L+1 for the
+// interleaved form, padded to 8 for the de-interleaved one; RESIZE/RESIZE2: filter length).
+// ADV = input positions per output (FIR decimation R, RESIZE source step D).
+// RESIZE2 = resize over the virtual 2X zero-stuffed line, odd taps skipped (upstream
+// doResize2, avir.h:4114-4328): two outputs per input position.
+template <int KIND_, int SUM_, int NT_, int ADV_>
+struct StepC {
+    static constexpr int KIND = KIND_, SUM = SUM_, NT = NT_, ADV = ADV_;
+    static constexpr int M = (KIND == K_RESIZE2) ? 16 : 8;          // outputs per batch
+    static constexpr int CH = (KIND == K_RESIZE2) ? 8 : 8 * ADV;    // input positions per batch
+    // sub-batch: outputs computed from one register window
+    static constexpr int MS = (KIND != K_RESIZE2 && NT + 7 * ADV > 48) ? 4 : M;
+    static constexpr int WS = (KIND == K_RESIZE2) ? 20 : NT + (MS - 1) * ADV; // window of a sub-batch
+    static constexpr int W = (KIND == K_RESIZE2) ? 20 : NT + (M - 1) * ADV;   // window of a batch
+    static constexpr int NTW = (KIND == K_RESIZE2) ? NT / 2 : NT;   // inputs one output reads
+};
+using NoStep = StepC<K_NONE, 0, 0, 1>;
+
+constexpr int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+// Compile-time software-pipeline schedule of a chain (see run_warp()).
+//   reps[i]  batches of step i per round
+//   delay[i] rounds step i lags behind step 0
+//   rsp[i]   positions in the ring step i reads (ring 0 = source)
+template <class S0, class S1, class S2, int REPS_LAST, int LA>
+struct ChainC {
+    using T0 = S0;
+    using T1 = S1;
+    using T2 = S2;
+    static constexpr int NS = (S2::KIND == K_NONE) ? 2 : 3;
+    static constexpr int LOOKAHEAD = LA;
+    static constexpr int reps2 = (NS == 3) ? REPS_LAST : 0;
+    static constexpr int reps1 = (NS == 3) ? (S2::CH * reps2) / S1::M : REPS_LAST;
+    static constexpr int reps0 = (S1::CH * reps1) / S0::M;
+    static_assert(NS == 2 || (S2::CH * reps2) % S1::M == 0, "step 1 batches per round");
+    static_assert((S1::CH * reps1) % S0::M == 0, "step 0 batches per round");
+    static constexpr int B = (NS == 3) ? S2::M * reps2 : S1::M * reps1; // final outputs per round
+    static constexpr int SRC_N = S0::CH * reps0;                        // source positions per round
+    static_assert(SRC_N % 16 == 0, "source positions per round must be whole 16-position loads");
+    // consumer i+1 needs its producer d rounds ahead
+    static constexpr int d0 = cdiv(cdiv(S1::W, S1::CH) - 1, reps1);
+    static constexpr int d1 = (NS == 3) ? cdiv(cdiv(S2::W, S2::CH) - 1, reps2) : 0;
+    static constexpr int delay0 = 0, delay1 = d0, delay2 = d0 + d1;
+    static constexpr int DELAY_LAST = (NS == 3) ? delay2 : delay1;
+    static constexpr int rsp1 = S1::CH * reps1 * (d0 + 1);
+    static constexpr int rsp2 = (NS == 3) ? S2::CH * reps2 * (d1 + 1) : 0;
+    // source ring: groups of SRC_N positions; step 0's window overhangs h groups
+    static constexpr int H = cdiv(S0::W - S0::CH, SRC_N);
+    static constexpr int NG = H + LA + 1;
+    static constexpr int rsp0 = NG * SRC_N;
+    static constexpr int MLAST = (NS == 3) ? S2::M : S1::M;
+
+    // shared memory of one warp, in float2 units
+    static constexpr int WARP_F2_H = rsp0 * kPitchT + (rsp1 + rsp2) * kPitchL + MLAST * kPitchT;
+    static constexpr int WARP_F2_V = rsp0 * kPitchL + (rsp1 + rsp2) * kPitchL;
+};
+
+// ---- small helpers ---------------------------------------------------------------------------------
+
+AVS_FN int imin_(int a, int b) { return a < b ? a : b; }
+AVS_FN int imax_(int a, int b) { return a > b ? a : b; }
+
+AVS_FN float2 f2mul(float t, float2 x) { return make_float2(__fmul_rn(t, x.x), __fmul_rn(t, x.y)); }
+AVS_FN float2 f2add(float2 a, float2 b) { return make_float2(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y)); }
+AVS_FN float2 f2hadd8(const float2* v) {
+    // float8::hadd (avir_float8_avx.h:264-273)
+    return f2add(f2add(f2add(v[0], v[4]), f2add(v[1], v[5])), f2add(f2add(v[2], v[6]), f2add(v[3], v[7])));
+}
+
+#if defined(__CUDACC__)
+AVS_FN void cp_async16(void* smem, const void* gmem) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
+}
+AVS_FN void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+AVS_FN void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+#else
+AVS_FN void cp_async16(void* smem, const void* gmem) { memcpy(smem, gmem, 16); }
+AVS_FN void cp_async_commit() {}
+template <int N>
+AVS_FN void cp_async_wait() {}
+#endif
+
+// First input position output j of a step reads.
+template <class S>
+AVS_FN int in_first(const StreamStep& sp, int j) {
+    if (S::KIND == K_FIR) return (j - sp.edge) * S::ADV - sp.latency;
+    if (S::KIND == K_RESIZE) return sp.sp_first + S::ADV * j - (S::NT / 2 - 1);
+    const int pv = sp.sp_first + j - (S::NT / 2 - 1); // virtual (2X) position
+    return (pv + (pv & 1)) >> 1;
+}
+
+// ---- arithmetic of one output from a register window (x[off ...]) ------------------------------
+
+template <class S, class X>
+AVS_FN float2 fir_one(const X& x, const int off, const float* t) {
+    if (S::SUM == AVIRB200_SUM_DIL8) {
+        float2 ln[8];
+#pragma unroll
+        for (int g = 0; g < S::NT / 8; ++g) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const float2 v = f2mul(t[g * 8 + q], x[off + g * 8 + q]);
+                ln[q] = (g == 0) ? v : f2add(ln[q], v);
+            }
+        }
+        return f2hadd8(ln);
+    }
+    constexpr int L = S::NT / 2;
+    float2 s = f2mul(t[L], x[off + L]);
+#pragma unroll
+    for (int i = 1; i <= L; ++i) s = f2add(s, f2mul(t[L + i], f2add(x[off + L + i], x[off + L - i])));
+    return s;
+}
+
+template <class S, class X>
+AVS_FN float2 resize_one(const X& x, const int off, const float* t, int zero_start) {
+    float2 r;
+    if (S::SUM == AVIRB200_SUM_DIL8) {
+        float2 ln[8];
+#pragma unroll
+        for (int g = 0; g < S::NT / 8; ++g) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const float2 v = f2mul(t[g * 8 + q], x[off + g * 8 + q]);
+                ln[q] = (g == 0) ? v : f2add(ln[q], v);
+            }
+        }
+        r = f2hadd8(ln);
+    } else {
+        r = f2mul(t[0], x[off]);
+#pragma unroll
+        for (int i = 1; i < S::NT; ++i) r = f2add(r, f2mul(t[i], x[off + i]));
+    }
+    if (zero_start) r = f2add(r, make_float2(0.0f, 0.0f));
+    return r;
+}
+
+// fo = parity of the output's first virtual position = index of its first tap
+template <class S, class X>
+AVS_FN float2 resize2_one(const X& x, const int off, const int fo, const float* t, int zero_start) {
+    float2 r = f2mul(t[fo], x[off]);
+#pragma unroll
+    for (int k = 1; k < S::NT / 2; ++k) r = f2add(r, f2mul(t[fo + 2 * k], x[off + k]));
+    if (zero_start) r = f2add(r, make_float2(0.0f, 0.0f));
+    return r;
+}
+
+// ---- output stage ---------------------------------------------------------------------------------------
+
+AVS_FN float epilogue_value(const StreamParams& p, float v, int c) {
+    if (p.gamma_out) {
+        if (c == p.alpha_index) v = __fmul_rn(v, p.out_gamma_mult);
+        else v = __fmul_rn(lin2srgb(v), p.out_gamma_mult);
+    }
+    if (p.dst_type != AVIRB200_F32) {
+        if (p.tr_mul == 1.0f) v = round_out(v, p.round_mode);
+        else v = __fmul_rn(round_out(__fmul_rn(v, p.tr_mul_inv), p.round_mode), p.tr_mul);
+        v = v < 0.0f ? 0.0f : (v > p.pk_out ? p.pk_out : v);
+    }
+    return v;
+}
+
+// ---- per-warp state of a run -------------------------------------------------------------------------
+
+template <class C, bool IS_V>
+struct WarpRun {
+    float2* ring0;  // source ring
+    float2* ring1;
+    float2* ring2;
+    float2* stage;  // row pass: transposition buffer of the final batch
+    int lane, line0, nlines;
+    int o0;         // source position held by slot 0 of ring 0
+    int a[kMaxSteps];   // output index of batch 0 of every step (= origin of the next ring)
+    int rd[kMaxSteps];  // read slot (positions) of each step in its input ring
+    int wr[kMaxSteps];  // write slot of each step in its output ring
+    int kb[kMaxSteps];  // batches done
+};
+
+template <class C, bool IS_V, int I>
+struct RingOf {
+    static constexpr int RSP = (I == 0) ? C::rsp0 : (I == 1 ? C::rsp1 : C::rsp2);
+    static constexpr int PITCH = (I == 0) ? (IS_V ? kPitchL : kPitchT) : kPitchL;
+};
+
+// ---- source loader: one group of SRC_N positions, 16 positions x 16 lines per sweep --------------
+
+template <class C, bool IS_V>
+AVS_FN void load_group(const StreamParams& p, const WarpRun<C, IS_V>& w, int g, int gslot) {
+    constexpr int PITCH = RingOf<C, IS_V, 0>::PITCH;
+    const int lane = w.lane;
+    const float* src = static_cast<const float*>(p.src);
+#pragma unroll
+    for (int q = 0; q < C::SRC_N / 16; ++q) {
+        const int pos0 = w.o0 + g * C::SRC_N + q * 16; // first source position of the sweep
+        float2* ring = w.ring0 + (size_t)(gslot + q * 16) * PITCH;
+        if (IS_V) {
+            // a position is an intermediate row; the warp's 16 pixel columns are 256 contiguous bytes
+            const int piece = lane & 15, rsub = lane >> 4;
+            const float4* col = reinterpret_cast<const float4*>(src) + w.line0 + imin_(piece, w.nlines - 1);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int row = rsub + 2 * k;
+                const int y = imin_(imax_(pos0 + row, 0), p.src_len - 1) - p.src_row_base;
+                cp_async16(ring + row * PITCH + piece * 2, col + (size_t)y * (size_t)(p.src_pitch / 4));
+            }
+        } else {
+            // a position is a pixel of a row: 16 consecutive pixels of one row per half warp
+            const int pos = lane & 15, lsub = lane >> 4;
+            const int x = imin_(imax_(pos0 + pos, 0), p.src_len - 1);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int line = lsub + 2 * k;
+                const float4* row = reinterpret_cast<const float4*>(
+                    src + (size_t)(w.line0 + imin_(line, w.nlines - 1)) * (size_t)p.src_pitch);
+                cp_async16(ring + pos * PITCH + line * 2, row + x);
+            }
+        }
+    }
+}
+
+// ---- per-output path for batches at the ends of a line ------------------------------------------------
+// Reads the input ring by absolute position, each tap clamped to [lo, hi].
+
+template <class C, bool IS_V, int I, class S>
+AVS_FN float2 slow_one(const StreamStep& sp, const float2* ring, int origin, int j, int lo, int hi) {
+    constexpr int RSP = RingOf<C, IS_V, I>::RSP;
+    constexpr int PITCH = RingOf<C, IS_V, I>::PITCH;
+    float2 x[S::NTW];
+    const int p0 = in_first<S>(sp, j);
+#pragma unroll
+    for (int t = 0; t < S::NTW; ++t) {
+        const int pos = imin_(imax_(p0 + t, lo), hi);
+        x[t] = ring[(size_t)((unsigned)(pos - origin) % (unsigned)RSP) * PITCH];
+    }
+    if (S::KIND == K_FIR) return fir_one<S>(x, 0, sp.taps);
+    if (S::KIND == K_RESIZE) return resize_one<S>(x, 0, sp.taps, sp.zero_start);
+    const int pv = sp.sp_first + j - (S::NT / 2 - 1);
+    return (pv & 1) ? resize2_one<S>(x, 0, 1, sp.taps, sp.zero_start)
+                    : resize2_one<S>(x, 0, 0, sp.taps, sp.zero_start);
+}
+
+// ---- final outputs -------------------------------------------------------------------------------------
+
+// Column pass: lane = (pixel column, channel pair); a batch is M destination rows.
+template <class C, int EPI, int M>
+AVS_FN void sink_v(const StreamParams& p, const WarpRun<C, true>& w, int j0, const float2* o) {
+    const int q = w.lane >> 1, c0 = (w.lane & 1) * 2;
+    if (q >= w.nlines) return;
+    const size_t esz = (p.dst_type == AVIRB200_F32) ? 4 : (p.dst_type == AVIRB200_U16 ? 2 : 1);
+    unsigned char* g0 = static_cast<unsigned char*>(p.dst) + ((size_t)(w.line0 + q) * 4 + c0) * esz;
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+        const int j = j0 + m;
+        if (j < p.out0 || j >= p.out1) continue;
+        unsigned char* g = g0 + (size_t)(j - p.dst_row_base) * (size_t)p.dst_pitch * esz;
+        float2 v = o[m];
+        if (EPI == 1) {
+            *reinterpret_cast<float2*>(g) = v;
+            continue;
+        }
+        v.x = epilogue_value(p, v.x, c0);
+        v.y = epilogue_value(p, v.y, c0 + 1);
+        if (p.dst_type == AVIRB200_F32) *reinterpret_cast<float2*>(g) = v;
+        else if (p.dst_type == AVIRB200_U8)
+            *reinterpret_cast<uchar2*>(g) = make_uchar2((unsigned char)v.x, (unsigned char)v.y);
+        else
+            *reinterpret_cast<ushort2*>(g) = make_ushort2((unsigned short)v.x, (unsigned short)v.y);
+    }
+}
+
+// Row pass: lanes hold (line, channel pair) of M consecutive pixels; transposed through the
+// staging rows so that every store instruction writes runs of whole pixels of a row.
+template <class C, int M>
+AVS_FN void sink_h(const StreamParams& p, const WarpRun<C, false>& w, int j0, const float2* o) {
+    AVS_SYNCWARP(); // the previous batch's staging reads are done
+#pragma unroll
+    for (int m = 0; m < M; ++m) w.stage[m * kPitchT + w.lane] = o[m];
+    AVS_SYNCWARP();
+    const int pos = w.lane & (M - 1), lsub = w.lane / M;
+    const int j = j0 + pos;
+    float* dst = static_cast<float*>(p.dst);
+#pragma unroll
+    for (int k = 0; k < M / 2; ++k) {
+        const int line = lsub + (32 / M) * k;
+        const float4 v = *reinterpret_cast<const float4*>(w.stage + pos * kPitchT + line * 2);
+        if (line < w.nlines && j >= p.out0 && j < p.out1)
+            reinterpret_cast<float4*>(dst + (size_t)(w.line0 + line) * (size_t)p.dst_pitch)[j] = v;
+    }
+}
+
+// ---- one batch of one step ------------------------------------------------------------------------------
+
+template <class C, bool IS_V, int EPI, int I, class S>
+AVS_FN void run_batch(const StreamParams& p, WarpRun<C, IS_V>& w) {
+    constexpr bool LAST = (I == C::NS - 1);
+    constexpr int RSP = RingOf<C, IS_V, I>::RSP;
+    constexpr int PITCH = RingOf<C, IS_V, I>::PITCH;
+    constexpr int M = S::M;
+    const StreamStep& sp = p.s[I];
+    const int j0 = w.a[I] + M * w.kb[I];
+    const float2* ring = ((I == 0) ? w.ring0 : (I == 1 ? w.ring1 : w.ring2)) + w.lane;
+    const int origin = (I == 0) ? w.o0 : w.a[I - 1];
+    const int rd = w.rd[I];
+    const int wr = w.wr[I];
+    // advance the ring cursors first (uniform bookkeeping, also for skipped batches)
+    w.kb[I] += 1;
+    w.rd[I] = (rd + S::CH == RSP) ? 0 : rd + S::CH;
+
+    float2 o[M];
+    bool have = true;
+    const int pin = in_first<S>(sp, j0);
+    const bool in_dom = (j0 >= 0) && (j0 + M <= sp.out_len);
+    const bool win_ok = (I == 0) || (pin >= 0 && pin + S::W <= sp.in_len);
+    if (j0 + M <= 0 || j0 >= sp.out_len) {
+        have = false; // nothing of this batch exists
+    } else if (in_dom && win_ok) {
+        // the window never wraps inside a piece of CH positions: pieces are ring-aligned
+        const float2* base[(S::W + S::CH - 1) / S::CH + 1];
+#pragma unroll
+        for (int k = 0; k < (S::W + S::CH - 1) / S::CH; ++k) {
+            int s = rd + k * S::CH;
+            if (s >= RSP) s -= RSP;
+            base[k] = ring + (size_t)s * PITCH;
+        }
+        if (S::KIND == K_RESIZE2) {
+            float2 x[S::W];
+#pragma unroll
+            for (int i = 0; i < S::W; ++i) x[i] = base[i / S::CH][(i % S::CH) * PITCH];
+            const int pv = sp.sp_first + j0 - (S::NT / 2 - 1);
+            if (pv & 1) {
+#pragma unroll
+                for (int m = 0; m < M; ++m)
+                    o[m] = resize2_one<S>(x, m >> 1, (m & 1) ? 0 : 1, sp.taps, sp.zero_start);
+            } else {
+#pragma unroll
+                for (int m = 0; m < M; ++m)
+                    o[m] = resize2_one<S>(x, (m + 1) >> 1, m & 1, sp.taps, sp.zero_start);
+            }
+        } else {
+#pragma unroll
+            for (int sb = 0; sb < M / S::MS; ++sb) {
+                float2 x[S::WS];
+#pragma unroll
+                for (int i = 0; i < S::WS; ++i) {
+                    const int wi = sb * S::MS * S::ADV + i; // index in the batch window
+                    x[i] = base[wi / S::CH][(wi % S::CH) * PITCH];
+                }
+#pragma unroll
+                for (int m = 0; m < S::MS; ++m) {
+                    if (S::KIND == K_FIR) o[sb * S::MS + m] = fir_one<S>(x, m * S::ADV, sp.taps);
+                    else o[sb * S::MS + m] = resize_one<S>(x, m * S::ADV, sp.taps, sp.zero_start);
+                }
+            }
+        }
+    } else {
+        const int lo = (I == 0) ? -0x40000000 : 0;
+        const int hi = (I == 0) ? 0x40000000 : sp.in_len - 1;
+#pragma unroll 1
+        for (int m = 0; m < M; ++m) {
+            const int j = j0 + m;
+            float2 v = make_float2(0.0f, 0.0f);
+            if (j >= 0 && j < sp.out_len) v = slow_one<C, IS_V, I, S>(sp, ring, origin, j, lo, hi);
+            // (a register array indexed by the loop counter: keep the loop rolled, select by value)
+#pragma unroll
+            for (int mm = 0; mm < M; ++mm)
+                if (mm == m) o[mm] = v;
+        }
+    }
+
+    if (!LAST) {
+        constexpr int RSPO = RingOf<C, IS_V, I + 1>::RSP;
+        constexpr int PITCHO = RingOf<C, IS_V, I + 1>::PITCH;
+        w.wr[I] = (wr + M == RSPO) ? 0 : wr + M;
+        if (have) {
+            float2* out = ((I == 0) ? w.ring1 : w.ring2) + w.lane + (size_t)wr * PITCHO;
+#pragma unroll
+            for (int m = 0; m < M; ++m) out[m * PITCHO] = o[m];
+        }
+    } else if (have) {
+        if constexpr (IS_V) sink_v<C, EPI, M>(p, w, j0, o);
+        else sink_h<C, M>(p, w, j0, o);
+    }
+}
+
+// ---- one run: `rounds` rounds of B final outputs of one 16-line strip -----------------------------
+
+template <class C, bool IS_V, int EPI>
+AVS_FN void run_warp(const StreamParams& p, WarpRun<C, IS_V>& w, int strip, int rho0, int rounds) {
+    using S0 = typename C::T0;
+    using S1 = typename C::T1;
+    using S2 = typename C::T2;
+    w.line0 = strip * kLines;
+    w.nlines = imin_(kLines, p.n_lines - w.line0);
+    if (C::NS == 3) {
+        w.a[2] = C::B * rho0;
+        w.a[1] = in_first<S2>(p.s[2], w.a[2]);
+    } else {
+        w.a[1] = C::B * rho0;
+    }
+    w.a[0] = in_first<S1>(p.s[1], w.a[1]);
+    w.o0 = in_first<S0>(p.s[0], w.a[0]);
+#pragma unroll
+    for (int i = 0; i < kMaxSteps; ++i) w.rd[i] = w.wr[i] = w.kb[i] = 0;
+
+    const int total = rounds + C::DELAY_LAST;  // wall rounds; step 0 runs all of them
+    const int groups = total + C::H;           // source groups step 0 reads
+    int gslot = 0;
+    constexpr int PRO = C::H + C::LOOKAHEAD;
+    for (int g = 0; g < PRO; ++g) {
+        if (g < groups) load_group<C, IS_V>(p, w, g, gslot);
+        cp_async_commit();
+        gslot = (gslot + C::SRC_N == C::rsp0) ? 0 : gslot + C::SRC_N;
+    }
+    for (int r = 0; r < total; ++r) {
+        cp_async_wait<C::LOOKAHEAD - 1>(); // groups <= r + H have landed (this lane's copies)
+        AVS_SYNCWARP();                    // ... all lanes'; and round r-1 is done with its slots
+        if (r + PRO < groups) load_group<C, IS_V>(p, w, r + PRO, gslot);
+        cp_async_commit();
+        gslot = (gslot + C::SRC_N == C::rsp0) ? 0 : gslot + C::SRC_N;
+
+#pragma unroll
+        for (int q = 0; q < C::reps0; ++q) run_batch<C, IS_V, EPI, 0, S0>(p, w);
+        if (r >= C::delay1) {
+#pragma unroll
+            for (int q = 0; q < C::reps1; ++q) run_batch<C, IS_V, EPI, 1, S1>(p, w);
+        }
+        if constexpr (C::NS == 3) {
+            if (r >= C::delay2) {
+#pragma unroll
+                for (int q = 0; q < C::reps2; ++q) run_batch<C, IS_V, EPI, 2, S2>(p, w);
+            }
+        }
+    }
+    cp_async_wait<0>();
+    AVS_SYNCWARP(); // the next run refills the rings
+}
+
+// ---- a warp's share of the pass -------------------------------------------------------------------------
+// Units = rounds of B final outputs, strip-major; every warp takes an equal contiguous share.
+
+template <class C, bool IS_V, int EPI>
+AVS_FN void stream_warp_main(const StreamParams& p, long long gw, long long nwarps, int lane, float2* sm) {
+    WarpRun<C, IS_V> w;
+    w.lane = lane;
+    w.ring0 = sm;
+    w.ring1 = w.ring0 + (size_t)C::rsp0 * RingOf<C, IS_V, 0>::PITCH;
+    w.ring2 = w.ring1 + (size_t)C::rsp1 * kPitchL;
+    w.stage = w.ring2 + (size_t)C::rsp2 * kPitchL;
+    const int rho_first = p.out0 / C::B, rho_last = (p.out1 - 1) / C::B;
+    const int rps = rho_last - rho_first + 1;
+    const int nstrips = (p.n_lines + kLines - 1) / kLines;
+    const long long units = (long long)nstrips * rps;
+    long long u0 = gw * units / nwarps;
+    const long long u1 = (gw + 1) * units / nwarps;
+    while (u0 < u1) {
+        const int strip = (int)(u0 / rps);
+        const int r0 = (int)(u0 - (long long)strip * rps);
+        const long long left = u1 - u0;
+        const int rounds = (left < (long long)(rps - r0)) ? (int)left : rps - r0;
+        run_warp<C, IS_V, EPI>(p, w, strip, rho_first + r0, rounds);
+        u0 += rounds;
+    }
+}
+
+#if defined(__CUDACC__)
+template <class C, bool IS_V, int EPI, int NW>
+__global__ void __launch_bounds__(NW * 32, 1) stream_pass_kernel(const __grid_constant__ StreamParams p) {
+    extern __shared__ __align__(16) unsigned char stream_smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float2* sm = reinterpret_cast<float2*>(stream_smem) + (size_t)warp * (IS_V ? C::WARP_F2_V : C::WARP_F2_H);
+    stream_warp_main<C, IS_V, EPI>(p, (long long)blockIdx.x * NW + warp, (long long)gridDim.x * NW, lane, sm);
+}
+#endif
+
+// ---- the chains ------------------------------------------------------------------------------------------
+// (kind, summation, taps, advance) per step; final batches per round; source look-ahead in rounds.
+
+// cfg3, float8_dil mirror (k = 2): RESIZE(24 taps, source step 2) -> 8-tap correction FIR.
+// The row pass carries the 272-byte transposition pitch and the staging rows, so it looks
+// two rounds ahead where the column pass affords three (8 warps per SM either way).
+using ChainDil24H = ChainC<StepC<K_RESIZE, AVIRB200_SUM_DIL8, 24, 2>, StepC<K_FIR, AVIRB200_SUM_DIL8, 8, 1>,
+                           NoStep, 1, 2>;
+using ChainDil24V = ChainC<StepC<K_RESIZE, AVIRB200_SUM_DIL8, 24, 2>, StepC<K_FIR, AVIRB200_SUM_DIL8, 8, 1>,
+                           NoStep, 1, 3>;
+
+template <class C>
+struct ChainTag {
+    using type = C;
+};
+
+// Calls f(ChainTag<row-pass chain>(), ChainTag<column-pass chain>()) for chain `id`.
+template <class F>
+inline bool stream_dispatch(int id, F&& f) {
+    switch (id) {
+    case kChainDil24: f(ChainTag<ChainDil24H>(), ChainTag<ChainDil24V>()); return true;
+    default: return false;
+    }
+}
+
+} // namespace avs

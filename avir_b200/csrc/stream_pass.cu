@@ -1,0 +1,57 @@
+// stream_pass.cu -- instantiations and launch of the warp-streaming pass kernel
+// (stream_kernel.cuh); kept in its own translation unit so that the chain kernels compile
+// in parallel with engine.cu.
+#include <cuda_runtime.h>
+
+#include "stream_kernel.cuh"
+#include "stream_launch.h"
+
+namespace avs {
+
+namespace {
+
+constexpr int kStreamWarps = 8;
+
+int sm_count() {
+    static const int sms = [] {
+        int d = 0, n = 0;
+        cudaGetDevice(&d);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d);
+        return n > 0 ? n : 1;
+    }();
+    return sms;
+}
+
+template <class C, bool IS_V, int EPI>
+int launch_one(const StreamParams& p, cudaStream_t st) {
+    constexpr int NW = kStreamWarps;
+    constexpr size_t smem = (size_t)NW * (IS_V ? C::WARP_F2_V : C::WARP_F2_H) * sizeof(float2);
+    static_assert(smem <= 227 * 1024, "per-warp rings do not fit the shared memory of an SM");
+    auto kern = stream_pass_kernel<C, IS_V, EPI, NW>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        return -1;
+    // one persistent block per SM; fewer when the pass has fewer rounds than warps
+    const long long rps = (long long)(p.out1 - 1) / C::B - p.out0 / C::B + 1;
+    const long long units = rps * ((p.n_lines + kLines - 1) / kLines);
+    long long blocks = (units + NW - 1) / NW;
+    if (blocks > sm_count()) blocks = sm_count();
+    if (blocks < 1) return 0;
+    kern<<<(int)blocks, NW * 32, smem, st>>>(p);
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+} // namespace
+
+int stream_launch(int chain, bool is_v, bool plain_f32, const StreamParams& p, void* stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int rc = -2;
+    const bool known = stream_dispatch(chain, [&](auto htag, auto vtag) {
+        using CH = typename decltype(htag)::type;
+        using CV = typename decltype(vtag)::type;
+        if (!is_v) rc = launch_one<CH, false, 0>(p, st);
+        else rc = plain_f32 ? launch_one<CV, true, 1>(p, st) : launch_one<CV, true, 0>(p, st);
+    });
+    return known ? rc : -2;
+}
+
+} // namespace avs

@@ -1,0 +1,160 @@
+// stream_types.h -- kernel parameters and host-side planning of the warp-streaming pass
+// kernel (stream_kernel.cuh): decides whether an axis of a plan is one of the regular chains
+// the kernel is instantiated for and folds the resize step's single effective phase into
+// kernel-parameter taps.  Pure host code without CUDA calls: the engine (engine.cu) and the
+// lockstep emulation used by the CPU tests (tests/emul) share it.
+#pragma once
+
+#include <stdint.h>
+#include <string.h>
+
+#include "avirb200.h"
+
+namespace avs {
+
+constexpr int kMaxSteps = 3;
+enum { K_FIR = 0, K_RESIZE = 1, K_RESIZE2 = 2, K_NONE = 3 };
+
+// Run-time description of one step (kernel parameters: taps are constant-bank operands).
+struct StreamStep {
+    int out_len, in_len;
+    int edge, latency;  // FIR
+    int sp_first;       // RESIZE/RESIZE2: source position of output 0 (position j: sp_first + ADV*j)
+    int zero_start;
+    float taps[64];
+};
+
+struct StreamParams {
+    StreamStep s[kMaxSteps];
+    int n_lines;          // rows (row pass) or pixel columns (column pass)
+    int src_len;          // positions of the source line
+    int out0, out1;       // final outputs [out0, out1) to produce
+    const void* src;      // fp32, 4 interleaved channels
+    long long src_pitch;  // elements between rows
+    int src_row_base;     // column pass: global row held by source row 0 (shards)
+    void* dst;
+    long long dst_pitch;
+    int dst_type, dst_row_base;
+    int gamma_out, alpha_index;
+    float out_gamma_mult;
+    int round_mode;
+    float tr_mul, tr_mul_inv, pk_out;
+};
+
+enum StreamChainId {
+    kChainNone = 0,
+    kChainDil24, // RESIZE(24, D2) -> FIR8                 cfg3, float8_dil mirror (k = 2)
+    kChainCount
+};
+
+struct StreamAxisPlan {
+    int chain = kChainNone;
+    int nsteps = 0;
+    int src_len = 0, dst_len = 0;
+    StreamStep s[kMaxSteps];
+};
+
+// What the compile-time chains expect of each step (mirrors the StepC arguments).
+struct StepSpec {
+    int kind, sum, nt, adv;
+};
+
+inline const StepSpec* chain_spec(int id, int* nsteps) {
+    static const StepSpec dil24[] = {{K_RESIZE, AVIRB200_SUM_DIL8, 24, 2}, {K_FIR, AVIRB200_SUM_DIL8, 8, 1}};
+    switch (id) {
+    case kChainDil24: *nsteps = 2; return dil24;
+    default: *nsteps = 0; return nullptr;
+    }
+}
+
+// Fills `out` from one descriptor step if it has the shape `sp` asks for.
+inline bool stream_match_step(const avirb200_step_desc& d, const StepSpec& sp, StreamStep& out) {
+    memset(&out, 0, sizeof out);
+    out.out_len = d.out_len;
+    out.in_len = d.in_len;
+    out.zero_start = d.zero_start;
+    if (sp.kind == K_FIR) {
+        if (d.kind != AVIRB200_STEP_FIR || d.ntaps != sp.nt || d.resample != sp.adv) return false;
+        if (sp.sum == AVIRB200_SUM_INL && d.ntaps != 2 * d.latency + 1) return false;
+        out.edge = d.edge;
+        out.latency = d.latency;
+        for (int t = 0; t < d.ntaps; ++t) out.taps[t] = d.taps[t];
+        return true;
+    }
+    if (d.kind != AVIRB200_STEP_RESIZE || d.ntaps != sp.nt || d.ntaps > 64 || d.out_len < 1) return false;
+    if (sp.kind == K_RESIZE && d.upsampled) return false;
+    if (sp.kind == K_RESIZE2 && !(d.upsampled && d.skip_odd)) return false;
+    const int step = (sp.kind == K_RESIZE2) ? 1 : sp.adv;
+    uint32_t f0 = 0;
+    if (d.order) memcpy(&f0, &d.frac[0], 4);
+    for (int j = 0; j < d.out_len; ++j) {
+        if (d.src_pos[j] != d.src_pos[0] + step * j) return false; // constant source step
+        if (d.phase[j] != d.phase[0]) return false;                // one effective phase
+        if (d.order) {
+            uint32_t fj;
+            memcpy(&fj, &d.frac[j], 4);
+            if (fj != f0) return false;
+        }
+    }
+    out.sp_first = d.src_pos[0];
+    // effective taps c0 + c1*x: the two float operations upstream performs per tap
+    // (avir.h:3945, avir_dil.h:649-650)
+    const float* c0 = d.taps + (size_t)d.phase[0] * d.ntaps * (d.order + 1);
+    for (int t = 0; t < d.ntaps; ++t) {
+        if (d.order) {
+            volatile float prod = c0[d.ntaps + t] * d.frac[0];
+            out.taps[t] = c0[t] + prod;
+        } else {
+            out.taps[t] = c0[t];
+        }
+    }
+    return true;
+}
+
+// Decides whether the axis runs on the streaming kernel; on success `out` holds everything
+// the kernel parameters need.
+inline bool stream_plan_axis(const avirb200_axis_desc& ad, int sum_mode, int channels, StreamAxisPlan& out) {
+    out.chain = kChainNone;
+    if (channels != 4) return false;
+    for (int id = 1; id < kChainCount; ++id) {
+        int ns = 0;
+        const StepSpec* spec = chain_spec(id, &ns);
+        if (ns != ad.nsteps) continue;
+        bool ok = true;
+        int prev = ad.src_len;
+        for (int i = 0; i < ns && ok; ++i) {
+            ok = (spec[i].sum == sum_mode) && ad.steps[i].in_len == prev &&
+                 stream_match_step(ad.steps[i], spec[i], out.s[i]);
+            prev = ad.steps[i].out_len;
+        }
+        if (!ok || prev != ad.dst_len) continue;
+        out.chain = id;
+        out.nsteps = ns;
+        out.src_len = ad.src_len;
+        out.dst_len = ad.dst_len;
+        return true;
+    }
+    return false;
+}
+
+// The row pass streams raw fp32 pixels into shared memory (cp.async): sources that need a
+// conversion on the way in (integer types, sRGB linearisation) stay on the tile kernel.
+inline bool stream_row_source_ok(const avirb200_plan_desc& d) {
+    return d.in_type == AVIRB200_F32 && !(d.use_gamma & 1);
+}
+
+// Kernel parameters of one pass (the caller fills the image pointers / bases).
+inline void stream_fill_params(StreamParams& p, const StreamAxisPlan& ap, const avirb200_plan_desc& d) {
+    memset(&p, 0, sizeof p);
+    for (int i = 0; i < ap.nsteps; ++i) p.s[i] = ap.s[i];
+    p.src_len = ap.src_len;
+    p.gamma_out = (d.use_gamma & 2) ? 1 : 0;
+    p.alpha_index = d.alpha_index;
+    p.out_gamma_mult = d.out_gamma_mult;
+    p.round_mode = d.round_mode;
+    p.tr_mul = d.tr_mul;
+    p.tr_mul_inv = d.tr_mul_inv;
+    p.pk_out = d.pk_out;
+}
+
+} // namespace avs

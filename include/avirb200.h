@@ -186,8 +186,14 @@ int avirb200_resize_sharded_local(const avirb200_plan* plan, int nranks, const v
                                   size_t src_pitch, void* d_dst, size_t dst_pitch,
                                   void* d_workspace, void* stream);
 
-/* Test switch: 1 = always use the fully generic pass kernel (skip specialised kernels). */
-void avirb200_debug_force_generic(int on);
+/* Test switch selecting the kernel family: 0 = product order (streaming kernel where the
+ * chain is regular, else the tile kernel, else the generic kernel); 1 = generic kernel only;
+ * 2 = tile kernel, else generic (no streaming kernel). */
+void avirb200_debug_force_generic(int mode);
+
+/* Which specialised kernels the plan's passes qualify for: bit 0 / 1 = row / column pass on
+ * the warp-streaming kernel, bit 2 / 3 = row / column pass on the tile kernel. */
+int avirb200_plan_kernel_paths(const avirb200_plan* plan);
 
 /* ---- LANCIR (upstream lancir.h) ------------------------------------------------------- */
 

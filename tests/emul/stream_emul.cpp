@@ -1,0 +1,115 @@
+// stream_emul.cpp -- TEST INFRASTRUCTURE: lockstep host emulation of the warp-streaming pass
+// kernel (avir_b200/csrc/stream_kernel.cuh).
+//
+// The kernel source is compiled here for the host: a warp is 32 threads that meet at a
+// pthread barrier wherever the device code executes __syncwarp(), cp.async becomes an
+// immediate 16-byte copy, "shared memory" is a per-warp heap block.  The emulation exists so
+// that the kernel's index logic (rings, software-pipeline delays, run splitting, edge
+// batches, shard ranges) can be checked bit-for-bit against the oracle on a machine without
+// a GPU (tests/test_stream_emul.py).  It is never linked into libavirb200.so and is not a
+// CPU execution path of the product.
+//
+// Build: g++ -O2 -ffp-contract=off -std=c++17 -shared -fPIC (tests/emul/build.py).
+
+#include <pthread.h>
+#include <stdlib.h>
+
+#include <thread>
+#include <vector>
+
+static thread_local pthread_barrier_t* g_bar = nullptr;
+void avs_emul_syncwarp() { pthread_barrier_wait(g_bar); }
+
+#include "stream_kernel.cuh"
+
+using namespace avs;
+
+namespace {
+
+template <class C, bool IS_V, int EPI>
+void emul_pass(const StreamParams& p, int nwarps) {
+    const size_t sm_float2 = (size_t)(IS_V ? C::WARP_F2_V : C::WARP_F2_H);
+    for (int gw = 0; gw < nwarps; ++gw) {
+        std::vector<float2> sm(sm_float2);
+        // poison: reads of never-written slots must not go unnoticed
+        for (auto& v : sm) v = make_float2(__builtin_nanf(""), __builtin_nanf(""));
+        pthread_barrier_t bar;
+        pthread_barrier_init(&bar, nullptr, 32);
+        std::vector<std::thread> th;
+        for (int lane = 0; lane < 32; ++lane) {
+            th.emplace_back([&, lane] {
+                g_bar = &bar;
+                stream_warp_main<C, IS_V, EPI>(p, gw, nwarps, lane, sm.data());
+            });
+        }
+        for (auto& t : th) t.join();
+        pthread_barrier_destroy(&bar);
+    }
+}
+
+template <bool IS_V>
+bool emul_dispatch(int chain, const StreamParams& p, int nwarps, bool plain) {
+    return stream_dispatch(chain, [&](auto htag, auto vtag) {
+        using CH = typename decltype(htag)::type;
+        using CV = typename decltype(vtag)::type;
+        if constexpr (IS_V) {
+            if (plain) emul_pass<CV, true, 1>(p, nwarps);
+            else emul_pass<CV, true, 0>(p, nwarps);
+        } else {
+            emul_pass<CH, false, 0>(p, nwarps);
+        }
+    });
+}
+
+} // namespace
+
+extern "C" {
+
+// 1 when both axes of the descriptor run on the streaming kernel (f32 source only).
+int stream_emul_applicable(const avirb200_plan_desc* d) {
+    StreamAxisPlan h, v;
+    return stream_row_source_ok(*d) && stream_plan_axis(d->h, d->sum_mode, d->channels, h) &&
+           stream_plan_axis(d->v, d->sum_mode, d->channels, v);
+}
+
+// Row pass with `warps_h` emulated warps, then the column pass in `bands` destination bands
+// (as the sharded schedule runs it) with `warps_v` warps each.
+int stream_emul_resize(const avirb200_plan_desc* d, const float* src, size_t src_pitch, void* dst,
+                       size_t dst_pitch, int warps_h, int warps_v, int bands) {
+    StreamAxisPlan h, v;
+    if (!stream_row_source_ok(*d) || !stream_plan_axis(d->h, d->sum_mode, d->channels, h) ||
+        !stream_plan_axis(d->v, d->sum_mode, d->channels, v))
+        return -4;
+    std::vector<float> mid((size_t)d->src_h * d->dst_w * 4);
+    StreamParams p;
+    stream_fill_params(p, h, *d);
+    p.n_lines = d->src_h;
+    p.out0 = 0;
+    p.out1 = d->dst_w;
+    p.src = src;
+    p.src_pitch = (long long)src_pitch;
+    p.dst = mid.data();
+    p.dst_pitch = (long long)d->dst_w * 4;
+    p.dst_type = AVIRB200_F32;
+    if (!emul_dispatch<false>(h.chain, p, warps_h, false)) return -4;
+
+    const bool plain = (d->out_type == AVIRB200_F32) && !(d->use_gamma & 2);
+    for (int b = 0; b < bands; ++b) {
+        stream_fill_params(p, v, *d);
+        p.n_lines = d->dst_w;
+        p.out0 = (int)((long long)d->dst_h * b / bands);
+        p.out1 = (int)((long long)d->dst_h * (b + 1) / bands);
+        if (p.out1 <= p.out0) continue;
+        p.src = mid.data();
+        p.src_pitch = (long long)d->dst_w * 4;
+        p.src_row_base = 0;
+        p.dst = dst;
+        p.dst_pitch = (long long)dst_pitch;
+        p.dst_type = d->out_type;
+        p.dst_row_base = 0;
+        if (!emul_dispatch<true>(v.chain, p, warps_v, plain)) return -4;
+    }
+    return 0;
+}
+
+} // extern "C"

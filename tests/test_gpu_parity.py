@@ -24,10 +24,11 @@ def expected(case, src):
     return cs.port_output(case, src)[0]
 
 
-@pytest.fixture(params=[0, 1], ids=["fast", "generic"])
+@pytest.fixture(params=[0, 2, 1], ids=["product", "tile", "generic"])
 def kernel_path(request):
-    """Every parity case runs through the specialised kernels (where they apply) and
-    through the fully generic kernel."""
+    """Every parity case runs in the product's kernel order (warp-streaming kernel where the
+    chain is regular, else the tile kernel, else the generic kernel), with the streaming
+    kernel switched off (tile kernel where it applies), and through the fully generic kernel."""
     ab.lib().avirb200_debug_force_generic(request.param)
     yield request.param
     ab.lib().avirb200_debug_force_generic(0)

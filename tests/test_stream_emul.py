@@ -1,0 +1,86 @@
+"""Index logic of the warp-streaming pass kernel, checked WITHOUT a GPU: the kernel source
+(avir_b200/csrc/stream_kernel.cuh) compiled for the host and executed in lockstep
+(tests/emul/stream_emul.cpp: 32 threads per warp meeting at every __syncwarp) against the
+oracle's C port executing the same plan descriptor.  Covers what differs from the tile
+kernel: per-warp rings and pipeline delays, run splitting over warps, batches at the ends
+of a line, ragged strips, destination bands of the sharded schedule.  The arithmetic itself
+is shared with the device build; the GPU parity tests (-m gpu) cover the real kernel."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import cases as cs
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+u8, u16, f32 = np.uint8, np.uint16, np.float32
+
+
+@pytest.fixture(scope="module")
+def emul():
+    from avir_b200 import build as b
+    lib = C.CDLL(b.build_emul())
+    lib.stream_emul_resize.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t,
+                                       C.c_int, C.c_int, C.c_int]
+    lib.stream_emul_resize.restype = C.c_int
+    lib.stream_emul_applicable.argtypes = [C.c_void_p]
+    lib.stream_emul_applicable.restype = C.c_int
+    return lib
+
+
+# (case, emulated warps of the row pass, of the column pass, destination bands)
+EMUL_CASES = [
+    ((2, 192, 108, 96, 54, 4, f32, f32, 16, {"buildmode": 1}), 3, 2, 1),   # cfg3 chain, scaled down
+    ((2, 192, 108, 96, 54, 4, f32, f32, 16, {}), 1, 1, 1),
+    ((2, 384, 216, 192, 108, 4, f32, f32, 16, {}), 7, 5, 3),             # runs split inside strips
+    ((2, 100, 70, 50, 35, 4, f32, f32, 16, {"buildmode": 1}), 4, 3, 2),   # ragged strips and batches
+    ((2, 100, 70, 50, 35, 4, f32, u8, 8, {"buildmode": 1}), 4, 3, 2),     # integer output stage
+    ((2, 100, 70, 50, 35, 4, f32, u16, 16, {"buildmode": 1}), 2, 2, 1),
+    ((2, 20, 18, 10, 9, 4, f32, f32, 16, {"buildmode": 1}), 2, 2, 2),     # shorter than the pipeline
+    ((2, 34, 6, 17, 3, 4, f32, f32, 16, {"buildmode": 1}), 1, 40, 1),     # more warps than rounds
+    ((2, 640, 40, 320, 20, 4, f32, f32, 16, {"buildmode": 1}), 9, 2, 5),
+]
+
+
+def _id(ec):
+    return "%s-w%d-%d-b%d" % (cs.case_id(ec[0]), ec[1], ec[2], ec[3])
+
+
+@pytest.mark.parametrize("ec", EMUL_CASES, ids=_id)
+def test_stream_kernel_emulation_matches_port(emul, ec):
+    case, wh, wv, bands = ec
+    fp, sw, sh, nw, nh, ch, ti, to, rb, kw = case
+    src = cs.make_input(case)
+    rs, v = cs.resizer_and_vars(case)
+    h, dp, modes = rs.descriptor(src.shape, src.dtype, nw, nh, to, kw.get("k", 0.0), v)
+    try:
+        assert emul.stream_emul_applicable(dp) == 1, "chain not on the streaming kernel: %r" % (modes,)
+        got = np.zeros((nh, nw, ch), to)
+        assert emul.stream_emul_resize(dp, src.ctypes.data, sw * ch, got.ctypes.data, nw * ch, wh, wv, bands) == 0
+    finally:
+        rs.free_descriptor(h)
+    want, _ = cs.port_output(case, src)
+    assert cs.count_mismatch(want, got) == 0
+
+
+def test_converted_sources_stay_on_the_tile_kernel(emul):
+    # input gamma needs a conversion between global and shared memory: not a cp.async stream
+    case = (2, 100, 70, 50, 35, 4, f32, u16, 16, {"buildmode": 1, "gamma": True, "alpha": 3})
+    rs, v = cs.resizer_and_vars(case)
+    h, dp, modes = rs.descriptor((70, 100, 4), f32, 50, 35, u16, 0.0, v)
+    try:
+        assert emul.stream_emul_applicable(dp) == 0
+    finally:
+        rs.free_descriptor(h)
+
+
+def test_irregular_chains_stay_on_the_tile_kernel(emul):
+    # non-integer ratio: positions are irregular and phases vary -> not a streaming chain
+    case = (2, 150, 90, 100, 55, 4, f32, f32, 16, {"buildmode": 1})
+    rs, v = cs.resizer_and_vars(case)
+    h, dp, modes = rs.descriptor((90, 150, 4), f32, 100, 55, f32, 0.0, v)
+    try:
+        assert emul.stream_emul_applicable(dp) == 0
+    finally:
+        rs.free_descriptor(h)
