@@ -32,6 +32,7 @@
 #pragma once
 
 #include <cuda_runtime.h>
+#include <stddef.h>
 #include <stdint.h>
 #include <string.h>
 
@@ -62,16 +63,24 @@ constexpr int kPitchL = 32;     // 256-byte rows where only the owning lane touc
 // ADV = input positions per output (FIR decimation R, RESIZE source step D).
 // RESIZE2 = resize over the virtual 2X zero-stuffed line, odd taps skipped (upstream
 // doResize2, avir.h:4114-4328): two outputs per input position.
-template <int KIND_, int SUM_, int NT_, int ADV_>
+template <int KIND_, int SUM_, int NT_, int ADV_, int ROLL_ = 1>
 struct StepC {
     static constexpr int KIND = KIND_, SUM = SUM_, NT = NT_, ADV = ADV_;
     static constexpr int M = (KIND == K_RESIZE2) ? 16 : 8;          // outputs per batch
     static constexpr int CH = (KIND == K_RESIZE2) ? 8 : 8 * ADV;    // input positions per batch
-    // sub-batch: outputs computed from one register window
-    static constexpr int MS = (KIND != K_RESIZE2 && NT + 7 * ADV > 48) ? 4 : M;
-    static constexpr int WS = (KIND == K_RESIZE2) ? 20 : NT + (MS - 1) * ADV; // window of a sub-batch
-    static constexpr int W = (KIND == K_RESIZE2) ? 20 : NT + (M - 1) * ADV;   // window of a batch
     static constexpr int NTW = (KIND == K_RESIZE2) ? NT / 2 : NT;   // inputs one output reads
+    // FIR / RESIZE keep their input window in a rolling register ring of two batches' worth
+    // of positions: every input is loaded from shared memory exactly once, LK positions
+    // before the first output that reads it (as far ahead as the ring and the batch's
+    // shared-memory window allow).
+    static constexpr bool ROLL = ROLL_ && (KIND == K_FIR || KIND == K_RESIZE);
+    static constexpr int RR = 2 * M * ADV;
+    static constexpr int WN = (KIND == K_RESIZE2) ? 20 : NT + (M - 1) * ADV; // window the batch needs
+    // a rolling batch leaves the ring loaded for the next one: it touches NT + LK + M*ADV positions
+    static constexpr int SLACK = ((WN + ADV + CH - 1) / CH) * CH - WN - ADV;
+    static constexpr int LK = !ROLL ? 0 : ((RR - NT < SLACK) ? RR - NT : SLACK);
+    static constexpr int W = ROLL ? WN + LK + ADV : WN;              // window the batch touches
+    static_assert(!ROLL || RR >= NT, "register ring shorter than the filter");
 };
 using NoStep = StepC<K_NONE, 0, 0, 1>;
 
@@ -81,13 +90,14 @@ constexpr int cdiv(int a, int b) { return (a + b - 1) / b; }
 //   reps[i]  batches of step i per round
 //   delay[i] rounds step i lags behind step 0
 //   rsp[i]   positions in the ring step i reads (ring 0 = source)
-template <class S0, class S1, class S2, int REPS_LAST, int LA>
+template <class S0, class S1, class S2, int REPS_LAST, int LA, int LPOS_ = 0>
 struct ChainC {
     using T0 = S0;
     using T1 = S1;
     using T2 = S2;
     static constexpr int NS = (S2::KIND == K_NONE) ? 2 : 3;
     static constexpr int LOOKAHEAD = LA;
+    static constexpr int LPOS = LPOS_; // source copies are issued 0: at the top of a round, 1: after step 0
     static constexpr int reps2 = (NS == 3) ? REPS_LAST : 0;
     static constexpr int reps1 = (NS == 3) ? (S2::CH * reps2) / S1::M : REPS_LAST;
     static constexpr int reps0 = (S1::CH * reps1) / S0::M;
@@ -235,7 +245,46 @@ struct WarpRun {
     int rd[kMaxSteps];  // read slot (positions) of each step in its input ring
     int wr[kMaxSteps];  // write slot of each step in its output ring
     int kb[kMaxSteps];  // batches done
+    int warm[kMaxSteps]; // batch number for which the step's register ring is loaded (-1: none)
+    // loader: one global pointer per cp.async of a sweep, advancing by 16 positions per sweep
+    // (registers that are only ever incremented: no write-after-read wait on the copy queue)
+    const float4* gp[8];
+    // row pass: the previous final batch, read back from the staging rows, waiting to be stored
+    float4 pend[C::MLAST / 2];
+    int pend_j0;
+    // rolling register rings of the input windows (compile-time indices only)
+    float2 xr0[C::T0::ROLL ? C::T0::RR : 1];
+    float2 xr1[C::T1::ROLL ? C::T1::RR : 1];
+    float2 xr2[C::T2::ROLL ? C::T2::RR : 1];
 };
+
+// View of a register ring: element i of the window that starts at slot OFF.
+template <int R, int OFF>
+struct RingView {
+    const float2* xr;
+    AVS_FN const float2& operator[](int i) const { return xr[(OFF + i) % R]; }
+};
+
+// One batch of a rolling step: M outputs; PH = parity of the batch number (the ring holds two
+// batches' worth of positions, so the window's slot offset alternates).  ld(i) reads input
+// position i of the batch window from shared memory.
+template <class S, int PH, class LD>
+AVS_FN void roll_batch(float2* xr, LD&& ld, bool cold, const StreamStep& sp, float2* o) {
+    constexpr int R = S::RR, OFF = PH * S::M * S::ADV, HELD = S::NT + S::LK;
+    if (cold) {
+#pragma unroll
+        for (int i = 0; i < HELD; ++i) xr[(OFF + i) % R] = ld(i);
+    }
+    const RingView<R, OFF> x{xr};
+#pragma unroll
+    for (int k = 0; k < S::M; ++k) {
+        if (S::KIND == K_FIR) o[k] = fir_one<S>(x, k * S::ADV, sp.taps);
+        else o[k] = resize_one<S>(x, k * S::ADV, sp.taps, sp.zero_start);
+        // positions [k*ADV, (k+1)*ADV) are dead now: refill their slots LK ahead of use
+#pragma unroll
+        for (int i = 0; i < S::ADV; ++i) xr[(OFF + HELD + k * S::ADV + i) % R] = ld(HELD + k * S::ADV + i);
+    }
+}
 
 template <class C, bool IS_V, int I>
 struct RingOf {
@@ -246,35 +295,69 @@ struct RingOf {
 // ---- source loader: one group of SRC_N positions, 16 positions x 16 lines per sweep --------------
 
 template <class C, bool IS_V>
-AVS_FN void load_group(const StreamParams& p, const WarpRun<C, IS_V>& w, int g, int gslot) {
+AVS_FN void loader_init(const StreamParams& p, WarpRun<C, IS_V>& w) {
+    const float4* src = static_cast<const float4*>(p.src);
+    const size_t pitch4 = (size_t)(p.src_pitch / 4); // float4 units between rows
+    const int lane = w.lane;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        if (IS_V) {
+            const int piece = lane & 15, rsub = lane >> 4;
+            w.gp[k] = src + (ptrdiff_t)(w.o0 + rsub + 2 * k - p.src_row_base) * (ptrdiff_t)pitch4 + w.line0 +
+                      imin_(piece, w.nlines - 1);
+        } else {
+            const int pos = lane & 15, lsub = lane >> 4;
+            w.gp[k] = src + (size_t)(w.line0 + imin_(lsub + 2 * k, w.nlines - 1)) * pitch4 + (ptrdiff_t)(w.o0 + pos);
+        }
+    }
+}
+
+// Issues source group g (must be called for g = 0, 1, 2, ... in order: the pointers advance).
+template <class C, bool IS_V>
+AVS_FN void load_group(const StreamParams& p, WarpRun<C, IS_V>& w, int g, int gslot, bool issue) {
     constexpr int PITCH = RingOf<C, IS_V, 0>::PITCH;
     const int lane = w.lane;
-    const float* src = static_cast<const float*>(p.src);
+    const float4* src = static_cast<const float4*>(p.src);
+    const size_t pitch4 = (size_t)(p.src_pitch / 4);
 #pragma unroll
     for (int q = 0; q < C::SRC_N / 16; ++q) {
         const int pos0 = w.o0 + g * C::SRC_N + q * 16; // first source position of the sweep
         float2* ring = w.ring0 + (size_t)(gslot + q * 16) * PITCH;
+        const bool interior = (pos0 >= 0) && (pos0 + 16 <= p.src_len);
         if (IS_V) {
             // a position is an intermediate row; the warp's 16 pixel columns are 256 contiguous bytes
             const int piece = lane & 15, rsub = lane >> 4;
-            const float4* col = reinterpret_cast<const float4*>(src) + w.line0 + imin_(piece, w.nlines - 1);
+            float2* d = ring + rsub * PITCH + piece * 2;
+            if (issue && interior) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const int row = rsub + 2 * k;
-                const int y = imin_(imax_(pos0 + row, 0), p.src_len - 1) - p.src_row_base;
-                cp_async16(ring + row * PITCH + piece * 2, col + (size_t)y * (size_t)(p.src_pitch / 4));
+                for (int k = 0; k < 8; ++k) cp_async16(d + 2 * k * PITCH, w.gp[k]);
+            } else if (issue) {
+                const float4* col = src + w.line0 + imin_(piece, w.nlines - 1);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int y = imin_(imax_(pos0 + rsub + 2 * k, 0), p.src_len - 1) - p.src_row_base;
+                    cp_async16(d + 2 * k * PITCH, col + (size_t)y * pitch4);
+                }
             }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) w.gp[k] += 16 * pitch4;
         } else {
             // a position is a pixel of a row: 16 consecutive pixels of one row per half warp
             const int pos = lane & 15, lsub = lane >> 4;
-            const int x = imin_(imax_(pos0 + pos, 0), p.src_len - 1);
+            float2* d = ring + pos * PITCH + lsub * 2;
+            if (issue && interior) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const int line = lsub + 2 * k;
-                const float4* row = reinterpret_cast<const float4*>(
-                    src + (size_t)(w.line0 + imin_(line, w.nlines - 1)) * (size_t)p.src_pitch);
-                cp_async16(ring + pos * PITCH + line * 2, row + x);
+                for (int k = 0; k < 8; ++k) cp_async16(d + 4 * k, w.gp[k]);
+            } else if (issue) {
+                const int x = imin_(imax_(pos0 + pos, 0), p.src_len - 1);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int line = imin_(lsub + 2 * k, w.nlines - 1);
+                    cp_async16(d + 4 * k, src + (size_t)(w.line0 + line) * pitch4 + x);
+                }
             }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) w.gp[k] += 16;
         }
     }
 }
@@ -303,50 +386,82 @@ AVS_FN float2 slow_one(const StreamStep& sp, const float2* ring, int origin, int
 // ---- final outputs -------------------------------------------------------------------------------------
 
 // Column pass: lane = (pixel column, channel pair); a batch is M destination rows.
+template <int EPI>
+AVS_FN void store_v(const StreamParams& p, unsigned char* g, float2 v, int c0) {
+    if (EPI == 1) {
+        *reinterpret_cast<float2*>(g) = v;
+        return;
+    }
+    v.x = epilogue_value(p, v.x, c0);
+    v.y = epilogue_value(p, v.y, c0 + 1);
+    if (p.dst_type == AVIRB200_F32) *reinterpret_cast<float2*>(g) = v;
+    else if (p.dst_type == AVIRB200_U8)
+        *reinterpret_cast<uchar2*>(g) = make_uchar2((unsigned char)v.x, (unsigned char)v.y);
+    else
+        *reinterpret_cast<ushort2*>(g) = make_ushort2((unsigned short)v.x, (unsigned short)v.y);
+}
+
 template <class C, int EPI, int M>
 AVS_FN void sink_v(const StreamParams& p, const WarpRun<C, true>& w, int j0, const float2* o) {
     const int q = w.lane >> 1, c0 = (w.lane & 1) * 2;
     if (q >= w.nlines) return;
     const size_t esz = (p.dst_type == AVIRB200_F32) ? 4 : (p.dst_type == AVIRB200_U16 ? 2 : 1);
-    unsigned char* g0 = static_cast<unsigned char*>(p.dst) + ((size_t)(w.line0 + q) * 4 + c0) * esz;
+    const size_t rowb = (size_t)p.dst_pitch * esz;
+    unsigned char* g = static_cast<unsigned char*>(p.dst) + ((size_t)(w.line0 + q) * 4 + c0) * esz +
+                       (ptrdiff_t)(j0 - p.dst_row_base) * (ptrdiff_t)rowb;
+    if (j0 >= p.out0 && j0 + M <= p.out1) {
 #pragma unroll
-    for (int m = 0; m < M; ++m) {
-        const int j = j0 + m;
-        if (j < p.out0 || j >= p.out1) continue;
-        unsigned char* g = g0 + (size_t)(j - p.dst_row_base) * (size_t)p.dst_pitch * esz;
-        float2 v = o[m];
-        if (EPI == 1) {
-            *reinterpret_cast<float2*>(g) = v;
-            continue;
+        for (int m = 0; m < M; ++m) {
+            store_v<EPI>(p, g, o[m], c0);
+            g += rowb;
         }
-        v.x = epilogue_value(p, v.x, c0);
-        v.y = epilogue_value(p, v.y, c0 + 1);
-        if (p.dst_type == AVIRB200_F32) *reinterpret_cast<float2*>(g) = v;
-        else if (p.dst_type == AVIRB200_U8)
-            *reinterpret_cast<uchar2*>(g) = make_uchar2((unsigned char)v.x, (unsigned char)v.y);
-        else
-            *reinterpret_cast<ushort2*>(g) = make_ushort2((unsigned short)v.x, (unsigned short)v.y);
+    } else {
+#pragma unroll
+        for (int m = 0; m < M; ++m) {
+            if (j0 + m >= p.out0 && j0 + m < p.out1) store_v<EPI>(p, g, o[m], c0);
+            g += rowb;
+        }
     }
 }
 
 // Row pass: lanes hold (line, channel pair) of M consecutive pixels; transposed through the
-// staging rows so that every store instruction writes runs of whole pixels of a row.
+// staging rows so that every store instruction writes runs of whole pixels of a row.  The
+// read-back of batch b is issued before batch b+1 is computed and its global stores after,
+// so that neither the shared-memory latency nor the stores' operand reads are waited for.
+constexpr int kNoPend = -0x7fffffff;
+
 template <class C, int M>
-AVS_FN void sink_h(const StreamParams& p, const WarpRun<C, false>& w, int j0, const float2* o) {
-    AVS_SYNCWARP(); // the previous batch's staging reads are done
-#pragma unroll
-    for (int m = 0; m < M; ++m) w.stage[m * kPitchT + w.lane] = o[m];
-    AVS_SYNCWARP();
+AVS_FN void sink_h_readback(WarpRun<C, false>& w) {
+    if (w.pend_j0 == kNoPend) return;
     const int pos = w.lane & (M - 1), lsub = w.lane / M;
-    const int j = j0 + pos;
+#pragma unroll
+    for (int k = 0; k < M / 2; ++k)
+        w.pend[k] = *reinterpret_cast<const float4*>(w.stage + pos * kPitchT + (lsub + (32 / M) * k) * 2);
+}
+
+template <class C, int M>
+AVS_FN void sink_h_store(const StreamParams& p, WarpRun<C, false>& w) {
+    if (w.pend_j0 == kNoPend) return;
+    const int pos = w.lane & (M - 1), lsub = w.lane / M;
+    const int j = w.pend_j0 + pos;
     float* dst = static_cast<float*>(p.dst);
+    const bool jok = (j >= p.out0) && (j < p.out1);
 #pragma unroll
     for (int k = 0; k < M / 2; ++k) {
         const int line = lsub + (32 / M) * k;
-        const float4 v = *reinterpret_cast<const float4*>(w.stage + pos * kPitchT + line * 2);
-        if (line < w.nlines && j >= p.out0 && j < p.out1)
-            reinterpret_cast<float4*>(dst + (size_t)(w.line0 + line) * (size_t)p.dst_pitch)[j] = v;
+        if (jok && line < w.nlines)
+            reinterpret_cast<float4*>(dst + (size_t)(w.line0 + line) * (size_t)p.dst_pitch)[j] = w.pend[k];
     }
+    w.pend_j0 = kNoPend;
+}
+
+template <class C, int M>
+AVS_FN void sink_h_stage(WarpRun<C, false>& w, int j0, const float2* o) {
+    AVS_SYNCWARP(); // every lane has read the previous batch back
+#pragma unroll
+    for (int m = 0; m < M; ++m) w.stage[m * kPitchT + w.lane] = o[m];
+    AVS_SYNCWARP();
+    w.pend_j0 = j0;
 }
 
 // ---- one batch of one step ------------------------------------------------------------------------------
@@ -358,7 +473,8 @@ AVS_FN void run_batch(const StreamParams& p, WarpRun<C, IS_V>& w) {
     constexpr int PITCH = RingOf<C, IS_V, I>::PITCH;
     constexpr int M = S::M;
     const StreamStep& sp = p.s[I];
-    const int j0 = w.a[I] + M * w.kb[I];
+    const int kbcur = w.kb[I];
+    const int j0 = w.a[I] + M * kbcur;
     const float2* ring = ((I == 0) ? w.ring0 : (I == 1 ? w.ring1 : w.ring2)) + w.lane;
     const int origin = (I == 0) ? w.o0 : w.a[I - 1];
     const int rd = w.rd[I];
@@ -367,6 +483,7 @@ AVS_FN void run_batch(const StreamParams& p, WarpRun<C, IS_V>& w) {
     w.kb[I] += 1;
     w.rd[I] = (rd + S::CH == RSP) ? 0 : rd + S::CH;
 
+    if constexpr (LAST && !IS_V) sink_h_readback<C, M>(w);
     float2 o[M];
     bool have = true;
     const int pin = in_first<S>(sp, j0);
@@ -383,7 +500,7 @@ AVS_FN void run_batch(const StreamParams& p, WarpRun<C, IS_V>& w) {
             if (s >= RSP) s -= RSP;
             base[k] = ring + (size_t)s * PITCH;
         }
-        if (S::KIND == K_RESIZE2) {
+        if constexpr (S::KIND == K_RESIZE2) {
             float2 x[S::W];
 #pragma unroll
             for (int i = 0; i < S::W; ++i) x[i] = base[i / S::CH][(i % S::CH) * PITCH];
@@ -397,21 +514,23 @@ AVS_FN void run_batch(const StreamParams& p, WarpRun<C, IS_V>& w) {
                 for (int m = 0; m < M; ++m)
                     o[m] = resize2_one<S>(x, (m + 1) >> 1, m & 1, sp.taps, sp.zero_start);
             }
-        } else {
+        } else if constexpr (!S::ROLL) {
+            // whole window of the batch in registers, reloaded every batch
+            float2 x[S::WN];
 #pragma unroll
-            for (int sb = 0; sb < M / S::MS; ++sb) {
-                float2 x[S::WS];
+            for (int i = 0; i < S::WN; ++i) x[i] = base[i / S::CH][(i % S::CH) * PITCH];
 #pragma unroll
-                for (int i = 0; i < S::WS; ++i) {
-                    const int wi = sb * S::MS * S::ADV + i; // index in the batch window
-                    x[i] = base[wi / S::CH][(wi % S::CH) * PITCH];
-                }
-#pragma unroll
-                for (int m = 0; m < S::MS; ++m) {
-                    if (S::KIND == K_FIR) o[sb * S::MS + m] = fir_one<S>(x, m * S::ADV, sp.taps);
-                    else o[sb * S::MS + m] = resize_one<S>(x, m * S::ADV, sp.taps, sp.zero_start);
-                }
+            for (int m = 0; m < M; ++m) {
+                if (S::KIND == K_FIR) o[m] = fir_one<S>(x, m * S::ADV, sp.taps);
+                else o[m] = resize_one<S>(x, m * S::ADV, sp.taps, sp.zero_start);
             }
+        } else {
+            float2* xr = (I == 0) ? w.xr0 : (I == 1 ? w.xr1 : w.xr2);
+            auto ld = [&](int i) { return base[i / S::CH][(i % S::CH) * PITCH]; };
+            const bool cold = (w.warm[I] != kbcur);
+            if (kbcur & 1) roll_batch<S, 1>(xr, ld, cold, sp, o);
+            else roll_batch<S, 0>(xr, ld, cold, sp, o);
+            w.warm[I] = kbcur + 1;
         }
     } else {
         const int lo = (I == 0) ? -0x40000000 : 0;
@@ -437,9 +556,11 @@ AVS_FN void run_batch(const StreamParams& p, WarpRun<C, IS_V>& w) {
 #pragma unroll
             for (int m = 0; m < M; ++m) out[m * PITCHO] = o[m];
         }
-    } else if (have) {
-        if constexpr (IS_V) sink_v<C, EPI, M>(p, w, j0, o);
-        else sink_h<C, M>(p, w, j0, o);
+    } else if constexpr (IS_V) {
+        if (have) sink_v<C, EPI, M>(p, w, j0, o);
+    } else {
+        sink_h_store<C, M>(p, w);
+        if (have) sink_h_stage<C, M>(w, j0, o);
     }
 }
 
@@ -461,26 +582,37 @@ AVS_FN void run_warp(const StreamParams& p, WarpRun<C, IS_V>& w, int strip, int 
     w.a[0] = in_first<S1>(p.s[1], w.a[1]);
     w.o0 = in_first<S0>(p.s[0], w.a[0]);
 #pragma unroll
-    for (int i = 0; i < kMaxSteps; ++i) w.rd[i] = w.wr[i] = w.kb[i] = 0;
+    for (int i = 0; i < kMaxSteps; ++i) {
+        w.rd[i] = w.wr[i] = w.kb[i] = 0;
+        w.warm[i] = -1;
+    }
 
     const int total = rounds + C::DELAY_LAST;  // wall rounds; step 0 runs all of them
     const int groups = total + C::H;           // source groups step 0 reads
     int gslot = 0;
     constexpr int PRO = C::H + C::LOOKAHEAD;
+    loader_init<C, IS_V>(p, w);
+    if constexpr (!IS_V) w.pend_j0 = kNoPend;
     for (int g = 0; g < PRO; ++g) {
-        if (g < groups) load_group<C, IS_V>(p, w, g, gslot);
+        load_group<C, IS_V>(p, w, g, gslot, g < groups);
         cp_async_commit();
         gslot = (gslot + C::SRC_N == C::rsp0) ? 0 : gslot + C::SRC_N;
     }
     for (int r = 0; r < total; ++r) {
         cp_async_wait<C::LOOKAHEAD - 1>(); // groups <= r + H have landed (this lane's copies)
         AVS_SYNCWARP();                    // ... all lanes'; and round r-1 is done with its slots
-        if (r + PRO < groups) load_group<C, IS_V>(p, w, r + PRO, gslot);
-        cp_async_commit();
-        gslot = (gslot + C::SRC_N == C::rsp0) ? 0 : gslot + C::SRC_N;
-
+        if (C::LPOS == 0) {
+            load_group<C, IS_V>(p, w, r + PRO, gslot, r + PRO < groups);
+            cp_async_commit();
+            gslot = (gslot + C::SRC_N == C::rsp0) ? 0 : gslot + C::SRC_N;
+        }
 #pragma unroll
         for (int q = 0; q < C::reps0; ++q) run_batch<C, IS_V, EPI, 0, S0>(p, w);
+        if (C::LPOS == 1) {
+            load_group<C, IS_V>(p, w, r + PRO, gslot, r + PRO < groups);
+            cp_async_commit();
+            gslot = (gslot + C::SRC_N == C::rsp0) ? 0 : gslot + C::SRC_N;
+        }
         if (r >= C::delay1) {
 #pragma unroll
             for (int q = 0; q < C::reps1; ++q) run_batch<C, IS_V, EPI, 1, S1>(p, w);
@@ -491,6 +623,11 @@ AVS_FN void run_warp(const StreamParams& p, WarpRun<C, IS_V>& w, int strip, int 
                 for (int q = 0; q < C::reps2; ++q) run_batch<C, IS_V, EPI, 2, S2>(p, w);
             }
         }
+    }
+    if constexpr (!IS_V) {
+        // the last batch is still in the staging rows
+        sink_h_readback<C, C::MLAST>(w);
+        sink_h_store<C, C::MLAST>(p, w);
     }
     cp_async_wait<0>();
     AVS_SYNCWARP(); // the next run refills the rings
@@ -539,10 +676,15 @@ __global__ void __launch_bounds__(NW * 32, 1) stream_pass_kernel(const __grid_co
 // cfg3, float8_dil mirror (k = 2): RESIZE(24 taps, source step 2) -> 8-tap correction FIR.
 // The row pass carries the 272-byte transposition pitch and the staging rows, so it looks
 // two rounds ahead where the column pass affords three (8 warps per SM either way).
-using ChainDil24H = ChainC<StepC<K_RESIZE, AVIRB200_SUM_DIL8, 24, 2>, StepC<K_FIR, AVIRB200_SUM_DIL8, 8, 1>,
-                           NoStep, 1, 2>;
-using ChainDil24V = ChainC<StepC<K_RESIZE, AVIRB200_SUM_DIL8, 24, 2>, StepC<K_FIR, AVIRB200_SUM_DIL8, 8, 1>,
-                           NoStep, 1, 3>;
+// VAR selects a scheduling variant (same arithmetic): bit 0 = resize window in a rolling
+// register ring, bit 1 = FIR window in a rolling register ring, bit 2 = source copies issued
+// after step 0 instead of at the top of the round.
+template <int VAR, int LA>
+using ChainDil24 = ChainC<StepC<K_RESIZE, AVIRB200_SUM_DIL8, 24, 2, (VAR & 1)>,
+                          StepC<K_FIR, AVIRB200_SUM_DIL8, 8, 1, ((VAR >> 1) & 1)>, NoStep, 1, LA, ((VAR >> 2) & 1)>;
+
+constexpr int kStreamVariants = 8;
+constexpr int kStreamDefaultVariant = 4;
 
 template <class C>
 struct ChainTag {
@@ -551,11 +693,24 @@ struct ChainTag {
 
 // Calls f(ChainTag<row-pass chain>(), ChainTag<column-pass chain>()) for chain `id`.
 template <class F>
-inline bool stream_dispatch(int id, F&& f) {
+inline bool stream_dispatch(int id, int variant, F&& f) {
+#define AVS_VARIANTS(NAME, LAH, LAV)                                                      \
+    switch (variant) {                                                                    \
+    case 0: f(ChainTag<NAME<0, LAH> >(), ChainTag<NAME<0, LAV> >()); return true;         \
+    case 1: f(ChainTag<NAME<1, LAH> >(), ChainTag<NAME<1, LAV> >()); return true;         \
+    case 2: f(ChainTag<NAME<2, LAH> >(), ChainTag<NAME<2, LAV> >()); return true;         \
+    case 3: f(ChainTag<NAME<3, LAH> >(), ChainTag<NAME<3, LAV> >()); return true;         \
+    case 4: f(ChainTag<NAME<4, LAH> >(), ChainTag<NAME<4, LAV> >()); return true;         \
+    case 5: f(ChainTag<NAME<5, LAH> >(), ChainTag<NAME<5, LAV> >()); return true;         \
+    case 6: f(ChainTag<NAME<6, LAH> >(), ChainTag<NAME<6, LAV> >()); return true;         \
+    case 7: f(ChainTag<NAME<7, LAH> >(), ChainTag<NAME<7, LAV> >()); return true;         \
+    default: return false;                                                                \
+    }
     switch (id) {
-    case kChainDil24: f(ChainTag<ChainDil24H>(), ChainTag<ChainDil24V>()); return true;
+    case kChainDil24: AVS_VARIANTS(ChainDil24, 2, 3)
     default: return false;
     }
+#undef AVS_VARIANTS
 }
 
 } // namespace avs

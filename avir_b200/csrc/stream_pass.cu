@@ -2,6 +2,7 @@
 // (stream_kernel.cuh); kept in its own translation unit so that the chain kernels compile
 // in parallel with engine.cu.
 #include <cuda_runtime.h>
+#include <stdlib.h>
 
 #include "stream_kernel.cuh"
 #include "stream_launch.h"
@@ -42,10 +43,19 @@ int launch_one(const StreamParams& p, cudaStream_t st) {
 
 } // namespace
 
+int stream_variant() {
+    static const int v = [] {
+        const char* e = getenv("AVIRB200_STREAM_VARIANT");
+        const int x = e ? atoi(e) : kStreamDefaultVariant;
+        return (x >= 0 && x < kStreamVariants) ? x : kStreamDefaultVariant;
+    }();
+    return v;
+}
+
 int stream_launch(int chain, bool is_v, bool plain_f32, const StreamParams& p, void* stream) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     int rc = -2;
-    const bool known = stream_dispatch(chain, [&](auto htag, auto vtag) {
+    const bool known = stream_dispatch(chain, stream_variant(), [&](auto htag, auto vtag) {
         using CH = typename decltype(htag)::type;
         using CV = typename decltype(vtag)::type;
         if (!is_v) rc = launch_one<CH, false, 0>(p, st);

@@ -48,8 +48,8 @@ void emul_pass(const StreamParams& p, int nwarps) {
 }
 
 template <bool IS_V>
-bool emul_dispatch(int chain, const StreamParams& p, int nwarps, bool plain) {
-    return stream_dispatch(chain, [&](auto htag, auto vtag) {
+bool emul_dispatch(int chain, int variant, const StreamParams& p, int nwarps, bool plain) {
+    return stream_dispatch(chain, variant, [&](auto htag, auto vtag) {
         using CH = typename decltype(htag)::type;
         using CV = typename decltype(vtag)::type;
         if constexpr (IS_V) {
@@ -75,7 +75,7 @@ int stream_emul_applicable(const avirb200_plan_desc* d) {
 // Row pass with `warps_h` emulated warps, then the column pass in `bands` destination bands
 // (as the sharded schedule runs it) with `warps_v` warps each.
 int stream_emul_resize(const avirb200_plan_desc* d, const float* src, size_t src_pitch, void* dst,
-                       size_t dst_pitch, int warps_h, int warps_v, int bands) {
+                       size_t dst_pitch, int warps_h, int warps_v, int bands, int variant) {
     StreamAxisPlan h, v;
     if (!stream_row_source_ok(*d) || !stream_plan_axis(d->h, d->sum_mode, d->channels, h) ||
         !stream_plan_axis(d->v, d->sum_mode, d->channels, v))
@@ -91,7 +91,7 @@ int stream_emul_resize(const avirb200_plan_desc* d, const float* src, size_t src
     p.dst = mid.data();
     p.dst_pitch = (long long)d->dst_w * 4;
     p.dst_type = AVIRB200_F32;
-    if (!emul_dispatch<false>(h.chain, p, warps_h, false)) return -4;
+    if (!emul_dispatch<false>(h.chain, variant, p, warps_h, false)) return -4;
 
     const bool plain = (d->out_type == AVIRB200_F32) && !(d->use_gamma & 2);
     for (int b = 0; b < bands; ++b) {
@@ -107,9 +107,11 @@ int stream_emul_resize(const avirb200_plan_desc* d, const float* src, size_t src
         p.dst_pitch = (long long)dst_pitch;
         p.dst_type = d->out_type;
         p.dst_row_base = 0;
-        if (!emul_dispatch<true>(v.chain, p, warps_v, plain)) return -4;
+        if (!emul_dispatch<true>(v.chain, variant, p, warps_v, plain)) return -4;
     }
     return 0;
 }
+
+int stream_emul_variants(void) { return kStreamVariants; }
 
 } // extern "C"

@@ -22,7 +22,7 @@ def emul():
     from avir_b200 import build as b
     lib = C.CDLL(b.build_emul())
     lib.stream_emul_resize.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t,
-                                       C.c_int, C.c_int, C.c_int]
+                                       C.c_int, C.c_int, C.c_int, C.c_int]
     lib.stream_emul_resize.restype = C.c_int
     lib.stream_emul_applicable.argtypes = [C.c_void_p]
     lib.stream_emul_applicable.restype = C.c_int
@@ -47,8 +47,11 @@ def _id(ec):
     return "%s-w%d-%d-b%d" % (cs.case_id(ec[0]), ec[1], ec[2], ec[3])
 
 
+# scheduling variants of the chain kernels (rolling register rings on/off per step, position of
+# the source copies in a round): all must produce the same bits
+@pytest.mark.parametrize("variant", range(8))
 @pytest.mark.parametrize("ec", EMUL_CASES, ids=_id)
-def test_stream_kernel_emulation_matches_port(emul, ec):
+def test_stream_kernel_emulation_matches_port(emul, ec, variant):
     case, wh, wv, bands = ec
     fp, sw, sh, nw, nh, ch, ti, to, rb, kw = case
     src = cs.make_input(case)
@@ -57,7 +60,8 @@ def test_stream_kernel_emulation_matches_port(emul, ec):
     try:
         assert emul.stream_emul_applicable(dp) == 1, "chain not on the streaming kernel: %r" % (modes,)
         got = np.zeros((nh, nw, ch), to)
-        assert emul.stream_emul_resize(dp, src.ctypes.data, sw * ch, got.ctypes.data, nw * ch, wh, wv, bands) == 0
+        assert emul.stream_emul_resize(dp, src.ctypes.data, sw * ch, got.ctypes.data, nw * ch, wh, wv, bands,
+                                       variant) == 0
     finally:
         rs.free_descriptor(h)
     want, _ = cs.port_output(case, src)
