@@ -119,8 +119,10 @@ def build_emul(force=False):
     if not force and not _newer(target, deps):
         return target
     cuda_inc = os.path.join(os.path.dirname(os.path.dirname(_nvcc())), "include")
+    tmp = "%s.%d.tmp" % (target, os.getpid())  # atomic: parallel test workers may build at once
     _run(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-I" + INC, "-I" + CSRC,
-          "-I" + cuda_inc, "-o", target, src, "-pthread"])
+          "-I" + cuda_inc, "-o", tmp, src, "-pthread"])
+    os.replace(tmp, target)
     return target
 
 

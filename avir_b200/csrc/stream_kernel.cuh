@@ -90,13 +90,14 @@ constexpr int cdiv(int a, int b) { return (a + b - 1) / b; }
 //   reps[i]  batches of step i per round
 //   delay[i] rounds step i lags behind step 0
 //   rsp[i]   positions in the ring step i reads (ring 0 = source)
-template <class S0, class S1, class S2, int REPS_LAST, int LA, int LPOS_ = 0>
+template <class S0, class S1, class S2, int REPS_LAST, int LA, int LPOS_ = 0, int STEADY_ = 1>
 struct ChainC {
     using T0 = S0;
     using T1 = S1;
     using T2 = S2;
     static constexpr int NS = (S2::KIND == K_NONE) ? 2 : 3;
     static constexpr int LOOKAHEAD = LA;
+    static constexpr bool STEADY_LOOP = (STEADY_ != 0); // straight-line code for the interior rounds of a run
     static constexpr int LPOS = LPOS_; // source copies are issued 0: at the top of a round, 1: after step 0
     static constexpr int reps2 = (NS == 3) ? REPS_LAST : 0;
     static constexpr int reps1 = (NS == 3) ? (S2::CH * reps2) / S1::M : REPS_LAST;
@@ -313,7 +314,8 @@ AVS_FN void loader_init(const StreamParams& p, WarpRun<C, IS_V>& w) {
 }
 
 // Issues source group g (must be called for g = 0, 1, 2, ... in order: the pointers advance).
-template <class C, bool IS_V>
+// STEADY: the caller guarantees issue && every sweep interior (no branches around the copies).
+template <class C, bool IS_V, bool STEADY>
 AVS_FN void load_group(const StreamParams& p, WarpRun<C, IS_V>& w, int g, int gslot, bool issue) {
     constexpr int PITCH = RingOf<C, IS_V, 0>::PITCH;
     const int lane = w.lane;
@@ -323,12 +325,13 @@ AVS_FN void load_group(const StreamParams& p, WarpRun<C, IS_V>& w, int g, int gs
     for (int q = 0; q < C::SRC_N / 16; ++q) {
         const int pos0 = w.o0 + g * C::SRC_N + q * 16; // first source position of the sweep
         float2* ring = w.ring0 + (size_t)(gslot + q * 16) * PITCH;
-        const bool interior = (pos0 >= 0) && (pos0 + 16 <= p.src_len);
+        const bool interior = STEADY || ((pos0 >= 0) && (pos0 + 16 <= p.src_len));
+        if (STEADY) issue = true;
         if (IS_V) {
             // a position is an intermediate row; the warp's 16 pixel columns are 256 contiguous bytes
             const int piece = lane & 15, rsub = lane >> 4;
             float2* d = ring + rsub * PITCH + piece * 2;
-            if (issue && interior) {
+            if (STEADY || (issue && interior)) {
 #pragma unroll
                 for (int k = 0; k < 8; ++k) cp_async16(d + 2 * k * PITCH, w.gp[k]);
             } else if (issue) {
@@ -345,7 +348,7 @@ AVS_FN void load_group(const StreamParams& p, WarpRun<C, IS_V>& w, int g, int gs
             // a position is a pixel of a row: 16 consecutive pixels of one row per half warp
             const int pos = lane & 15, lsub = lane >> 4;
             float2* d = ring + pos * PITCH + lsub * 2;
-            if (issue && interior) {
+            if (STEADY || (issue && interior)) {
 #pragma unroll
                 for (int k = 0; k < 8; ++k) cp_async16(d + 4 * k, w.gp[k]);
             } else if (issue) {
@@ -401,7 +404,7 @@ AVS_FN void store_v(const StreamParams& p, unsigned char* g, float2 v, int c0) {
         *reinterpret_cast<ushort2*>(g) = make_ushort2((unsigned short)v.x, (unsigned short)v.y);
 }
 
-template <class C, int EPI, int M>
+template <class C, int EPI, int M, bool STEADY>
 AVS_FN void sink_v(const StreamParams& p, const WarpRun<C, true>& w, int j0, const float2* o) {
     const int q = w.lane >> 1, c0 = (w.lane & 1) * 2;
     if (q >= w.nlines) return;
@@ -409,7 +412,7 @@ AVS_FN void sink_v(const StreamParams& p, const WarpRun<C, true>& w, int j0, con
     const size_t rowb = (size_t)p.dst_pitch * esz;
     unsigned char* g = static_cast<unsigned char*>(p.dst) + ((size_t)(w.line0 + q) * 4 + c0) * esz +
                        (ptrdiff_t)(j0 - p.dst_row_base) * (ptrdiff_t)rowb;
-    if (j0 >= p.out0 && j0 + M <= p.out1) {
+    if (STEADY || (j0 >= p.out0 && j0 + M <= p.out1)) {
 #pragma unroll
         for (int m = 0; m < M; ++m) {
             store_v<EPI>(p, g, o[m], c0);
@@ -432,7 +435,8 @@ constexpr int kNoPend = -0x7fffffff;
 
 template <class C, int M>
 AVS_FN void sink_h_readback(WarpRun<C, false>& w) {
-    if (w.pend_j0 == kNoPend) return;
+    // unconditional (no branch around the loads: a join would wait for them); without a
+    // pending batch the values are never stored
     const int pos = w.lane & (M - 1), lsub = w.lane / M;
 #pragma unroll
     for (int k = 0; k < M / 2; ++k)
@@ -441,16 +445,16 @@ AVS_FN void sink_h_readback(WarpRun<C, false>& w) {
 
 template <class C, int M>
 AVS_FN void sink_h_store(const StreamParams& p, WarpRun<C, false>& w) {
-    if (w.pend_j0 == kNoPend) return;
     const int pos = w.lane & (M - 1), lsub = w.lane / M;
     const int j = w.pend_j0 + pos;
     float* dst = static_cast<float*>(p.dst);
-    const bool jok = (j >= p.out0) && (j < p.out1);
+    const bool jok = (w.pend_j0 != kNoPend) && (j >= p.out0) && (j < p.out1);
+    float4* g = reinterpret_cast<float4*>(dst + (size_t)(w.line0 + lsub) * (size_t)p.dst_pitch) + j;
+    const size_t gstep = (size_t)(32 / M) * (size_t)(p.dst_pitch / 4);
 #pragma unroll
     for (int k = 0; k < M / 2; ++k) {
-        const int line = lsub + (32 / M) * k;
-        if (jok && line < w.nlines)
-            reinterpret_cast<float4*>(dst + (size_t)(w.line0 + line) * (size_t)p.dst_pitch)[j] = w.pend[k];
+        if (jok && lsub + (32 / M) * k < w.nlines) *g = w.pend[k];
+        g += gstep;
     }
     w.pend_j0 = kNoPend;
 }
@@ -466,11 +470,60 @@ AVS_FN void sink_h_stage(WarpRun<C, false>& w, int j0, const float2* o) {
 
 // ---- one batch of one step ------------------------------------------------------------------------------
 
-template <class C, bool IS_V, int EPI, int I, class S>
+// Outputs of one in-domain batch whose whole window lies inside its input line.
+template <class C, bool IS_V, int I, class S>
+AVS_FN void fast_batch(const StreamParams& p, WarpRun<C, IS_V>& w, const float2* ring, int rd, int kbcur,
+                       int j0, float2* o) {
+    constexpr int RSP = RingOf<C, IS_V, I>::RSP;
+    constexpr int PITCH = RingOf<C, IS_V, I>::PITCH;
+    constexpr int M = S::M;
+    const StreamStep& sp = p.s[I];
+    // the window never wraps inside a piece of CH positions: pieces are ring-aligned
+    const float2* base[(S::W + S::CH - 1) / S::CH + 1];
+#pragma unroll
+    for (int k = 0; k < (S::W + S::CH - 1) / S::CH; ++k) {
+        int s = rd + k * S::CH;
+        if (s >= RSP) s -= RSP;
+        base[k] = ring + (size_t)s * PITCH;
+    }
+    if constexpr (S::KIND == K_RESIZE2) {
+        float2 x[S::W];
+#pragma unroll
+        for (int i = 0; i < S::W; ++i) x[i] = base[i / S::CH][(i % S::CH) * PITCH];
+        const int pv = sp.sp_first + j0 - (S::NT / 2 - 1);
+        if (pv & 1) {
+#pragma unroll
+            for (int m = 0; m < M; ++m) o[m] = resize2_one<S>(x, m >> 1, (m & 1) ? 0 : 1, sp.taps, sp.zero_start);
+        } else {
+#pragma unroll
+            for (int m = 0; m < M; ++m) o[m] = resize2_one<S>(x, (m + 1) >> 1, m & 1, sp.taps, sp.zero_start);
+        }
+    } else if constexpr (!S::ROLL) {
+        // whole window of the batch in registers, reloaded every batch
+        float2 x[S::WN];
+#pragma unroll
+        for (int i = 0; i < S::WN; ++i) x[i] = base[i / S::CH][(i % S::CH) * PITCH];
+#pragma unroll
+        for (int m = 0; m < M; ++m) {
+            if (S::KIND == K_FIR) o[m] = fir_one<S>(x, m * S::ADV, sp.taps);
+            else o[m] = resize_one<S>(x, m * S::ADV, sp.taps, sp.zero_start);
+        }
+    } else {
+        float2* xr = (I == 0) ? w.xr0 : (I == 1 ? w.xr1 : w.xr2);
+        auto ld = [&](int i) { return base[i / S::CH][(i % S::CH) * PITCH]; };
+        const bool cold = (w.warm[I] != kbcur);
+        if (kbcur & 1) roll_batch<S, 1>(xr, ld, cold, sp, o);
+        else roll_batch<S, 0>(xr, ld, cold, sp, o);
+        w.warm[I] = kbcur + 1;
+    }
+}
+
+// STEADY: the batch is known to be in-domain with its window inside the input line and (last
+// step) its outputs inside [out0, out1): straight-line code, no checks.
+template <class C, bool IS_V, int EPI, int I, class S, bool STEADY>
 AVS_FN void run_batch(const StreamParams& p, WarpRun<C, IS_V>& w) {
     constexpr bool LAST = (I == C::NS - 1);
     constexpr int RSP = RingOf<C, IS_V, I>::RSP;
-    constexpr int PITCH = RingOf<C, IS_V, I>::PITCH;
     constexpr int M = S::M;
     const StreamStep& sp = p.s[I];
     const int kbcur = w.kb[I];
@@ -486,82 +539,70 @@ AVS_FN void run_batch(const StreamParams& p, WarpRun<C, IS_V>& w) {
     if constexpr (LAST && !IS_V) sink_h_readback<C, M>(w);
     float2 o[M];
     bool have = true;
-    const int pin = in_first<S>(sp, j0);
-    const bool in_dom = (j0 >= 0) && (j0 + M <= sp.out_len);
-    const bool win_ok = (I == 0) || (pin >= 0 && pin + S::W <= sp.in_len);
-    if (j0 + M <= 0 || j0 >= sp.out_len) {
-        have = false; // nothing of this batch exists
-    } else if (in_dom && win_ok) {
-        // the window never wraps inside a piece of CH positions: pieces are ring-aligned
-        const float2* base[(S::W + S::CH - 1) / S::CH + 1];
-#pragma unroll
-        for (int k = 0; k < (S::W + S::CH - 1) / S::CH; ++k) {
-            int s = rd + k * S::CH;
-            if (s >= RSP) s -= RSP;
-            base[k] = ring + (size_t)s * PITCH;
-        }
-        if constexpr (S::KIND == K_RESIZE2) {
-            float2 x[S::W];
-#pragma unroll
-            for (int i = 0; i < S::W; ++i) x[i] = base[i / S::CH][(i % S::CH) * PITCH];
-            const int pv = sp.sp_first + j0 - (S::NT / 2 - 1);
-            if (pv & 1) {
-#pragma unroll
-                for (int m = 0; m < M; ++m)
-                    o[m] = resize2_one<S>(x, m >> 1, (m & 1) ? 0 : 1, sp.taps, sp.zero_start);
-            } else {
-#pragma unroll
-                for (int m = 0; m < M; ++m)
-                    o[m] = resize2_one<S>(x, (m + 1) >> 1, m & 1, sp.taps, sp.zero_start);
-            }
-        } else if constexpr (!S::ROLL) {
-            // whole window of the batch in registers, reloaded every batch
-            float2 x[S::WN];
-#pragma unroll
-            for (int i = 0; i < S::WN; ++i) x[i] = base[i / S::CH][(i % S::CH) * PITCH];
-#pragma unroll
-            for (int m = 0; m < M; ++m) {
-                if (S::KIND == K_FIR) o[m] = fir_one<S>(x, m * S::ADV, sp.taps);
-                else o[m] = resize_one<S>(x, m * S::ADV, sp.taps, sp.zero_start);
-            }
-        } else {
-            float2* xr = (I == 0) ? w.xr0 : (I == 1 ? w.xr1 : w.xr2);
-            auto ld = [&](int i) { return base[i / S::CH][(i % S::CH) * PITCH]; };
-            const bool cold = (w.warm[I] != kbcur);
-            if (kbcur & 1) roll_batch<S, 1>(xr, ld, cold, sp, o);
-            else roll_batch<S, 0>(xr, ld, cold, sp, o);
-            w.warm[I] = kbcur + 1;
-        }
+    if constexpr (STEADY) {
+        fast_batch<C, IS_V, I, S>(p, w, ring, rd, kbcur, j0, o);
     } else {
-        const int lo = (I == 0) ? -0x40000000 : 0;
-        const int hi = (I == 0) ? 0x40000000 : sp.in_len - 1;
+        const int pin = in_first<S>(sp, j0);
+        const bool in_dom = (j0 >= 0) && (j0 + M <= sp.out_len);
+        const bool win_ok = (I == 0) || (pin >= 0 && pin + S::W <= sp.in_len);
+        if (j0 + M <= 0 || j0 >= sp.out_len) {
+            have = false; // nothing of this batch exists
+        } else if (in_dom && win_ok) {
+            fast_batch<C, IS_V, I, S>(p, w, ring, rd, kbcur, j0, o);
+        } else {
+            const int lo = (I == 0) ? -0x40000000 : 0;
+            const int hi = (I == 0) ? 0x40000000 : sp.in_len - 1;
 #pragma unroll 1
-        for (int m = 0; m < M; ++m) {
-            const int j = j0 + m;
-            float2 v = make_float2(0.0f, 0.0f);
-            if (j >= 0 && j < sp.out_len) v = slow_one<C, IS_V, I, S>(sp, ring, origin, j, lo, hi);
-            // (a register array indexed by the loop counter: keep the loop rolled, select by value)
+            for (int m = 0; m < M; ++m) {
+                const int j = j0 + m;
+                float2 v = make_float2(0.0f, 0.0f);
+                if (j >= 0 && j < sp.out_len) v = slow_one<C, IS_V, I, S>(sp, ring, origin, j, lo, hi);
+                // (a register array indexed by the loop counter: keep the loop rolled, select by value)
 #pragma unroll
-            for (int mm = 0; mm < M; ++mm)
-                if (mm == m) o[mm] = v;
+                for (int mm = 0; mm < M; ++mm)
+                    if (mm == m) o[mm] = v;
+            }
         }
     }
 
-    if (!LAST) {
+    if constexpr (!LAST) {
         constexpr int RSPO = RingOf<C, IS_V, I + 1>::RSP;
         constexpr int PITCHO = RingOf<C, IS_V, I + 1>::PITCH;
         w.wr[I] = (wr + M == RSPO) ? 0 : wr + M;
-        if (have) {
+        if (STEADY || have) {
             float2* out = ((I == 0) ? w.ring1 : w.ring2) + w.lane + (size_t)wr * PITCHO;
 #pragma unroll
             for (int m = 0; m < M; ++m) out[m * PITCHO] = o[m];
         }
     } else if constexpr (IS_V) {
-        if (have) sink_v<C, EPI, M>(p, w, j0, o);
+        if (STEADY || have) sink_v<C, EPI, M, STEADY>(p, w, j0, o);
     } else {
         sink_h_store<C, M>(p, w);
-        if (have) sink_h_stage<C, M>(w, j0, o);
+        if (STEADY || have) sink_h_stage<C, M>(w, j0, o);
     }
+}
+
+// Rounds [lo, hi] of a run in which step I's batches all satisfy the STEADY conditions.
+AVS_FN int fdiv_(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
+AVS_FN int cdiv_(int a, int b) { return -fdiv_(-a, b); }
+
+template <class C, bool IS_V, int I, class S>
+AVS_FN void steady_bounds(const StreamParams& p, const WarpRun<C, IS_V>& w, int delay, int reps, int& lo, int& hi) {
+    constexpr bool LAST = (I == C::NS - 1);
+    const StreamStep& sp = p.s[I];
+    int kb_lo = imax_(0, cdiv_(-w.a[I], S::M));
+    int kb_hi = fdiv_(sp.out_len - S::M - w.a[I], S::M);
+    if (I > 0) {
+        const int pin0 = in_first<S>(sp, w.a[I]); // window of batch kb starts at pin0 + CH * kb
+        kb_lo = imax_(kb_lo, cdiv_(-pin0, S::CH));
+        kb_hi = imin_(kb_hi, fdiv_(sp.in_len - S::W - pin0, S::CH));
+    }
+    if (LAST) {
+        kb_lo = imax_(kb_lo, cdiv_(p.out0 - w.a[I], S::M));
+        kb_hi = imin_(kb_hi, fdiv_(p.out1 - S::M - w.a[I], S::M));
+    }
+    lo = imax_(lo, delay + cdiv_(kb_lo, reps));
+    hi = imin_(hi, delay + fdiv_(kb_hi - reps + 1, reps));
 }
 
 // ---- one run: `rounds` rounds of B final outputs of one 16-line strip -----------------------------
@@ -594,36 +635,56 @@ AVS_FN void run_warp(const StreamParams& p, WarpRun<C, IS_V>& w, int strip, int 
     loader_init<C, IS_V>(p, w);
     if constexpr (!IS_V) w.pend_j0 = kNoPend;
     for (int g = 0; g < PRO; ++g) {
-        load_group<C, IS_V>(p, w, g, gslot, g < groups);
+        load_group<C, IS_V, false>(p, w, g, gslot, g < groups);
         cp_async_commit();
         gslot = (gslot + C::SRC_N == C::rsp0) ? 0 : gslot + C::SRC_N;
     }
-    for (int r = 0; r < total; ++r) {
-        cp_async_wait<C::LOOKAHEAD - 1>(); // groups <= r + H have landed (this lane's copies)
-        AVS_SYNCWARP();                    // ... all lanes'; and round r-1 is done with its slots
-        if (C::LPOS == 0) {
-            load_group<C, IS_V>(p, w, r + PRO, gslot, r + PRO < groups);
-            cp_async_commit();
-            gslot = (gslot + C::SRC_N == C::rsp0) ? 0 : gslot + C::SRC_N;
-        }
-#pragma unroll
-        for (int q = 0; q < C::reps0; ++q) run_batch<C, IS_V, EPI, 0, S0>(p, w);
-        if (C::LPOS == 1) {
-            load_group<C, IS_V>(p, w, r + PRO, gslot, r + PRO < groups);
-            cp_async_commit();
-            gslot = (gslot + C::SRC_N == C::rsp0) ? 0 : gslot + C::SRC_N;
-        }
-        if (r >= C::delay1) {
-#pragma unroll
-            for (int q = 0; q < C::reps1; ++q) run_batch<C, IS_V, EPI, 1, S1>(p, w);
-        }
-        if constexpr (C::NS == 3) {
-            if (r >= C::delay2) {
-#pragma unroll
-                for (int q = 0; q < C::reps2; ++q) run_batch<C, IS_V, EPI, 2, S2>(p, w);
-            }
+    // rounds [slo, shi]: every batch of every step and the source group issued are "steady"
+    int slo = C::DELAY_LAST, shi = total - 1;
+    steady_bounds<C, IS_V, 0, S0>(p, w, C::delay0, C::reps0, slo, shi);
+    steady_bounds<C, IS_V, 1, S1>(p, w, C::delay1, C::reps1, slo, shi);
+    if constexpr (C::NS == 3) steady_bounds<C, IS_V, 2, S2>(p, w, C::delay2, C::reps2, slo, shi);
+    slo = imax_(slo, cdiv_(-w.o0, C::SRC_N) - PRO);
+    shi = imin_(shi, imin_(fdiv_(p.src_len - w.o0, C::SRC_N) - 1, groups - 1) - PRO);
+
+#define AVS_ROUND(STEADY)                                                                             \
+    {                                                                                                 \
+        cp_async_wait<C::LOOKAHEAD - 1>(); /* groups <= r + H have landed (this lane's copies) */     \
+        AVS_SYNCWARP();                    /* ... all lanes'; round r-1 is done with its slots */     \
+        if (C::LPOS == 0) {                                                                           \
+            load_group<C, IS_V, STEADY>(p, w, r + PRO, gslot, r + PRO < groups);                      \
+            cp_async_commit();                                                                        \
+            gslot = (gslot + C::SRC_N == C::rsp0) ? 0 : gslot + C::SRC_N;                             \
+        }                                                                                             \
+        _Pragma("unroll") for (int q = 0; q < C::reps0; ++q) run_batch<C, IS_V, EPI, 0, S0, STEADY>(p, w); \
+        if (C::LPOS == 1) {                                                                           \
+            load_group<C, IS_V, STEADY>(p, w, r + PRO, gslot, r + PRO < groups);                      \
+            cp_async_commit();                                                                        \
+            gslot = (gslot + C::SRC_N == C::rsp0) ? 0 : gslot + C::SRC_N;                             \
+        }                                                                                             \
+        if (STEADY || r >= C::delay1) {                                                               \
+            _Pragma("unroll") for (int q = 0; q < C::reps1; ++q) run_batch<C, IS_V, EPI, 1, S1, STEADY>(p, w); \
+        }                                                                                             \
+        if constexpr (C::NS == 3) {                                                                   \
+            if (STEADY || r >= C::delay2) {                                                           \
+                _Pragma("unroll") for (int q = 0; q < C::reps2; ++q) run_batch<C, IS_V, EPI, 2, S2, STEADY>(p, w); \
+            }                                                                                         \
+        }                                                                                             \
+    }
+    int r = 0;
+    while (r < total) {
+        if (C::STEADY_LOOP && r >= slo && r <= shi) {
+            // the hot loop: straight-line rounds
+            do {
+                AVS_ROUND(true)
+                ++r;
+            } while (r <= shi);
+        } else {
+            AVS_ROUND(false)
+            ++r;
         }
     }
+#undef AVS_ROUND
     if constexpr (!IS_V) {
         // the last batch is still in the staging rows
         sink_h_readback<C, C::MLAST>(w);
@@ -678,32 +739,41 @@ __global__ void __launch_bounds__(NW * 32, 1) stream_pass_kernel(const __grid_co
 // two rounds ahead where the column pass affords three (8 warps per SM either way).
 // VAR selects a scheduling variant (same arithmetic): bit 0 = resize window in a rolling
 // register ring, bit 1 = FIR window in a rolling register ring, bit 2 = source copies issued
-// after step 0 instead of at the top of the round.
+// after step 0 instead of at the top of the round, bit 3 = no separate straight-line loop for
+// the interior rounds.
 template <int VAR, int LA>
 using ChainDil24 = ChainC<StepC<K_RESIZE, AVIRB200_SUM_DIL8, 24, 2, (VAR & 1)>,
-                          StepC<K_FIR, AVIRB200_SUM_DIL8, 8, 1, ((VAR >> 1) & 1)>, NoStep, 1, LA, ((VAR >> 2) & 1)>;
+                          StepC<K_FIR, AVIRB200_SUM_DIL8, 8, 1, ((VAR >> 1) & 1)>, NoStep, 1, LA, ((VAR >> 2) & 1),
+                          !((VAR >> 3) & 1)>;
 
-constexpr int kStreamVariants = 8;
-constexpr int kStreamDefaultVariant = 4;
+constexpr int kStreamVariants = 16;
+constexpr int kStreamDefaultVariantH = 0, kStreamDefaultVariantV = 8;
 
 template <class C>
 struct ChainTag {
     using type = C;
 };
 
-// Calls f(ChainTag<row-pass chain>(), ChainTag<column-pass chain>()) for chain `id`.
+template <bool V>
+struct PassTag {
+    static constexpr bool is_v = V;
+};
+
+// Calls f(ChainTag<Chain>(), PassTag<is_v>()) with the description of chain `id` in scheduling
+// variant `variant` for the row pass (is_v false) or the column pass.
 template <class F>
-inline bool stream_dispatch(int id, int variant, F&& f) {
+inline bool stream_dispatch(int id, bool is_v, int variant, F&& f) {
+#define AVS_V(NAME, N, LAH, LAV)                                                          \
+    case N:                                                                               \
+        if (is_v) f(ChainTag<NAME<N, LAV> >(), PassTag<true>());                          \
+        else f(ChainTag<NAME<N, LAH> >(), PassTag<false>());                              \
+        return true;
 #define AVS_VARIANTS(NAME, LAH, LAV)                                                      \
     switch (variant) {                                                                    \
-    case 0: f(ChainTag<NAME<0, LAH> >(), ChainTag<NAME<0, LAV> >()); return true;         \
-    case 1: f(ChainTag<NAME<1, LAH> >(), ChainTag<NAME<1, LAV> >()); return true;         \
-    case 2: f(ChainTag<NAME<2, LAH> >(), ChainTag<NAME<2, LAV> >()); return true;         \
-    case 3: f(ChainTag<NAME<3, LAH> >(), ChainTag<NAME<3, LAV> >()); return true;         \
-    case 4: f(ChainTag<NAME<4, LAH> >(), ChainTag<NAME<4, LAV> >()); return true;         \
-    case 5: f(ChainTag<NAME<5, LAH> >(), ChainTag<NAME<5, LAV> >()); return true;         \
-    case 6: f(ChainTag<NAME<6, LAH> >(), ChainTag<NAME<6, LAV> >()); return true;         \
-    case 7: f(ChainTag<NAME<7, LAH> >(), ChainTag<NAME<7, LAV> >()); return true;         \
+        AVS_V(NAME, 0, LAH, LAV) AVS_V(NAME, 1, LAH, LAV) AVS_V(NAME, 2, LAH, LAV) AVS_V(NAME, 3, LAH, LAV)     \
+        AVS_V(NAME, 4, LAH, LAV) AVS_V(NAME, 5, LAH, LAV) AVS_V(NAME, 6, LAH, LAV) AVS_V(NAME, 7, LAH, LAV)     \
+        AVS_V(NAME, 8, LAH, LAV) AVS_V(NAME, 9, LAH, LAV) AVS_V(NAME, 10, LAH, LAV) AVS_V(NAME, 11, LAH, LAV)   \
+        AVS_V(NAME, 12, LAH, LAV) AVS_V(NAME, 13, LAH, LAV) AVS_V(NAME, 14, LAH, LAV) AVS_V(NAME, 15, LAH, LAV) \
     default: return false;                                                                \
     }
     switch (id) {
@@ -711,6 +781,7 @@ inline bool stream_dispatch(int id, int variant, F&& f) {
     default: return false;
     }
 #undef AVS_VARIANTS
+#undef AVS_V
 }
 
 } // namespace avs

@@ -43,23 +43,32 @@ int launch_one(const StreamParams& p, cudaStream_t st) {
 
 } // namespace
 
-int stream_variant() {
-    static const int v = [] {
-        const char* e = getenv("AVIRB200_STREAM_VARIANT");
-        const int x = e ? atoi(e) : kStreamDefaultVariant;
-        return (x >= 0 && x < kStreamVariants) ? x : kStreamDefaultVariant;
-    }();
-    return v;
+// Scheduling variant of a pass: AVIRB200_STREAM_VARIANT_H / _V (or AVIRB200_STREAM_VARIANT for
+// both) override the defaults; tuning and test switch, every variant computes the same bits.
+int stream_variant(bool is_v) {
+    static const int v[2] = {
+        [] {
+            const char* e = getenv("AVIRB200_STREAM_VARIANT_H");
+            if (!e) e = getenv("AVIRB200_STREAM_VARIANT");
+            const int x = e ? atoi(e) : kStreamDefaultVariantH;
+            return (x >= 0 && x < kStreamVariants) ? x : kStreamDefaultVariantH;
+        }(),
+        [] {
+            const char* e = getenv("AVIRB200_STREAM_VARIANT_V");
+            if (!e) e = getenv("AVIRB200_STREAM_VARIANT");
+            const int x = e ? atoi(e) : kStreamDefaultVariantV;
+            return (x >= 0 && x < kStreamVariants) ? x : kStreamDefaultVariantV;
+        }()};
+    return v[is_v ? 1 : 0];
 }
 
 int stream_launch(int chain, bool is_v, bool plain_f32, const StreamParams& p, void* stream) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     int rc = -2;
-    const bool known = stream_dispatch(chain, stream_variant(), [&](auto htag, auto vtag) {
-        using CH = typename decltype(htag)::type;
-        using CV = typename decltype(vtag)::type;
-        if (!is_v) rc = launch_one<CH, false, 0>(p, st);
-        else rc = plain_f32 ? launch_one<CV, true, 1>(p, st) : launch_one<CV, true, 0>(p, st);
+    const bool known = stream_dispatch(chain, is_v, stream_variant(is_v), [&](auto tag, auto pass) {
+        using C = typename decltype(tag)::type;
+        if constexpr (!decltype(pass)::is_v) rc = launch_one<C, false, 0>(p, st);
+        else rc = plain_f32 ? launch_one<C, true, 1>(p, st) : launch_one<C, true, 0>(p, st);
     });
     return known ? rc : -2;
 }

@@ -49,14 +49,15 @@ void emul_pass(const StreamParams& p, int nwarps) {
 
 template <bool IS_V>
 bool emul_dispatch(int chain, int variant, const StreamParams& p, int nwarps, bool plain) {
-    return stream_dispatch(chain, variant, [&](auto htag, auto vtag) {
-        using CH = typename decltype(htag)::type;
-        using CV = typename decltype(vtag)::type;
-        if constexpr (IS_V) {
-            if (plain) emul_pass<CV, true, 1>(p, nwarps);
-            else emul_pass<CV, true, 0>(p, nwarps);
+    return stream_dispatch(chain, IS_V, variant, [&](auto tag, auto pass) {
+        using C = typename decltype(tag)::type;
+        if constexpr (decltype(pass)::is_v != IS_V) {
+            (void)p; // (the dispatcher instantiates the callback for both passes)
+        } else if constexpr (IS_V) {
+            if (plain) emul_pass<C, true, 1>(p, nwarps);
+            else emul_pass<C, true, 0>(p, nwarps);
         } else {
-            emul_pass<CH, false, 0>(p, nwarps);
+            emul_pass<C, false, 0>(p, nwarps);
         }
     });
 }

@@ -48,8 +48,9 @@ def _id(ec):
 
 
 # scheduling variants of the chain kernels (rolling register rings on/off per step, position of
-# the source copies in a round): all must produce the same bits
-@pytest.mark.parametrize("variant", range(8))
+# the source copies in a round, separate straight-line loop for the interior rounds): all must
+# produce the same bits
+@pytest.mark.parametrize("variant", range(16))
 @pytest.mark.parametrize("ec", EMUL_CASES, ids=_id)
 def test_stream_kernel_emulation_matches_port(emul, ec, variant):
     case, wh, wv, bands = ec
