@@ -37,6 +37,21 @@ def _newer(target, sources):
     return any(os.path.getmtime(s) > t for s in sources)
 
 
+class _BuildLock:
+    """Serialises builds between processes (parallel test workers import the package at once)."""
+
+    def __enter__(self):
+        import fcntl
+        self.f = open(os.path.join(PKG, ".build.lock"), "w")
+        fcntl.flock(self.f, fcntl.LOCK_EX)
+        return self
+
+    def __exit__(self, *a):
+        import fcntl
+        fcntl.flock(self.f, fcntl.LOCK_UN)
+        self.f.close()
+
+
 def _run(cmd):
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
@@ -71,6 +86,11 @@ def _obj_stale(obj, src):
 
 
 def build_cuda(force=False, verbose=False):
+    with _BuildLock():
+        return _build_cuda(force, verbose)
+
+
+def _build_cuda(force=False, verbose=False):
     """One object per .cu (compiled in parallel, only when one of its own includes changed),
     linked into libavirb200.so."""
     from concurrent.futures import ThreadPoolExecutor
@@ -82,19 +102,30 @@ def build_cuda(force=False, verbose=False):
 
     def compile_one(job):
         cu, obj = job
-        return _run([_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) +
-                    ["-MD", "-MF", obj + ".d", "-c", cu, "-o", obj])
+        tmp = "%s.%d.tmp" % (obj, os.getpid())  # atomic: parallel test workers may build at once
+        out = _run([_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) +
+                   ["-MD", "-MF", tmp + ".d", "-MT", obj, "-c", cu, "-o", tmp])
+        os.replace(tmp + ".d", obj + ".d")
+        os.replace(tmp, obj)
+        return out
 
     with ThreadPoolExecutor(max_workers=4) as ex:
         for out in ex.map(compile_one, todo):
             if verbose:
                 print(out)
     if todo or not os.path.exists(target):
-        _run([_nvcc(), "-shared", "-o", target] + objs + ["-lcudart_static", "-ldl", "-lpthread", "-lrt"])
+        tmp = "%s.%d.tmp" % (target, os.getpid())
+        _run([_nvcc(), "-shared", "-o", tmp] + objs + ["-lcudart_static", "-ldl", "-lpthread", "-lrt"])
+        os.replace(tmp, target)
     return target
 
 
 def build_host(force=False):
+    with _BuildLock():
+        return _build_host(force)
+
+
+def _build_host(force=False):
     target = os.path.join(PKG, "libavirb200_host.so")
     src = os.path.join(CSRC, "host_capi.cpp")
     deps = [src] + _sources([INC], (".h", ".hpp")) + [os.path.join(PKG, "libavirb200.so")]
@@ -111,6 +142,11 @@ def build_oracles():
 
 
 def build_emul(force=False):
+    with _BuildLock():
+        return _build_emul(force)
+
+
+def _build_emul(force=False):
     """TEST INFRASTRUCTURE: host lockstep emulation of the streaming kernel (tests/emul)."""
     d = os.path.join(ROOT, "tests", "emul")
     target = os.path.join(d, "libstream_emul.so")

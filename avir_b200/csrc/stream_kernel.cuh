@@ -55,8 +55,13 @@ using avb::lin2srgb;
 using avb::round_out;
 
 constexpr int kLines = 16;      // lines per warp (2 lanes per line)
-constexpr int kPitchT = 34;     // float2 units: 272-byte rows, conflict-free transposed access
-constexpr int kPitchL = 32;     // 256-byte rows where only the owning lane touches a column
+constexpr int kPitchL = 32;     // float2 units: [position][lane] rows of 256 bytes
+// Row pass, source ring and output staging: [line][position][4 channels] with one pixel of
+// padding per line.  The copies into it (cp.async) and out of the staging rows then move
+// runs of whole pixels of a row -- 256 contiguous bytes per half warp on both sides -- and
+// the transposition into lanes (lane = line x channel pair) happens in the compute lanes'
+// own 8-byte reads and writes, which the padding keeps conflict-free (16 lines fall into 8
+// distinct 16-byte bank groups twice: two wavefronts, the minimum for 256 bytes).
 
 // Compile-time description of one step.  NT = taps (FIR: stored taps, 2L+1 for the
 // interleaved form, padded to 8 for the de-interleaved one; RESIZE/RESIZE2: filter length).
@@ -90,7 +95,7 @@ constexpr int cdiv(int a, int b) { return (a + b - 1) / b; }
 //   reps[i]  batches of step i per round
 //   delay[i] rounds step i lags behind step 0
 //   rsp[i]   positions in the ring step i reads (ring 0 = source)
-template <class S0, class S1, class S2, int REPS_LAST, int LA, int LPOS_ = 0, int STEADY_ = 1>
+template <class S0, class S1, class S2, int REPS_LAST, int LA, int LPOS_ = 0, int STEADY_ = 1, int PRE_ = 0>
 struct ChainC {
     using T0 = S0;
     using T1 = S1;
@@ -108,8 +113,14 @@ struct ChainC {
     static constexpr int SRC_N = S0::CH * reps0;                        // source positions per round
     static_assert(SRC_N % 16 == 0, "source positions per round must be whole 16-position loads");
     // consumer i+1 needs its producer d rounds ahead
-    static constexpr int d0 = cdiv(cdiv(S1::W, S1::CH) - 1, reps1);
-    static constexpr int d1 = (NS == 3) ? cdiv(cdiv(S2::W, S2::CH) - 1, reps2) : 0;
+    // PRE: in the straight-line rounds a later step's window is read from shared memory at the
+    // top of the round, before step 0's arithmetic (its latency hides behind that); the
+    // window must then be complete one round earlier: one more round of delay and ring.
+    static constexpr bool PRE1 = PRE_ && (S1::KIND == K_FIR || S1::KIND == K_RESIZE) && !S1::ROLL && reps1 == 1;
+    static constexpr bool PRE2 = PRE_ && (NS == 3) && (S2::KIND == K_FIR || S2::KIND == K_RESIZE) && !S2::ROLL &&
+                                 reps2 == 1;
+    static constexpr int d0 = cdiv(cdiv(S1::W, S1::CH) - 1, reps1) + (PRE1 ? 1 : 0);
+    static constexpr int d1 = (NS == 3) ? cdiv(cdiv(S2::W, S2::CH) - 1, reps2) + (PRE2 ? 1 : 0) : 0;
     static constexpr int delay0 = 0, delay1 = d0, delay2 = d0 + d1;
     static constexpr int DELAY_LAST = (NS == 3) ? delay2 : delay1;
     static constexpr int rsp1 = S1::CH * reps1 * (d0 + 1);
@@ -121,7 +132,9 @@ struct ChainC {
     static constexpr int MLAST = (NS == 3) ? S2::M : S1::M;
 
     // shared memory of one warp, in float2 units
-    static constexpr int WARP_F2_H = rsp0 * kPitchT + (rsp1 + rsp2) * kPitchL + MLAST * kPitchT;
+    static constexpr int LINE_F2 = rsp0 * 2 + 2; // row pass: float2 units per line of the source ring
+    static constexpr int STAGE_LINE = MLAST * 2 + 2;
+    static constexpr int WARP_F2_H = kLines * LINE_F2 + (rsp1 + rsp2) * kPitchL + kLines * STAGE_LINE;
     static constexpr int WARP_F2_V = rsp0 * kPitchL + (rsp1 + rsp2) * kPitchL;
 };
 
@@ -248,7 +261,9 @@ struct WarpRun {
     int kb[kMaxSteps];  // batches done
     int warm[kMaxSteps]; // batch number for which the step's register ring is loaded (-1: none)
     // loader: one global pointer per cp.async of a sweep, advancing by 16 positions per sweep
-    // (registers that are only ever incremented: no write-after-read wait on the copy queue)
+    // (they point one sweep behind and are advanced BEFORE use: the copies read them in place
+    // and the next write to them is a whole round away -- no write-after-read wait on the
+    // copy queue)
     const float4* gp[8];
     // row pass: the previous final batch, read back from the staging rows, waiting to be stored
     float4 pend[C::MLAST / 2];
@@ -257,6 +272,9 @@ struct WarpRun {
     float2 xr0[C::T0::ROLL ? C::T0::RR : 1];
     float2 xr1[C::T1::ROLL ? C::T1::RR : 1];
     float2 xr2[C::T2::ROLL ? C::T2::RR : 1];
+    // windows of later steps read ahead at the top of a straight-line round
+    float2 xp1[C::PRE1 ? C::T1::WN : 1];
+    float2 xp2[C::PRE2 ? C::T2::WN : 1];
 };
 
 // View of a register ring: element i of the window that starts at slot OFF.
@@ -290,7 +308,11 @@ AVS_FN void roll_batch(float2* xr, LD&& ld, bool cold, const StreamStep& sp, flo
 template <class C, bool IS_V, int I>
 struct RingOf {
     static constexpr int RSP = (I == 0) ? C::rsp0 : (I == 1 ? C::rsp1 : C::rsp2);
-    static constexpr int PITCH = (I == 0) ? (IS_V ? kPitchL : kPitchT) : kPitchL;
+    // float2 units between consecutive positions, and the lane's own offset
+    static constexpr int PITCH = (I == 0 && !IS_V) ? 2 : kPitchL;
+    static AVS_FN int lane_off(int lane) {
+        return (I == 0 && !IS_V) ? (lane >> 1) * C::LINE_F2 + (lane & 1) : lane;
+    }
 };
 
 // ---- source loader: one group of SRC_N positions, 16 positions x 16 lines per sweep --------------
@@ -304,11 +326,11 @@ AVS_FN void loader_init(const StreamParams& p, WarpRun<C, IS_V>& w) {
     for (int k = 0; k < 8; ++k) {
         if (IS_V) {
             const int piece = lane & 15, rsub = lane >> 4;
-            w.gp[k] = src + (ptrdiff_t)(w.o0 + rsub + 2 * k - p.src_row_base) * (ptrdiff_t)pitch4 + w.line0 +
+            w.gp[k] = src + (ptrdiff_t)(w.o0 - 16 + rsub + 2 * k - p.src_row_base) * (ptrdiff_t)pitch4 + w.line0 +
                       imin_(piece, w.nlines - 1);
         } else {
             const int pos = lane & 15, lsub = lane >> 4;
-            w.gp[k] = src + (size_t)(w.line0 + imin_(lsub + 2 * k, w.nlines - 1)) * pitch4 + (ptrdiff_t)(w.o0 + pos);
+            w.gp[k] = src + (size_t)(w.line0 + imin_(lsub + 2 * k, w.nlines - 1)) * pitch4 + (ptrdiff_t)(w.o0 - 16 + pos);
         }
     }
 }
@@ -331,6 +353,8 @@ AVS_FN void load_group(const StreamParams& p, WarpRun<C, IS_V>& w, int g, int gs
             // a position is an intermediate row; the warp's 16 pixel columns are 256 contiguous bytes
             const int piece = lane & 15, rsub = lane >> 4;
             float2* d = ring + rsub * PITCH + piece * 2;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) w.gp[k] += 16 * pitch4;
             if (STEADY || (issue && interior)) {
 #pragma unroll
                 for (int k = 0; k < 8; ++k) cp_async16(d + 2 * k * PITCH, w.gp[k]);
@@ -342,25 +366,23 @@ AVS_FN void load_group(const StreamParams& p, WarpRun<C, IS_V>& w, int g, int gs
                     cp_async16(d + 2 * k * PITCH, col + (size_t)y * pitch4);
                 }
             }
-#pragma unroll
-            for (int k = 0; k < 8; ++k) w.gp[k] += 16 * pitch4;
         } else {
             // a position is a pixel of a row: 16 consecutive pixels of one row per half warp
             const int pos = lane & 15, lsub = lane >> 4;
-            float2* d = ring + pos * PITCH + lsub * 2;
+            float2* d = ring + pos * PITCH + lsub * C::LINE_F2; // line lsub + 2k: + 2k * LINE_F2
+#pragma unroll
+            for (int k = 0; k < 8; ++k) w.gp[k] += 16;
             if (STEADY || (issue && interior)) {
 #pragma unroll
-                for (int k = 0; k < 8; ++k) cp_async16(d + 4 * k, w.gp[k]);
+                for (int k = 0; k < 8; ++k) cp_async16(d + 2 * k * C::LINE_F2, w.gp[k]);
             } else if (issue) {
                 const int x = imin_(imax_(pos0 + pos, 0), p.src_len - 1);
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
                     const int line = imin_(lsub + 2 * k, w.nlines - 1);
-                    cp_async16(d + 4 * k, src + (size_t)(w.line0 + line) * pitch4 + x);
+                    cp_async16(d + 2 * k * C::LINE_F2, src + (size_t)(w.line0 + line) * pitch4 + x);
                 }
             }
-#pragma unroll
-            for (int k = 0; k < 8; ++k) w.gp[k] += 16;
         }
     }
 }
@@ -440,7 +462,7 @@ AVS_FN void sink_h_readback(WarpRun<C, false>& w) {
     const int pos = w.lane & (M - 1), lsub = w.lane / M;
 #pragma unroll
     for (int k = 0; k < M / 2; ++k)
-        w.pend[k] = *reinterpret_cast<const float4*>(w.stage + pos * kPitchT + (lsub + (32 / M) * k) * 2);
+        w.pend[k] = *reinterpret_cast<const float4*>(w.stage + (lsub + (32 / M) * k) * C::STAGE_LINE + pos * 2);
 }
 
 template <class C, int M>
@@ -463,7 +485,7 @@ template <class C, int M>
 AVS_FN void sink_h_stage(WarpRun<C, false>& w, int j0, const float2* o) {
     AVS_SYNCWARP(); // every lane has read the previous batch back
 #pragma unroll
-    for (int m = 0; m < M; ++m) w.stage[m * kPitchT + w.lane] = o[m];
+    for (int m = 0; m < M; ++m) w.stage[(w.lane >> 1) * C::STAGE_LINE + m * 2 + (w.lane & 1)] = o[m];
     AVS_SYNCWARP();
     w.pend_j0 = j0;
 }
@@ -472,20 +494,49 @@ AVS_FN void sink_h_stage(WarpRun<C, false>& w, int j0, const float2* o) {
 
 // Outputs of one in-domain batch whose whole window lies inside its input line.
 template <class C, bool IS_V, int I, class S>
-AVS_FN void fast_batch(const StreamParams& p, WarpRun<C, IS_V>& w, const float2* ring, int rd, int kbcur,
-                       int j0, float2* o) {
+AVS_FN void window_bases(const float2* ring, int rd, const float2** base) {
     constexpr int RSP = RingOf<C, IS_V, I>::RSP;
     constexpr int PITCH = RingOf<C, IS_V, I>::PITCH;
-    constexpr int M = S::M;
-    const StreamStep& sp = p.s[I];
     // the window never wraps inside a piece of CH positions: pieces are ring-aligned
-    const float2* base[(S::W + S::CH - 1) / S::CH + 1];
 #pragma unroll
     for (int k = 0; k < (S::W + S::CH - 1) / S::CH; ++k) {
         int s = rd + k * S::CH;
         if (s >= RSP) s -= RSP;
         base[k] = ring + (size_t)s * PITCH;
     }
+}
+
+// Reads the window of step I's next batch into registers (straight-line rounds, PRE chains).
+template <class C, bool IS_V, int I, class S>
+AVS_FN void preload_window(WarpRun<C, IS_V>& w) {
+    constexpr int PITCH = RingOf<C, IS_V, I>::PITCH;
+    const float2* ring = ((I == 1) ? w.ring1 : w.ring2) + RingOf<C, IS_V, I>::lane_off(w.lane);
+    const float2* base[(S::W + S::CH - 1) / S::CH + 1];
+    window_bases<C, IS_V, I, S>(ring, w.rd[I], base);
+    float2* xp = (I == 1) ? w.xp1 : w.xp2;
+#pragma unroll
+    for (int i = 0; i < S::WN; ++i) xp[i] = base[i / S::CH][(i % S::CH) * PITCH];
+}
+
+// PRELOADED: the window is already in w.xp1 / w.xp2 (preload_window).
+template <class C, bool IS_V, int I, class S, bool PRELOADED = false>
+AVS_FN void fast_batch(const StreamParams& p, WarpRun<C, IS_V>& w, const float2* ring, int rd, int kbcur,
+                       int j0, float2* o) {
+    constexpr int RSP = RingOf<C, IS_V, I>::RSP;
+    constexpr int PITCH = RingOf<C, IS_V, I>::PITCH;
+    constexpr int M = S::M;
+    const StreamStep& sp = p.s[I];
+    if constexpr (PRELOADED) {
+        const float2* x = (I == 1) ? w.xp1 : w.xp2;
+#pragma unroll
+        for (int m = 0; m < M; ++m) {
+            if (S::KIND == K_FIR) o[m] = fir_one<S>(x, m * S::ADV, sp.taps);
+            else o[m] = resize_one<S>(x, m * S::ADV, sp.taps, sp.zero_start);
+        }
+        return;
+    }
+    const float2* base[(S::W + S::CH - 1) / S::CH + 1];
+    window_bases<C, IS_V, I, S>(ring, rd, base);
     if constexpr (S::KIND == K_RESIZE2) {
         float2 x[S::W];
 #pragma unroll
@@ -528,7 +579,7 @@ AVS_FN void run_batch(const StreamParams& p, WarpRun<C, IS_V>& w) {
     const StreamStep& sp = p.s[I];
     const int kbcur = w.kb[I];
     const int j0 = w.a[I] + M * kbcur;
-    const float2* ring = ((I == 0) ? w.ring0 : (I == 1 ? w.ring1 : w.ring2)) + w.lane;
+    const float2* ring = ((I == 0) ? w.ring0 : (I == 1 ? w.ring1 : w.ring2)) + RingOf<C, IS_V, I>::lane_off(w.lane);
     const int origin = (I == 0) ? w.o0 : w.a[I - 1];
     const int rd = w.rd[I];
     const int wr = w.wr[I];
@@ -536,11 +587,13 @@ AVS_FN void run_batch(const StreamParams& p, WarpRun<C, IS_V>& w) {
     w.kb[I] += 1;
     w.rd[I] = (rd + S::CH == RSP) ? 0 : rd + S::CH;
 
-    if constexpr (LAST && !IS_V) sink_h_readback<C, M>(w);
+    constexpr bool PRE = STEADY && ((I == 1 && C::PRE1) || (I == 2 && C::PRE2));
+    // (PRE chains read the row sink's staged batch back at the top of the round as well)
+    if constexpr (LAST && !IS_V && !(STEADY && C::PRE1)) sink_h_readback<C, M>(w);
     float2 o[M];
     bool have = true;
     if constexpr (STEADY) {
-        fast_batch<C, IS_V, I, S>(p, w, ring, rd, kbcur, j0, o);
+        fast_batch<C, IS_V, I, S, PRE>(p, w, ring, rd, kbcur, j0, o);
     } else {
         const int pin = in_first<S>(sp, j0);
         const bool in_dom = (j0 >= 0) && (j0 + M <= sp.out_len);
@@ -651,6 +704,11 @@ AVS_FN void run_warp(const StreamParams& p, WarpRun<C, IS_V>& w, int strip, int 
     {                                                                                                 \
         cp_async_wait<C::LOOKAHEAD - 1>(); /* groups <= r + H have landed (this lane's copies) */     \
         AVS_SYNCWARP();                    /* ... all lanes'; round r-1 is done with its slots */     \
+        if constexpr (STEADY && C::PRE1) {                                                            \
+            preload_window<C, IS_V, 1, S1>(w);                                                        \
+            if constexpr (C::PRE2) preload_window<C, IS_V, 2, S2>(w);                                 \
+            if constexpr (!IS_V) sink_h_readback<C, C::MLAST>(w);                                     \
+        }                                                                                             \
         if (C::LPOS == 0) {                                                                           \
             load_group<C, IS_V, STEADY>(p, w, r + PRO, gslot, r + PRO < groups);                      \
             cp_async_commit();                                                                        \
@@ -702,7 +760,7 @@ AVS_FN void stream_warp_main(const StreamParams& p, long long gw, long long nwar
     WarpRun<C, IS_V> w;
     w.lane = lane;
     w.ring0 = sm;
-    w.ring1 = w.ring0 + (size_t)C::rsp0 * RingOf<C, IS_V, 0>::PITCH;
+    w.ring1 = w.ring0 + (IS_V ? (size_t)C::rsp0 * kPitchL : (size_t)kLines * C::LINE_F2);
     w.ring2 = w.ring1 + (size_t)C::rsp1 * kPitchL;
     w.stage = w.ring2 + (size_t)C::rsp2 * kPitchL;
     const int rho_first = p.out0 / C::B, rho_last = (p.out1 - 1) / C::B;
@@ -737,17 +795,18 @@ __global__ void __launch_bounds__(NW * 32, 1) stream_pass_kernel(const __grid_co
 // cfg3, float8_dil mirror (k = 2): RESIZE(24 taps, source step 2) -> 8-tap correction FIR.
 // The row pass carries the 272-byte transposition pitch and the staging rows, so it looks
 // two rounds ahead where the column pass affords three (8 warps per SM either way).
-// VAR selects a scheduling variant (same arithmetic): bit 0 = resize window in a rolling
-// register ring, bit 1 = FIR window in a rolling register ring, bit 2 = source copies issued
-// after step 0 instead of at the top of the round, bit 3 = no separate straight-line loop for
-// the interior rounds.
+// VAR selects a scheduling variant (same arithmetic): bit 0 = later steps' windows read ahead
+// at the top of a round (one more round of delay and ring; the source look-ahead shrinks by a
+// round to stay within shared memory), bit 1 = resize window in a rolling register
+// ring, bit 2 = source copies issued after step 0 instead of at the top of the round, bit 3 =
+// no separate straight-line loop for the interior rounds.
 template <int VAR, int LA>
-using ChainDil24 = ChainC<StepC<K_RESIZE, AVIRB200_SUM_DIL8, 24, 2, (VAR & 1)>,
-                          StepC<K_FIR, AVIRB200_SUM_DIL8, 8, 1, ((VAR >> 1) & 1)>, NoStep, 1, LA, ((VAR >> 2) & 1),
-                          !((VAR >> 3) & 1)>;
+using ChainDil24 = ChainC<StepC<K_RESIZE, AVIRB200_SUM_DIL8, 24, 2, ((VAR >> 1) & 1)>,
+                          StepC<K_FIR, AVIRB200_SUM_DIL8, 8, 1, 0>, NoStep, 1, (VAR & 1) ? LA - 1 : LA,
+                          ((VAR >> 2) & 1), !((VAR >> 3) & 1), (VAR & 1)>;
 
 constexpr int kStreamVariants = 16;
-constexpr int kStreamDefaultVariantH = 0, kStreamDefaultVariantV = 8;
+constexpr int kStreamDefaultVariantH = 0, kStreamDefaultVariantV = 9;
 
 template <class C>
 struct ChainTag {

@@ -32,6 +32,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--cfg", default="cfg3")
     ap.add_argument("--n", type=int, default=20)
+    ap.add_argument("--only", default="both", choices=["both", "row", "col"])
     a = ap.parse_args()
     fp, sw, sh, nw, nh, ti, to, rb, kw = CFG[a.cfg]
     lib = ab.lib()
@@ -76,12 +77,15 @@ def main():
             ts.append(e0.elapsed_time(e1))
         return sorted(ts)[len(ts) // 2]
 
-    rms, cms = med(row), med(col)
+    row()
+    rms = med(row) if a.only != "col" else None
+    cms = med(col) if a.only != "row" else None
     digest = hashlib.sha1(d_dst.cpu().numpy().tobytes()).hexdigest()[:16]
     paths = lib.avirb200_plan_kernel_paths(plan)
-    print(json.dumps({"cfg": a.cfg, "variant": os.environ.get("AVIRB200_STREAM_VARIANT", "default"),
+    print(json.dumps({"cfg": a.cfg, "variant_h": os.environ.get("AVIRB200_STREAM_VARIANT_H", "default"),
+                      "variant_v": os.environ.get("AVIRB200_STREAM_VARIANT_V", "default"),
                       "stream_disabled": os.environ.get("AVIRB200_DISABLE_STREAM", "0"),
-                      "kernel_paths": paths, "row_ms": rms, "col_ms": cms, "sum_ms": rms + cms,
+                      "kernel_paths": paths, "row_ms": rms, "col_ms": cms,
                       "out_sha1": digest, "build_modes": list(modes)}))
     lib.avirb200_plan_destroy(plan)
     rs.free_descriptor(h)
