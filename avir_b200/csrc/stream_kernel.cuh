@@ -68,24 +68,13 @@ constexpr int kPitchL = 32;     // float2 units: [position][lane] rows of 256 by
 // ADV = input positions per output (FIR decimation R, RESIZE source step D).
 // RESIZE2 = resize over the virtual 2X zero-stuffed line, odd taps skipped (upstream
 // doResize2, avir.h:4114-4328): two outputs per input position.
-template <int KIND_, int SUM_, int NT_, int ADV_, int ROLL_ = 1>
+template <int KIND_, int SUM_, int NT_, int ADV_>
 struct StepC {
     static constexpr int KIND = KIND_, SUM = SUM_, NT = NT_, ADV = ADV_;
     static constexpr int M = (KIND == K_RESIZE2) ? 16 : 8;          // outputs per batch
     static constexpr int CH = (KIND == K_RESIZE2) ? 8 : 8 * ADV;    // input positions per batch
     static constexpr int NTW = (KIND == K_RESIZE2) ? NT / 2 : NT;   // inputs one output reads
-    // FIR / RESIZE keep their input window in a rolling register ring of two batches' worth
-    // of positions: every input is loaded from shared memory exactly once, LK positions
-    // before the first output that reads it (as far ahead as the ring and the batch's
-    // shared-memory window allow).
-    static constexpr bool ROLL = ROLL_ && (KIND == K_FIR || KIND == K_RESIZE);
-    static constexpr int RR = 2 * M * ADV;
-    static constexpr int WN = (KIND == K_RESIZE2) ? 20 : NT + (M - 1) * ADV; // window the batch needs
-    // a rolling batch leaves the ring loaded for the next one: it touches NT + LK + M*ADV positions
-    static constexpr int SLACK = ((WN + ADV + CH - 1) / CH) * CH - WN - ADV;
-    static constexpr int LK = !ROLL ? 0 : ((RR - NT < SLACK) ? RR - NT : SLACK);
-    static constexpr int W = ROLL ? WN + LK + ADV : WN;              // window the batch touches
-    static_assert(!ROLL || RR >= NT, "register ring shorter than the filter");
+    static constexpr int W = (KIND == K_RESIZE2) ? 20 : NT + (M - 1) * ADV; // window of a batch
 };
 using NoStep = StepC<K_NONE, 0, 0, 1>;
 
@@ -95,15 +84,15 @@ constexpr int cdiv(int a, int b) { return (a + b - 1) / b; }
 //   reps[i]  batches of step i per round
 //   delay[i] rounds step i lags behind step 0
 //   rsp[i]   positions in the ring step i reads (ring 0 = source)
-template <class S0, class S1, class S2, int REPS_LAST, int LA, int LPOS_ = 0, int STEADY_ = 1, int PRE_ = 0>
+template <class S0, class S1, class S2, int REPS_LAST, int LA, int STEADY_ = 1, int PRE_ = 0>
 struct ChainC {
     using T0 = S0;
     using T1 = S1;
     using T2 = S2;
     static constexpr int NS = (S2::KIND == K_NONE) ? 2 : 3;
     static constexpr int LOOKAHEAD = LA;
+    static constexpr int NWARPS = 8; // warps per block (one block per SM)
     static constexpr bool STEADY_LOOP = (STEADY_ != 0); // straight-line code for the interior rounds of a run
-    static constexpr int LPOS = LPOS_; // source copies are issued 0: at the top of a round, 1: after step 0
     static constexpr int reps2 = (NS == 3) ? REPS_LAST : 0;
     static constexpr int reps1 = (NS == 3) ? (S2::CH * reps2) / S1::M : REPS_LAST;
     static constexpr int reps0 = (S1::CH * reps1) / S0::M;
@@ -116,9 +105,8 @@ struct ChainC {
     // PRE: in the straight-line rounds a later step's window is read from shared memory at the
     // top of the round, before step 0's arithmetic (its latency hides behind that); the
     // window must then be complete one round earlier: one more round of delay and ring.
-    static constexpr bool PRE1 = PRE_ && (S1::KIND == K_FIR || S1::KIND == K_RESIZE) && !S1::ROLL && reps1 == 1;
-    static constexpr bool PRE2 = PRE_ && (NS == 3) && (S2::KIND == K_FIR || S2::KIND == K_RESIZE) && !S2::ROLL &&
-                                 reps2 == 1;
+    static constexpr bool PRE1 = PRE_ && (S1::KIND == K_FIR || S1::KIND == K_RESIZE) && reps1 == 1;
+    static constexpr bool PRE2 = PRE_ && (NS == 3) && (S2::KIND == K_FIR || S2::KIND == K_RESIZE) && reps2 == 1;
     static constexpr int d0 = cdiv(cdiv(S1::W, S1::CH) - 1, reps1) + (PRE1 ? 1 : 0);
     static constexpr int d1 = (NS == 3) ? cdiv(cdiv(S2::W, S2::CH) - 1, reps2) + (PRE2 ? 1 : 0) : 0;
     static constexpr int delay0 = 0, delay1 = d0, delay2 = d0 + d1;
@@ -259,7 +247,6 @@ struct WarpRun {
     int rd[kMaxSteps];  // read slot (positions) of each step in its input ring
     int wr[kMaxSteps];  // write slot of each step in its output ring
     int kb[kMaxSteps];  // batches done
-    int warm[kMaxSteps]; // batch number for which the step's register ring is loaded (-1: none)
     // loader: one global pointer per cp.async of a sweep, advancing by 16 positions per sweep
     // (they point one sweep behind and are advanced BEFORE use: the copies read them in place
     // and the next write to them is a whole round away -- no write-after-read wait on the
@@ -268,42 +255,10 @@ struct WarpRun {
     // row pass: the previous final batch, read back from the staging rows, waiting to be stored
     float4 pend[C::MLAST / 2];
     int pend_j0;
-    // rolling register rings of the input windows (compile-time indices only)
-    float2 xr0[C::T0::ROLL ? C::T0::RR : 1];
-    float2 xr1[C::T1::ROLL ? C::T1::RR : 1];
-    float2 xr2[C::T2::ROLL ? C::T2::RR : 1];
     // windows of later steps read ahead at the top of a straight-line round
-    float2 xp1[C::PRE1 ? C::T1::WN : 1];
-    float2 xp2[C::PRE2 ? C::T2::WN : 1];
+    float2 xp1[C::PRE1 ? C::T1::W : 1];
+    float2 xp2[C::PRE2 ? C::T2::W : 1];
 };
-
-// View of a register ring: element i of the window that starts at slot OFF.
-template <int R, int OFF>
-struct RingView {
-    const float2* xr;
-    AVS_FN const float2& operator[](int i) const { return xr[(OFF + i) % R]; }
-};
-
-// One batch of a rolling step: M outputs; PH = parity of the batch number (the ring holds two
-// batches' worth of positions, so the window's slot offset alternates).  ld(i) reads input
-// position i of the batch window from shared memory.
-template <class S, int PH, class LD>
-AVS_FN void roll_batch(float2* xr, LD&& ld, bool cold, const StreamStep& sp, float2* o) {
-    constexpr int R = S::RR, OFF = PH * S::M * S::ADV, HELD = S::NT + S::LK;
-    if (cold) {
-#pragma unroll
-        for (int i = 0; i < HELD; ++i) xr[(OFF + i) % R] = ld(i);
-    }
-    const RingView<R, OFF> x{xr};
-#pragma unroll
-    for (int k = 0; k < S::M; ++k) {
-        if (S::KIND == K_FIR) o[k] = fir_one<S>(x, k * S::ADV, sp.taps);
-        else o[k] = resize_one<S>(x, k * S::ADV, sp.taps, sp.zero_start);
-        // positions [k*ADV, (k+1)*ADV) are dead now: refill their slots LK ahead of use
-#pragma unroll
-        for (int i = 0; i < S::ADV; ++i) xr[(OFF + HELD + k * S::ADV + i) % R] = ld(HELD + k * S::ADV + i);
-    }
-}
 
 template <class C, bool IS_V, int I>
 struct RingOf {
@@ -515,7 +470,7 @@ AVS_FN void preload_window(WarpRun<C, IS_V>& w) {
     window_bases<C, IS_V, I, S>(ring, w.rd[I], base);
     float2* xp = (I == 1) ? w.xp1 : w.xp2;
 #pragma unroll
-    for (int i = 0; i < S::WN; ++i) xp[i] = base[i / S::CH][(i % S::CH) * PITCH];
+    for (int i = 0; i < S::W; ++i) xp[i] = base[i / S::CH][(i % S::CH) * PITCH];
 }
 
 // PRELOADED: the window is already in w.xp1 / w.xp2 (preload_window).
@@ -549,23 +504,16 @@ AVS_FN void fast_batch(const StreamParams& p, WarpRun<C, IS_V>& w, const float2*
 #pragma unroll
             for (int m = 0; m < M; ++m) o[m] = resize2_one<S>(x, (m + 1) >> 1, m & 1, sp.taps, sp.zero_start);
         }
-    } else if constexpr (!S::ROLL) {
-        // whole window of the batch in registers, reloaded every batch
-        float2 x[S::WN];
+    } else {
+        // whole window of the batch in registers
+        float2 x[S::W];
 #pragma unroll
-        for (int i = 0; i < S::WN; ++i) x[i] = base[i / S::CH][(i % S::CH) * PITCH];
+        for (int i = 0; i < S::W; ++i) x[i] = base[i / S::CH][(i % S::CH) * PITCH];
 #pragma unroll
         for (int m = 0; m < M; ++m) {
             if (S::KIND == K_FIR) o[m] = fir_one<S>(x, m * S::ADV, sp.taps);
             else o[m] = resize_one<S>(x, m * S::ADV, sp.taps, sp.zero_start);
         }
-    } else {
-        float2* xr = (I == 0) ? w.xr0 : (I == 1 ? w.xr1 : w.xr2);
-        auto ld = [&](int i) { return base[i / S::CH][(i % S::CH) * PITCH]; };
-        const bool cold = (w.warm[I] != kbcur);
-        if (kbcur & 1) roll_batch<S, 1>(xr, ld, cold, sp, o);
-        else roll_batch<S, 0>(xr, ld, cold, sp, o);
-        w.warm[I] = kbcur + 1;
     }
 }
 
@@ -676,10 +624,7 @@ AVS_FN void run_warp(const StreamParams& p, WarpRun<C, IS_V>& w, int strip, int 
     w.a[0] = in_first<S1>(p.s[1], w.a[1]);
     w.o0 = in_first<S0>(p.s[0], w.a[0]);
 #pragma unroll
-    for (int i = 0; i < kMaxSteps; ++i) {
-        w.rd[i] = w.wr[i] = w.kb[i] = 0;
-        w.warm[i] = -1;
-    }
+    for (int i = 0; i < kMaxSteps; ++i) w.rd[i] = w.wr[i] = w.kb[i] = 0;
 
     const int total = rounds + C::DELAY_LAST;  // wall rounds; step 0 runs all of them
     const int groups = total + C::H;           // source groups step 0 reads
@@ -709,17 +654,10 @@ AVS_FN void run_warp(const StreamParams& p, WarpRun<C, IS_V>& w, int strip, int 
             if constexpr (C::PRE2) preload_window<C, IS_V, 2, S2>(w);                                 \
             if constexpr (!IS_V) sink_h_readback<C, C::MLAST>(w);                                     \
         }                                                                                             \
-        if (C::LPOS == 0) {                                                                           \
-            load_group<C, IS_V, STEADY>(p, w, r + PRO, gslot, r + PRO < groups);                      \
-            cp_async_commit();                                                                        \
-            gslot = (gslot + C::SRC_N == C::rsp0) ? 0 : gslot + C::SRC_N;                             \
-        }                                                                                             \
+        load_group<C, IS_V, STEADY>(p, w, r + PRO, gslot, r + PRO < groups);                          \
+        cp_async_commit();                                                                            \
+        gslot = (gslot + C::SRC_N == C::rsp0) ? 0 : gslot + C::SRC_N;                                 \
         _Pragma("unroll") for (int q = 0; q < C::reps0; ++q) run_batch<C, IS_V, EPI, 0, S0, STEADY>(p, w); \
-        if (C::LPOS == 1) {                                                                           \
-            load_group<C, IS_V, STEADY>(p, w, r + PRO, gslot, r + PRO < groups);                      \
-            cp_async_commit();                                                                        \
-            gslot = (gslot + C::SRC_N == C::rsp0) ? 0 : gslot + C::SRC_N;                             \
-        }                                                                                             \
         if (STEADY || r >= C::delay1) {                                                               \
             _Pragma("unroll") for (int q = 0; q < C::reps1; ++q) run_batch<C, IS_V, EPI, 1, S1, STEADY>(p, w); \
         }                                                                                             \
@@ -780,33 +718,35 @@ AVS_FN void stream_warp_main(const StreamParams& p, long long gw, long long nwar
 }
 
 #if defined(__CUDACC__)
-template <class C, bool IS_V, int EPI, int NW>
-__global__ void __launch_bounds__(NW * 32, 1) stream_pass_kernel(const __grid_constant__ StreamParams p) {
+template <class C, bool IS_V, int EPI>
+__global__ void __launch_bounds__(C::NWARPS * 32, 1) stream_pass_kernel(const __grid_constant__ StreamParams p) {
     extern __shared__ __align__(16) unsigned char stream_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float2* sm = reinterpret_cast<float2*>(stream_smem) + (size_t)warp * (IS_V ? C::WARP_F2_V : C::WARP_F2_H);
-    stream_warp_main<C, IS_V, EPI>(p, (long long)blockIdx.x * NW + warp, (long long)gridDim.x * NW, lane, sm);
+    stream_warp_main<C, IS_V, EPI>(p, (long long)blockIdx.x * C::NWARPS + warp, (long long)gridDim.x * C::NWARPS, lane, sm);
 }
 #endif
 
 // ---- the chains ------------------------------------------------------------------------------------------
 // (kind, summation, taps, advance) per step; final batches per round; source look-ahead in rounds.
 
-// cfg3, float8_dil mirror (k = 2): RESIZE(24 taps, source step 2) -> 8-tap correction FIR.
-// The row pass carries the 272-byte transposition pitch and the staging rows, so it looks
-// two rounds ahead where the column pass affords three (8 warps per SM either way).
-// VAR selects a scheduling variant (same arithmetic): bit 0 = later steps' windows read ahead
-// at the top of a round (one more round of delay and ring; the source look-ahead shrinks by a
-// round to stay within shared memory), bit 1 = resize window in a rolling register
-// ring, bit 2 = source copies issued after step 0 instead of at the top of the round, bit 3 =
-// no separate straight-line loop for the interior rounds.
-template <int VAR, int LA>
-using ChainDil24 = ChainC<StepC<K_RESIZE, AVIRB200_SUM_DIL8, 24, 2, ((VAR >> 1) & 1)>,
-                          StepC<K_FIR, AVIRB200_SUM_DIL8, 8, 1, 0>, NoStep, 1, (VAR & 1) ? LA - 1 : LA,
-                          ((VAR >> 2) & 1), !((VAR >> 3) & 1), (VAR & 1)>;
+// Scheduling variants (same arithmetic): bit 0 = later steps' windows read ahead at the top of
+// a round (one more round of delay and ring; the source look-ahead shrinks by a round to stay
+// within shared memory), bit 1 = no separate straight-line loop for the interior rounds.
+// Measured on cfg3 (profiles/r01_variant_sweeps.jsonl): the row pass is fastest with the
+// straight-line loop (variant 0), the column pass without it and with read-ahead (variant 3).
+constexpr int kStreamVariants = 4;
+constexpr int kStreamDefaultVariantH = 0, kStreamDefaultVariantV = 3;
 
-constexpr int kStreamVariants = 16;
-constexpr int kStreamDefaultVariantH = 0, kStreamDefaultVariantV = 9;
+// The row pass carries the staging rows, so it looks two rounds ahead for its source where
+// the column pass affords three (8 warps per SM either way).
+template <class S0, class S1, class S2, int REPS_LAST, int VAR, bool IS_V>
+using ChainV = ChainC<S0, S1, S2, REPS_LAST, (IS_V ? 3 : 2) - (VAR & 1), !((VAR >> 1) & 1), (VAR & 1)>;
+
+// cfg3, float8_dil mirror (k = 2): RESIZE(24 taps, source step 2) -> 8-tap correction FIR
+template <int VAR, bool IS_V>
+using ChainDil24 = ChainV<StepC<K_RESIZE, AVIRB200_SUM_DIL8, 24, 2>, StepC<K_FIR, AVIRB200_SUM_DIL8, 8, 1>, NoStep,
+                          1, VAR, IS_V>;
 
 template <class C>
 struct ChainTag {
@@ -822,21 +762,18 @@ struct PassTag {
 // variant `variant` for the row pass (is_v false) or the column pass.
 template <class F>
 inline bool stream_dispatch(int id, bool is_v, int variant, F&& f) {
-#define AVS_V(NAME, N, LAH, LAV)                                                          \
+#define AVS_V(NAME, N)                                                                    \
     case N:                                                                               \
-        if (is_v) f(ChainTag<NAME<N, LAV> >(), PassTag<true>());                          \
-        else f(ChainTag<NAME<N, LAH> >(), PassTag<false>());                              \
+        if (is_v) f(ChainTag<NAME<N, true> >(), PassTag<true>());                         \
+        else f(ChainTag<NAME<N, false> >(), PassTag<false>());                            \
         return true;
-#define AVS_VARIANTS(NAME, LAH, LAV)                                                      \
+#define AVS_VARIANTS(NAME)                                                                \
     switch (variant) {                                                                    \
-        AVS_V(NAME, 0, LAH, LAV) AVS_V(NAME, 1, LAH, LAV) AVS_V(NAME, 2, LAH, LAV) AVS_V(NAME, 3, LAH, LAV)     \
-        AVS_V(NAME, 4, LAH, LAV) AVS_V(NAME, 5, LAH, LAV) AVS_V(NAME, 6, LAH, LAV) AVS_V(NAME, 7, LAH, LAV)     \
-        AVS_V(NAME, 8, LAH, LAV) AVS_V(NAME, 9, LAH, LAV) AVS_V(NAME, 10, LAH, LAV) AVS_V(NAME, 11, LAH, LAV)   \
-        AVS_V(NAME, 12, LAH, LAV) AVS_V(NAME, 13, LAH, LAV) AVS_V(NAME, 14, LAH, LAV) AVS_V(NAME, 15, LAH, LAV) \
+        AVS_V(NAME, 0) AVS_V(NAME, 1) AVS_V(NAME, 2) AVS_V(NAME, 3)                       \
     default: return false;                                                                \
     }
     switch (id) {
-    case kChainDil24: AVS_VARIANTS(ChainDil24, 2, 3)
+    case kChainDil24: AVS_VARIANTS(ChainDil24)
     default: return false;
     }
 #undef AVS_VARIANTS

@@ -11,8 +11,6 @@ namespace avs {
 
 namespace {
 
-constexpr int kStreamWarps = 8;
-
 int sm_count() {
     static const int sms = [] {
         int d = 0, n = 0;
@@ -25,10 +23,10 @@ int sm_count() {
 
 template <class C, bool IS_V, int EPI>
 int launch_one(const StreamParams& p, cudaStream_t st) {
-    constexpr int NW = kStreamWarps;
+    constexpr int NW = C::NWARPS;
     constexpr size_t smem = (size_t)NW * (IS_V ? C::WARP_F2_V : C::WARP_F2_H) * sizeof(float2);
     static_assert(smem <= 227 * 1024, "per-warp rings do not fit the shared memory of an SM");
-    auto kern = stream_pass_kernel<C, IS_V, EPI, NW>;
+    auto kern = stream_pass_kernel<C, IS_V, EPI>;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
         return -1;
     // one persistent block per SM; fewer when the pass has fewer rounds than warps

@@ -47,10 +47,9 @@ def _id(ec):
     return "%s-w%d-%d-b%d" % (cs.case_id(ec[0]), ec[1], ec[2], ec[3])
 
 
-# scheduling variants of the chain kernels (rolling register rings on/off per step, position of
-# the source copies in a round, separate straight-line loop for the interior rounds): all must
-# produce the same bits
-@pytest.mark.parametrize("variant", range(16))
+# scheduling variants of the chain kernels (later steps' windows read ahead or not, separate
+# straight-line loop for the interior rounds or not): all must produce the same bits
+@pytest.mark.parametrize("variant", range(4))
 @pytest.mark.parametrize("ec", EMUL_CASES, ids=_id)
 def test_stream_kernel_emulation_matches_port(emul, ec, variant):
     case, wh, wv, bands = ec
