@@ -738,15 +738,30 @@ __global__ void __launch_bounds__(C::NWARPS * 32, 1) stream_pass_kernel(const __
 constexpr int kStreamVariants = 4;
 constexpr int kStreamDefaultVariantH = 0, kStreamDefaultVariantV = 3;
 
-// The row pass carries the staging rows, so it looks two rounds ahead for its source where
-// the column pass affords three (8 warps per SM either way).
-template <class S0, class S1, class S2, int REPS_LAST, int VAR, bool IS_V>
-using ChainV = ChainC<S0, S1, S2, REPS_LAST, (IS_V ? 3 : 2) - (VAR & 1), !((VAR >> 1) & 1), (VAR & 1)>;
+// Source look-ahead in rounds (LAH row pass, LAV column pass) is what shared memory affords at
+// 8 warps per SM: the row pass carries the staging rows, three-step chains a second
+// intermediate ring.  PRE_OK: the chain has room for the read-ahead variant (one more chunk
+// of every intermediate ring, paid for with one round of source look-ahead).
+template <class S0, class S1, class S2, int REPS_LAST, int LAH, int LAV, bool PRE_OK, int VAR, bool IS_V>
+using ChainV = ChainC<S0, S1, S2, REPS_LAST, (IS_V ? LAV : LAH) - ((PRE_OK && (VAR & 1)) ? 1 : 0), !((VAR >> 1) & 1),
+                      (PRE_OK && (VAR & 1)) ? 1 : 0>;
 
 // cfg3, float8_dil mirror (k = 2): RESIZE(24 taps, source step 2) -> 8-tap correction FIR
 template <int VAR, bool IS_V>
 using ChainDil24 = ChainV<StepC<K_RESIZE, AVIRB200_SUM_DIL8, 24, 2>, StepC<K_FIR, AVIRB200_SUM_DIL8, 8, 1>, NoStep,
-                          1, VAR, IS_V>;
+                          1, 2, 3, true, VAR, IS_V>;
+// k = 2 in build mode 1, interleaved classes (fpclass_def<float>, fpclass_float4): RESIZE(24) -> FIR(7)
+template <int VAR, bool IS_V>
+using ChainInl24 = ChainV<StepC<K_RESIZE, AVIRB200_SUM_INL, 24, 2>, StepC<K_FIR, AVIRB200_SUM_INL, 7, 1>, NoStep,
+                          1, 2, 3, true, VAR, IS_V>;
+// cfg3, float4 mirror (k = 2, build mode 0): FIR(7) -> RESIZE(18, source step 2) -> FIR(7)
+template <int VAR, bool IS_V>
+using ChainInl3 = ChainV<StepC<K_FIR, AVIRB200_SUM_INL, 7, 1>, StepC<K_RESIZE, AVIRB200_SUM_INL, 18, 2>,
+                         StepC<K_FIR, AVIRB200_SUM_INL, 7, 1>, 1, 1, 2, false, VAR, IS_V>;
+// cfg2 (k = 0.5): FIR(7) -> RESIZE(24) over the virtual 2X line; 32 final outputs per round
+template <int VAR, bool IS_V>
+using ChainUp2 = ChainV<StepC<K_FIR, AVIRB200_SUM_INL, 7, 1>, StepC<K_RESIZE2, AVIRB200_SUM_INL, 24, 1>, NoStep,
+                        2, 1, 3, false, VAR, IS_V>;
 
 template <class C>
 struct ChainTag {
@@ -774,6 +789,9 @@ inline bool stream_dispatch(int id, bool is_v, int variant, F&& f) {
     }
     switch (id) {
     case kChainDil24: AVS_VARIANTS(ChainDil24)
+    case kChainInl24: AVS_VARIANTS(ChainInl24)
+    case kChainInl3: AVS_VARIANTS(ChainInl3)
+    case kChainUp2: AVS_VARIANTS(ChainUp2)
     default: return false;
     }
 #undef AVS_VARIANTS

@@ -44,6 +44,9 @@ struct StreamParams {
 enum StreamChainId {
     kChainNone = 0,
     kChainDil24, // RESIZE(24, D2) -> FIR8                 cfg3, float8_dil mirror (k = 2)
+    kChainInl24, // RESIZE(24, D2) -> FIR7                 k = 2, build mode 1, interleaved classes
+    kChainInl3,  // FIR7 -> RESIZE(18, D2) -> FIR7         cfg3, float4 mirror (k = 2, build mode 0)
+    kChainUp2,   // FIR7 -> RESIZE2(24)                    cfg2 (k = 0.5, build mode 1)
     kChainCount
 };
 
@@ -61,8 +64,15 @@ struct StepSpec {
 
 inline const StepSpec* chain_spec(int id, int* nsteps) {
     static const StepSpec dil24[] = {{K_RESIZE, AVIRB200_SUM_DIL8, 24, 2}, {K_FIR, AVIRB200_SUM_DIL8, 8, 1}};
+    static const StepSpec inl24[] = {{K_RESIZE, AVIRB200_SUM_INL, 24, 2}, {K_FIR, AVIRB200_SUM_INL, 7, 1}};
+    static const StepSpec inl3[] = {{K_FIR, AVIRB200_SUM_INL, 7, 1}, {K_RESIZE, AVIRB200_SUM_INL, 18, 2},
+                                    {K_FIR, AVIRB200_SUM_INL, 7, 1}};
+    static const StepSpec up2[] = {{K_FIR, AVIRB200_SUM_INL, 7, 1}, {K_RESIZE2, AVIRB200_SUM_INL, 24, 1}};
     switch (id) {
     case kChainDil24: *nsteps = 2; return dil24;
+    case kChainInl24: *nsteps = 2; return inl24;
+    case kChainInl3: *nsteps = 3; return inl3;
+    case kChainUp2: *nsteps = 2; return up2;
     default: *nsteps = 0; return nullptr;
     }
 }

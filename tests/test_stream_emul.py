@@ -40,6 +40,20 @@ EMUL_CASES = [
     ((2, 20, 18, 10, 9, 4, f32, f32, 16, {"buildmode": 1}), 2, 2, 2),     # shorter than the pipeline
     ((2, 34, 6, 17, 3, 4, f32, f32, 16, {"buildmode": 1}), 1, 40, 1),     # more warps than rounds
     ((2, 640, 40, 320, 20, 4, f32, f32, 16, {"buildmode": 1}), 9, 2, 5),
+    # interleaved classes, k = 2 in build mode 1: RESIZE(24) -> FIR(7)
+    ((1, 192, 108, 96, 54, 4, f32, f32, 16, {"buildmode": 1}), 3, 2, 1),
+    ((0, 100, 70, 50, 35, 4, f32, u8, 8, {"buildmode": 1}), 4, 3, 2),
+    ((1, 100, 70, 50, 35, 4, f32, u16, 16, {"buildmode": 1}), 2, 5, 3),
+    # cfg3 float4 mirror chain (build mode 0): FIR(7) -> RESIZE(18) -> FIR(7)
+    ((1, 192, 108, 96, 54, 4, f32, f32, 16, {"buildmode": 0}), 3, 2, 1),
+    ((1, 100, 70, 50, 35, 4, f32, f32, 16, {"buildmode": 0}), 4, 3, 2),
+    ((1, 20, 18, 10, 9, 4, f32, u8, 16, {"buildmode": 0}), 2, 2, 2),
+    ((1, 640, 40, 320, 20, 4, f32, f32, 16, {"buildmode": 0}), 9, 2, 5),
+    # cfg2 chain (k = 0.5, build mode 1): FIR(7) -> RESIZE(24) over the virtual 2X line
+    ((1, 96, 54, 192, 108, 4, f32, f32, 8, {"buildmode": 1}), 3, 2, 1),
+    ((1, 50, 35, 100, 70, 4, f32, u8, 8, {"buildmode": 1}), 4, 3, 2),
+    ((1, 10, 9, 20, 18, 4, f32, f32, 8, {"buildmode": 1}), 2, 2, 2),
+    ((1, 320, 20, 640, 40, 4, f32, u8, 8, {"buildmode": 1}), 9, 2, 5),
 ]
 
 
