@@ -1,8 +1,13 @@
 // lancir.cu -- LANCIR (upstream lancir.h) on sm_100a: column pass, row pass + output.
 //
-// Arithmetic to mirror (4-channel images, upstream AVX/SSE2 build; lancir.h:2466-2515):
+// Arithmetic to mirror (upstream AVX build).  4-channel images (resize4, lancir.h:2466-2515):
 // per channel two interleaved partial sums over the taps -- even taps into one, odd taps
-// into the other -- added at the end.  Source reads clamp to the image (upstream pads by
+// into the other -- added at the end.  1- and 2-channel images (resize1/resize2,
+// lancir.h:2101-2320): four chains S0..S3 over taps j mod 4, joined as (S0+S2)+(S1+S3); when
+// kl%4 == 2 the last two products join as ((S0+S2)+Pa)+((S1+S3)+Pb).  3-channel images
+// (resize3, lancir.h:2322-2440): the same four chains, Pa folded into chain 0, Pb folded
+// into chain 1 for channel 0 but added last for channels 1 and 2; tree (S0+S1)+(S2+S3).
+// Source reads clamp to the image (upstream pads by
 // replication: copyScanlineNv lancir.h:1406-1594, padScanlineNh 1611-1734).  Output
 // (lancir.h:1772-2056): optional multiply, clamp, round-to-nearest-even; the last
 // `(NewWidth*C) & 3` elements of a row round as (int)(v + 0.5f) instead.
@@ -62,6 +67,45 @@ __device__ __forceinline__ float lload(const void* p, int type, long long i) {
     return ((const float*)p)[i];
 }
 
+// One output sample: the tap sum in upstream's order for `C` channels, channel `c`.
+template <class G>
+__device__ __forceinline__ float ltapsum(const int C, const int c, const int kl,
+                                         const float* __restrict__ f, G get) {
+    if (C == 4) {
+        float ev = __fmul_rn(__ldg(f), get(0)), od = __fmul_rn(__ldg(f + 1), get(1));
+        for (int t = 2; t < kl; t += 2) {
+            ev = __fadd_rn(ev, __fmul_rn(__ldg(f + t), get(t)));
+            od = __fadd_rn(od, __fmul_rn(__ldg(f + t + 1), get(t + 1)));
+        }
+        return __fadd_rn(ev, od);
+    }
+    const int n4 = kl & ~3;
+    float s0 = __fmul_rn(__ldg(f), get(0)), s1 = __fmul_rn(__ldg(f + 1), get(1));
+    float s2 = __fmul_rn(__ldg(f + 2), get(2)), s3 = __fmul_rn(__ldg(f + 3), get(3));
+    for (int t = 4; t < n4; t += 4) {
+        s0 = __fadd_rn(s0, __fmul_rn(__ldg(f + t), get(t)));
+        s1 = __fadd_rn(s1, __fmul_rn(__ldg(f + t + 1), get(t + 1)));
+        s2 = __fadd_rn(s2, __fmul_rn(__ldg(f + t + 2), get(t + 2)));
+        s3 = __fadd_rn(s3, __fmul_rn(__ldg(f + t + 3), get(t + 3)));
+    }
+    const bool rem = (kl & 3) == 2;
+    float pa = 0.0f, pb = 0.0f;
+    if (rem) {
+        pa = __fmul_rn(__ldg(f + n4), get(n4));
+        pb = __fmul_rn(__ldg(f + n4 + 1), get(n4 + 1));
+    }
+    if (C == 3) {
+        if (rem) s0 = __fadd_rn(s0, pa);
+        if (rem && c == 0) s1 = __fadd_rn(s1, pb);
+        float r = __fadd_rn(__fadd_rn(s0, s1), __fadd_rn(s2, s3));
+        if (rem && c != 0) r = __fadd_rn(r, pb);
+        return r;
+    }
+    float a = __fadd_rn(s0, s2), b = __fadd_rn(s1, s3);
+    if (rem) { a = __fadd_rn(a, pa); b = __fadd_rn(b, pb); }
+    return __fadd_rn(a, b);
+}
+
 // Column pass: one thread per (x, c) element of an output row; grid.y = output row.
 __global__ void __launch_bounds__(256) lancir_col_kernel(const __grid_constant__ LParams p) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x; // element within a row
@@ -71,16 +115,15 @@ __global__ void __launch_bounds__(256) lancir_col_kernel(const __grid_constant__
     const int kl = p.v.kl;
     const float* f = p.v.taps + (size_t)__ldg(p.v.phase + y) * kl;
     const int s0 = __ldg(p.v.src_pos + y);
-    float ev = 0.0f, od = 0.0f;
-    for (int t = 0; t < kl; ++t) {
+    const void* src = p.src;
+    const int in_type = p.in_type, src_h = p.src_h;
+    const long long pitch = p.src_pitch;
+    const float r = ltapsum(p.C, e % p.C, kl, f, [&](int t) {
         int sy = s0 + t;
-        sy = sy < 0 ? 0 : (sy >= p.src_h ? p.src_h - 1 : sy);
-        const float prod = __fmul_rn(__ldg(f + t), lload(p.src, p.in_type, (long long)sy * p.src_pitch + e));
-        if (t < 2) { if (t == 0) ev = prod; else od = prod; }
-        else if (t & 1) od = __fadd_rn(od, prod);
-        else ev = __fadd_rn(ev, prod);
-    }
-    p.mid[(size_t)y * row_elems + e] = __fadd_rn(ev, od);
+        sy = sy < 0 ? 0 : (sy >= src_h ? src_h - 1 : sy);
+        return lload(src, in_type, (long long)sy * pitch + e);
+    });
+    p.mid[(size_t)y * row_elems + e] = r;
 }
 
 // Row pass + output: one thread per output element; grid.y = row.
@@ -94,16 +137,12 @@ __global__ void __launch_bounds__(256) lancir_row_kernel(const __grid_constant__
     const float* f = p.h.taps + (size_t)__ldg(p.h.phase + x) * kl;
     const int s0 = __ldg(p.h.src_pos + x);
     const float* row = p.mid + (size_t)y * p.src_w * p.C;
-    float ev = 0.0f, od = 0.0f;
-    for (int t = 0; t < kl; ++t) {
+    const int C = p.C, src_w = p.src_w;
+    float v = ltapsum(C, c, kl, f, [&](int t) {
         int sx = s0 + t;
-        sx = sx < 0 ? 0 : (sx >= p.src_w ? p.src_w - 1 : sx);
-        const float prod = __fmul_rn(__ldg(f + t), row[(size_t)sx * p.C + c]);
-        if (t < 2) { if (t == 0) ev = prod; else od = prod; }
-        else if (t & 1) od = __fadd_rn(od, prod);
-        else ev = __fadd_rn(ev, prod);
-    }
-    float v = __fadd_rn(ev, od);
+        sx = sx < 0 ? 0 : (sx >= src_w ? src_w - 1 : sx);
+        return row[(size_t)sx * C + c];
+    });
     if (!p.unity) v = __fmul_rn(v, p.out_mul);
     const long long g = (long long)y * p.dst_pitch + e;
     if (p.out_type == AVIRB200_F32) {
@@ -145,7 +184,9 @@ extern "C" {
 int lancirb200_plan_create(const lancirb200_plan_desc* d, lancirb200_plan** out) {
     if (d == nullptr || out == nullptr) return lfail(AVIRB200_ERR_BAD_ARG, "null argument");
     *out = nullptr;
-    if (d->channels != 4) return lfail(AVIRB200_ERR_UNSUPPORTED, "LANCIR GPU path is 4-channel");
+    if (d->channels < 1 || d->channels > 4) return lfail(AVIRB200_ERR_BAD_ARG, "channels must be 1..4");
+    if (d->v.kernel_len < 4 || d->h.kernel_len < 4 || ((d->v.kernel_len | d->h.kernel_len) & 1))
+        return lfail(AVIRB200_ERR_BAD_ARG, "kernel length must be even and >= 4");
     if (d->src_w < 1 || d->src_h < 1 || d->dst_w < 1 || d->dst_h < 1)
         return lfail(AVIRB200_ERR_BAD_ARG, "bad geometry");
     for (int a = 0; a < 2; ++a) {

@@ -6,9 +6,8 @@
 // 1/1000 phase quantisation); the two filtering passes (columns first, then rows) and the
 // output conversion run as sm_100a kernels behind the C ABI in avirb200.h.
 //
-// Bit-exact scope: 4-channel images mirror upstream's AVX/SSE2 summation tree (two
-// interleaved partial sums, lancir.h:2466-2515).  1-3 channel images use other trees
-// upstream; they are rejected (return 0) rather than silently approximated.
+// Bit-exact scope: upstream's AVX build.  Its tap-sum tree differs per channel count
+// (resize1..resize4, lancir.h:2101-2515); the kernels mirror each of the four.
 // There is no CPU fallback.
 
 #ifndef LANCIR_B200_H
@@ -204,7 +203,6 @@ public:
             }
             return NewHeight;
         }
-        if (ElCount != 4) return 0; // outside the bit-exact GPU scope
         const size_t SrcScanlineSize =
             (size_t)(Params.SrcSSize < 1 ? SrcWidth * ElCount : Params.SrcSSize);
         if (!ensurePlan<Tin, Tout>(SrcWidth, SrcHeight, NewWidth, NewHeight, ElCount, Params))

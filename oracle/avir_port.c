@@ -411,25 +411,52 @@ void avir_port_srgb_lut(float* out256)
     for (int i = 0; i < 256; i++) out256[i] = srgb2lin_u8(i);
 }
 
-/* ---- LANCIR (upstream lancir.h), 4-channel restatement -----------------------------------
- * Column pass first (lancir.h:603-646), then row pass + output (lancir.h:650-706); per
- * channel two interleaved partial sums (even / odd taps), resize4: lancir.h:2466-2515.
+/* ---- LANCIR (upstream lancir.h, AVX build), 1-4 channel restatement -----------------------
+ * Column pass first (lancir.h:603-646), then row pass + output (lancir.h:650-706).  Both
+ * passes run the same resizeN tap loop; its summation tree depends on the channel count:
+ *   C=4 (resize4, lancir.h:2466-2515): even taps and odd taps in two chains, added at the end;
+ *   C=1 (resize1, lancir.h:2101-2214) and C=2 (resize2, 2216-2320): four chains S0..S3 over
+ *     taps t = j mod 4 of the first kl&~3 taps; when kl%4 == 2 the last two products Pa, Pb
+ *     join as ((S0+S2)+Pa) + ((S1+S3)+Pb), else (S0+S2)+(S1+S3);
+ *   C=3 (resize3, 2322-2440): same four chains; Pa joins chain 0 before the tree; channel 0
+ *     also folds Pb into chain 1 (lane 3 of the 128-bit accumulator), channels 1 and 2 add
+ *     Pb last: c0 = (S0'+S1')+(S2+S3), c1,c2 = ((S0'+S1)+(S2+S3))+Pb.
  * Output: lancir.h:1772-2056 (vector body rounds to nearest-even, the last (W*C)&3
  * elements of a row use (int)(v+0.5f)). */
 static float lancir_tapsum(const float* f, int kl, const float* base, long long stride, int s0,
-                           int n)
+                           int n, int C, int c)
 {
-    float ev = 0.0f, od = 0.0f;
-    for (int t = 0; t < kl; t++) {
-        int s = s0 + t;
-        s = s < 0 ? 0 : (s >= n ? n - 1 : s);
-        const float prod = f[t] * base[(long long)s * stride];
-        if (t == 0) ev = prod;
-        else if (t == 1) od = prod;
-        else if (t & 1) od += prod;
-        else ev += prod;
+#define LTAP(t) (f[t] * base[(long long)((s0 + (t)) < 0 ? 0 : ((s0 + (t)) >= n ? n - 1 : (s0 + (t)))) * stride])
+    if (C == 4) {
+        float ev = LTAP(0), od = LTAP(1);
+        for (int t = 2; t < kl; t += 2) {
+            ev += LTAP(t);
+            od += LTAP(t + 1);
+        }
+        return ev + od;
     }
-    return ev + od;
+    const int n4 = kl & ~3;
+    float s[4];
+    for (int j = 0; j < 4; j++) s[j] = LTAP(j);
+    for (int t = 4; t < n4; t += 4)
+        for (int j = 0; j < 4; j++) s[j] += LTAP(t + j);
+    const int rem = (kl & 3) == 2;
+    float pa = 0.0f, pb = 0.0f;
+    if (rem) { pa = LTAP(n4); pb = LTAP(n4 + 1); }
+#undef LTAP
+    if (C == 3) {
+        if (rem) s[0] += pa;
+        if (c == 0) {
+            if (rem) s[1] += pb;
+            return (s[0] + s[1]) + (s[2] + s[3]);
+        }
+        float r = (s[0] + s[1]) + (s[2] + s[3]);
+        if (rem) r += pb;
+        return r;
+    }
+    float a = s[0] + s[2], b = s[1] + s[3];
+    if (rem) { a += pa; b += pb; }
+    return a + b;
 }
 
 int lancir_port_resize(const lancirb200_plan_desc* d, const void* src, size_t src_pitch, void* dst,
@@ -446,7 +473,8 @@ int lancir_port_resize(const lancirb200_plan_desc* d, const void* src, size_t sr
         const float* f = d->v.taps + (size_t)d->v.phase[y] * d->v.kernel_len;
         for (int e = 0; e < sw * C; e++)
             mid[(size_t)y * sw * C + e] =
-                lancir_tapsum(f, d->v.kernel_len, in + e, (long long)sw * C, d->v.src_pos[y], sh);
+                lancir_tapsum(f, d->v.kernel_len, in + e, (long long)sw * C, d->v.src_pos[y], sh, C,
+                              e % C);
     }
     const int out_elems = dw * C;
     for (int y = 0; y < dh; y++) {
@@ -454,7 +482,7 @@ int lancir_port_resize(const lancirb200_plan_desc* d, const void* src, size_t sr
             const float* f = d->h.taps + (size_t)d->h.phase[x] * d->h.kernel_len;
             for (int c = 0; c < C; c++) {
                 float v = lancir_tapsum(f, d->h.kernel_len, mid + (size_t)y * sw * C + c, C,
-                                        d->h.src_pos[x], sw);
+                                        d->h.src_pos[x], sw, C, c);
                 if (!d->is_unity_mul) v = v * d->out_mul;
                 const int e = x * C + c;
                 const size_t idx = (size_t)y * dst_pitch + e;

@@ -44,6 +44,16 @@ LANCIR_CASES = [
     (60, 40, 40, 27, u8, u16, {}),
 ]
 
+# (sw, sh, nw, nh, channels, Tin, Tout, la): upstream's 1-3 channel summation trees
+LANCIR_C_CASES = [
+    (64, 48, 103, 77, 3, u8, u8, 3.0),      # BASELINE cfg1 ratio (k = 0.625), RGB
+    (64, 48, 103, 77, 1, u8, u8, 3.0),
+    (64, 48, 103, 77, 2, u16, u16, 3.0),
+    (77, 51, 47, 29, 3, f32, f32, 3.0),     # kernel length 10: kl % 4 == 2 tail
+    (77, 51, 47, 29, 1, f32, f32, 3.0),
+    (77, 51, 47, 29, 2, f32, u8, 3.0),
+]
+
 
 def main():
     assert o.have_ref(), "build oracle/_ref first (make -C oracle ref)"
@@ -61,6 +71,12 @@ def main():
         assert r == nh
         np.savez_compressed(os.path.join(HERE, "lancir_%02d.npz" % i), src=src, out=out,
                             geom=np.array([sw, sh, nw, nh]))
+    for i, (sw, sh, nw, nh, ch, ti, to, la) in enumerate(LANCIR_C_CASES):
+        src = o.lcg_image(sh, sw, ch, ti, seed=300 + i)
+        r, out = o.lancir_ref(src, nw, nh, to, la=la)
+        assert r == nh
+        np.savez_compressed(os.path.join(HERE, "lancir_%02d.npz" % (len(LANCIR_CASES) + i)),
+                            src=src, out=out, geom=np.array([sw, sh, nw, nh]))
     print("wrote", len(GOLDEN_CASES), "AVIR and", len(LANCIR_CASES), "LANCIR fixtures;",
           o.ref().avir_ref_version().decode())
 

@@ -69,5 +69,3 @@ def test_lancir_argument_errors_follow_upstream():
     # lancir.h:392-408: bad sizes / la < 2 -> 0
     r, _ = ab.CLancIR().resizeImage(np.zeros((8, 8, 4), np.uint8), 4, 4, ab.CLancIRParams(la=1.5))
     assert r == 0
-    r, _ = ab.CLancIR().resizeImage(np.zeros((8, 8, 3), np.uint8), 4, 4)  # C != 4: not on GPU path
-    assert r == 0

@@ -230,12 +230,27 @@ LANCIR = [
     (50, 30, 70, 45, np.uint8, np.float32, {"kx": 0.7, "ky": -0.66, "ox": 0.25, "oy": 0.1}),
     (640, 480, 1024, 768, np.uint8, np.uint8, {}),       # BASELINE cfg1 geometry (RGBA)
     (1920, 1080, 960, 540, np.uint8, np.uint8, {}),
+    # 1-3 channel images: upstream's resize1/resize2/resize3 summation trees
+    (640, 480, 1024, 768, np.uint8, np.uint8, {"C": 3}),     # BASELINE cfg1 as quoted (RGB)
+    (640, 480, 1024, 768, np.uint8, np.uint8, {"C": 1}),
+    (640, 480, 1024, 768, np.uint16, np.uint16, {"C": 2}),
+    (64, 48, 103, 77, np.float32, np.float32, {"C": 3, "la": 4.0}),
+    (96, 54, 48, 27, np.uint16, np.uint16, {"C": 3}),
+    (96, 54, 48, 27, np.float32, np.float32, {"C": 2}),
+    (96, 54, 48, 27, np.uint8, np.float32, {"C": 1}),
+    (77, 51, 50, 31, np.float32, np.float32, {"C": 3, "la": 2.0}),
+    (77, 51, 47, 29, np.float32, np.float32, {"C": 1, "la": 3.0, "kx": 1.3, "ky": 2.2}),
+    (77, 51, 47, 29, np.float32, np.float32, {"C": 2, "la": 3.0, "kx": 1.3, "ky": 2.2}),
+    (77, 51, 47, 29, np.float32, np.float32, {"C": 3, "la": 3.0, "kx": 1.3, "ky": 2.2}),
+    (1920, 1080, 1280, 720, np.uint8, np.uint8, {"C": 3}),
+    (33, 21, 7, 5, np.uint8, np.uint8, {"C": 3}),
 ]
 
 
 @pytest.mark.parametrize("sw,sh,nw,nh,ti,to,kw", LANCIR)
 def test_lancir_bit_exact(sw, sh, nw, nh, ti, to, kw):
-    src = o.lcg_image(sh, sw, 4, ti, seed=3)
+    kw = dict(kw)
+    src = o.lcg_image(sh, sw, kw.pop("C", 4), ti, seed=3)
     if o.have_ref():
         r, ref = o.lancir_ref(src, nw, nh, to, **kw)
         assert r == nh

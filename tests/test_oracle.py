@@ -124,6 +124,29 @@ def test_port_matches_golden_fixtures():
         assert cs.count_mismatch(z["out"], mine) == 0, f
 
 
+def test_lancir_port_matches_golden_fixtures():
+    """Pins the LANCIR restatement (all four channel-count trees) where oracle/_ref is absent."""
+    import avir_b200 as ab
+    h = ab.host_lib()
+    T = {np.dtype(np.uint8): 0, np.dtype(np.uint16): 1, np.dtype(np.float32): 2}
+    files = sorted(f for f in os.listdir(cs.GOLDEN) if f.startswith("lancir_"))
+    assert len(files) >= 11 and {np.load(os.path.join(cs.GOLDEN, f))["src"].shape[2]
+                                 for f in files} == {1, 2, 3, 4}
+    for f in files:
+        z = np.load(os.path.join(cs.GOLDEN, f))
+        src, want = np.ascontiguousarray(z["src"]), z["out"]
+        sw, sh, nw, nh = [int(v) for v in z["geom"]]
+        ch = src.shape[2]
+        hd = h.lancirb200_host_desc_create(T[src.dtype], T[want.dtype], sw, sh, nw, nh, ch, 0.0, 0.0,
+                                           0.0, 0.0, 3.0)
+        assert hd
+        dst = np.zeros_like(want)
+        assert cs.port().lancir_port_resize(h.lancirb200_host_desc_get(hd), src.ctypes.data, sw * ch,
+                                            dst.ctypes.data, nw * ch) == 0
+        h.lancirb200_host_desc_free(hd)
+        assert cs.count_mismatch(want, dst) == 0, f
+
+
 @needs_ref
 def test_srgb_u8_table_matches_upstream():
     # feed every byte value through upstream's linearisation: 1x1 float output, no resize
@@ -158,17 +181,35 @@ def test_lancir_port_matches_upstream():
             (50, 30, 70, 45, np.uint8, np.float32, {"kx": 0.7, "ky": -0.66, "ox": 0.25, "oy": 0.1}),
             (50, 30, 25, 15, np.uint8, np.uint8, {"la": 2.0}),
             (50, 30, 25, 15, np.uint8, np.uint8, {"la": 4.5}),
+            # 1-3 channels: upstream's resize1/2/3 trees, kernel lengths 6 (kl%4==2), 8, 12, 10
+            (64, 48, 103, 77, np.uint8, np.uint8, {"C": 3}),
+            (64, 48, 103, 77, np.uint8, np.uint8, {"C": 2}),
+            (64, 48, 103, 77, np.uint8, np.uint8, {"C": 1}),
+            (64, 48, 103, 77, np.float32, np.float32, {"C": 3, "la": 4.0}),
+            (96, 54, 48, 27, np.uint16, np.uint16, {"C": 3}),
+            (96, 54, 48, 27, np.float32, np.float32, {"C": 2}),
+            (96, 54, 48, 27, np.uint8, np.float32, {"C": 1}),
+            (77, 51, 50, 31, np.float32, np.float32, {"C": 3, "la": 2.0}),
+            (77, 51, 50, 31, np.float32, np.float32, {"C": 1, "la": 2.0}),
+            (77, 51, 47, 30, np.uint8, np.uint8, {"C": 2, "la": 3.0}),
+            (77, 51, 47, 29, np.float32, np.float32, {"C": 3, "la": 3.0}),
+            (77, 51, 47, 29, np.float32, np.float32, {"C": 1, "la": 3.0, "kx": 1.3, "ky": 2.2}),
+            (77, 51, 47, 29, np.float32, np.float32, {"C": 2, "la": 3.0, "kx": 1.3, "ky": 2.2}),
+            (77, 51, 47, 29, np.float32, np.float32, {"C": 3, "la": 3.0, "kx": 1.3, "ky": 2.2}),
+            (33, 21, 7, 5, np.uint8, np.uint8, {"C": 3}),
     ]:
-        src = o.lcg_image(sh, sw, 4, ti, seed=3)
+        kw = dict(kw)
+        ch = kw.pop("C", 4)
+        src = o.lcg_image(sh, sw, ch, ti, seed=3)
         r, ref = o.lancir_ref(src, nw, nh, to, **kw)
         assert r == nh
         T = {np.uint8: 0, np.uint16: 1, np.float32: 2}
-        hd = h.lancirb200_host_desc_create(T[ti], T[to], sw, sh, nw, nh, 4, kw.get("kx", 0.0),
+        hd = h.lancirb200_host_desc_create(T[ti], T[to], sw, sh, nw, nh, ch, kw.get("kx", 0.0),
                                            kw.get("ky", 0.0), kw.get("ox", 0.0), kw.get("oy", 0.0),
                                            kw.get("la", 3.0))
         assert hd
-        dst = np.zeros((nh, nw, 4), to)
-        assert cs.port().lancir_port_resize(h.lancirb200_host_desc_get(hd), src.ctypes.data, sw * 4,
-                                            dst.ctypes.data, nw * 4) == 0
+        dst = np.zeros((nh, nw, ch), to)
+        assert cs.port().lancir_port_resize(h.lancirb200_host_desc_get(hd), src.ctypes.data, sw * ch,
+                                            dst.ctypes.data, nw * ch) == 0
         h.lancirb200_host_desc_free(hd)
-        assert cs.count_mismatch(ref, dst) == 0, (sw, sh, nw, nh, ti, to, kw)
+        assert cs.count_mismatch(ref, dst) == 0, (sw, sh, nw, nh, ch, ti, to, kw)
