@@ -123,6 +123,9 @@ struct avirb200_plan {
     void* d_ws = nullptr;
     size_t d_src_bytes = 0, d_dst_bytes = 0, d_ws_bytes = 0;
     cudaStream_t stream = nullptr;
+    // pipelined resize_host: copy-in / copy-out streams and per-band events
+    cudaStream_t stream_in = nullptr, stream_out = nullptr;
+    std::vector<cudaEvent_t> ev_in, ev_out;
     mutable int last_launches = 0;
 };
 
@@ -623,6 +626,10 @@ void avirb200_plan_destroy(avirb200_plan* pl) {
     cudaFree(pl->d_ws);
     fast_plan_free(pl->fast);
     if (pl->stream) cudaStreamDestroy(pl->stream);
+    if (pl->stream_in) cudaStreamDestroy(pl->stream_in);
+    if (pl->stream_out) cudaStreamDestroy(pl->stream_out);
+    for (cudaEvent_t e : pl->ev_in) cudaEventDestroy(e);
+    for (cudaEvent_t e : pl->ev_out) cudaEventDestroy(e);
     delete pl;
 }
 
@@ -698,12 +705,85 @@ int avirb200_resize_host(avirb200_plan* pl, const void* h_src, size_t src_pitch,
         CUDA_TRY(cudaMalloc(&pl->d_ws, ws));
         pl->d_ws_bytes = ws;
     }
-    CUDA_TRY(cudaMemcpy2DAsync(pl->d_src, in_row, h_src, src_pitch * dtype_size(d.in_type), in_row,
+    const size_t in_el = dtype_size(d.in_type), out_el = dtype_size(d.out_type);
+    // Pipelined form for large images: the image is cut into row bands (the multi-GPU band
+    // arithmetic, one shared intermediate buffer instead of a halo exchange).  Band b's rows
+    // travel host->device on the copy-in stream while the kernels of band b-1 run on the
+    // compute stream and band b-2's destination rows travel back on the copy-out stream: the
+    // call takes about as long as the larger of the two PCIe directions instead of their sum.
+    // The arithmetic does not depend on the banding (tests: 8-band schedule == unsharded bits).
+    int nb = (int)(in_bytes >> 25); // bands of >= 32 MiB of source
+    if (nb > 16) nb = 16;
+    if (const char* e = getenv("AVIRB200_HOST_BANDS")) nb = atoi(e); // test / tuning switch
+    {   // an aliased or overlapping destination (upstream allows NewBuf == SrcBuf) must not be
+        // written before the whole source has been read
+        const char* s0 = static_cast<const char*>(h_src);
+        const char* d0 = static_cast<const char*>(h_dst);
+        const char* s1 = s0 + ((size_t)(d.src_h - 1) * src_pitch + (size_t)d.src_w * d.channels) * in_el;
+        const char* d1 = d0 + ((size_t)(d.dst_h - 1) * dst_pitch + (size_t)d.dst_w * d.channels) * out_el;
+        if (s0 < d1 && d0 < s1) nb = 1;
+    }
+    std::vector<avirb200_shard_info> si;
+    while (nb >= 2) { // fewer bands until every band's column pass needs only its neighbours' rows
+        si.assign(nb, avirb200_shard_info());
+        bool ok = true;
+        for (int b = 0; b < nb && ok; ++b) ok = (shard_compute(pl, b, nb, &si[b]) == 0);
+        if (ok) break;
+        nb /= 2;
+    }
+    if (nb >= 2) {
+        if (pl->stream_in == nullptr) CUDA_TRY(cudaStreamCreateWithFlags(&pl->stream_in, cudaStreamNonBlocking));
+        if (pl->stream_out == nullptr) CUDA_TRY(cudaStreamCreateWithFlags(&pl->stream_out, cudaStreamNonBlocking));
+        while ((int)pl->ev_in.size() < nb) {
+            cudaEvent_t e0, e1;
+            CUDA_TRY(cudaEventCreateWithFlags(&e0, cudaEventDisableTiming));
+            pl->ev_in.push_back(e0);
+            CUDA_TRY(cudaEventCreateWithFlags(&e1, cudaEventDisableTiming));
+            pl->ev_out.push_back(e1);
+        }
+        const size_t rowf = (size_t)d.dst_w * d.channels;
+        const size_t dsrc_pitch = (size_t)d.src_w * d.channels, ddst_pitch = rowf;
+        int launches = 0;
+        for (int b = 0; b < nb; ++b) {
+            CUDA_TRY(cudaMemcpy2DAsync(static_cast<char*>(pl->d_src) + (size_t)si[b].src_row0 * in_row, in_row,
+                                       static_cast<const char*>(h_src) + (size_t)si[b].src_row0 * src_pitch * in_el,
+                                       src_pitch * in_el, in_row, si[b].src_rows, cudaMemcpyHostToDevice,
+                                       pl->stream_in));
+            CUDA_TRY(cudaEventRecord(pl->ev_in[b], pl->stream_in));
+        }
+        auto col_band = [&](int b) -> int {
+            char* dd = static_cast<char*>(pl->d_dst) + (size_t)si[b].dst_row0 * out_row;
+            int r = run_col_pass(pl, static_cast<const float*>(pl->d_ws), 0, dd, ddst_pitch, si[b].dst_row0,
+                                 si[b].dst_row0 + si[b].dst_rows, pl->stream, &launches);
+            if (r != 0) return r;
+            CUDA_TRY(cudaEventRecord(pl->ev_out[b], pl->stream));
+            CUDA_TRY(cudaStreamWaitEvent(pl->stream_out, pl->ev_out[b], 0));
+            CUDA_TRY(cudaMemcpy2DAsync(static_cast<char*>(h_dst) + (size_t)si[b].dst_row0 * dst_pitch * out_el,
+                                       dst_pitch * out_el, dd, out_row, out_row, si[b].dst_rows,
+                                       cudaMemcpyDeviceToHost, pl->stream_out));
+            return 0;
+        };
+        for (int b = 0; b < nb; ++b) {
+            CUDA_TRY(cudaStreamWaitEvent(pl->stream, pl->ev_in[b], 0));
+            int r = run_row_pass(pl, static_cast<const char*>(pl->d_src) + (size_t)si[b].src_row0 * in_row,
+                                 dsrc_pitch, static_cast<float*>(pl->d_ws) + (size_t)si[b].src_row0 * rowf,
+                                 si[b].src_rows, pl->stream, &launches);
+            if (r != 0) return r;
+            if (b > 0 && (r = col_band(b - 1)) != 0) return r; // needs rows of bands b-2 .. b only
+        }
+        int r = col_band(nb - 1);
+        if (r != 0) return r;
+        pl->last_launches = launches;
+        CUDA_TRY(cudaStreamSynchronize(pl->stream_out));
+        CUDA_TRY(cudaStreamSynchronize(pl->stream));
+        return 0;
+    }
+    CUDA_TRY(cudaMemcpy2DAsync(pl->d_src, in_row, h_src, src_pitch * in_el, in_row,
                                d.src_h, cudaMemcpyHostToDevice, pl->stream));
     int r = avirb200_resize_device(pl, pl->d_src, (size_t)d.src_w * d.channels, pl->d_dst,
                                    (size_t)d.dst_w * d.channels, pl->d_ws, pl->stream);
     if (r != 0) return r;
-    CUDA_TRY(cudaMemcpy2DAsync(h_dst, dst_pitch * dtype_size(d.out_type), pl->d_dst, out_row,
+    CUDA_TRY(cudaMemcpy2DAsync(h_dst, dst_pitch * out_el, pl->d_dst, out_row,
                                out_row, d.dst_h, cudaMemcpyDeviceToHost, pl->stream));
     CUDA_TRY(cudaStreamSynchronize(pl->stream));
     return 0;

@@ -131,11 +131,45 @@ struct ChainC {
 AVS_FN int imin_(int a, int b) { return a < b ? a : b; }
 AVS_FN int imax_(int a, int b) { return a > b ? a : b; }
 
-AVS_FN float2 f2mul(float t, float2 x) { return make_float2(__fmul_rn(t, x.x), __fmul_rn(t, x.y)); }
-AVS_FN float2 f2add(float2 a, float2 b) { return make_float2(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y)); }
-AVS_FN float2 f2hadd8(const float2* v) {
+// The two channels a lane owns travel as one packed pair.  Upstream multiplies and adds
+// separately (two roundings per tap), so the packed fused multiply-add is not usable; the
+// packed multiply is, and the packed add is written as fma(a, 1, b) -- exactly round(a + b)
+// -- with the 1 read from the kernel parameters: ptxas 12.9 contracts mul.rn.f32x2 feeding
+// add.rn.f32x2 (and feeding an fma by a literal 1) into one FFMA2 even under -fmad=false,
+// a run-time 1 it cannot.  Two lanes per issued instruction: the FP32 pipe's time is the
+// same, the issue slots halve (the loops are issue-bound: profiles/r01_stream_ncu_summary).
+#if defined(__CUDACC__) && !defined(AVS_SCALAR_MATH)
+#define AVS_PACKED_MATH 1
+typedef unsigned long long avs_u64;
+AVS_FN avs_u64 f2pk(float2 v) {
+    avs_u64 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(v.x), "f"(v.y));
+    return r;
+}
+AVS_FN float2 f2up(avs_u64 v) {
+    float2 r;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+    return r;
+}
+AVS_FN float2 f2mul(const StreamTap& t, float2 x) {
+    avs_u64 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(f2pk(x)), "l"(f2pk(make_float2(t.lo, t.hi))));
+    return f2up(r);
+}
+AVS_FN float2 f2add(float2 a, float2 b, const StreamTap& one) {
+    avs_u64 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(f2pk(a)), "l"(f2pk(make_float2(one.lo, one.hi))), "l"(f2pk(b)));
+    return f2up(r);
+}
+#else
+#define AVS_PACKED_MATH 0
+AVS_FN float2 f2mul(const StreamTap& t, float2 x) { return make_float2(__fmul_rn(t.lo, x.x), __fmul_rn(t.hi, x.y)); }
+AVS_FN float2 f2add(float2 a, float2 b, const StreamTap&) { return make_float2(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y)); }
+#endif
+AVS_FN float2 f2hadd8(const float2* v, const StreamTap& one) {
     // float8::hadd (avir_float8_avx.h:264-273)
-    return f2add(f2add(f2add(v[0], v[4]), f2add(v[1], v[5])), f2add(f2add(v[2], v[6]), f2add(v[3], v[7])));
+    return f2add(f2add(f2add(v[0], v[4], one), f2add(v[1], v[5], one), one),
+                 f2add(f2add(v[2], v[6], one), f2add(v[3], v[7], one), one), one);
 }
 
 #if defined(__CUDACC__)
@@ -165,7 +199,8 @@ AVS_FN int in_first(const StreamStep& sp, int j) {
 // ---- arithmetic of one output from a register window (x[off ...]) ------------------------------
 
 template <class S, class X>
-AVS_FN float2 fir_one(const X& x, const int off, const float* t) {
+AVS_FN float2 fir_one(const X& x, const int off, const StreamTap* t) {
+    const StreamTap& one = t[kTapOne];
     if (S::SUM == AVIRB200_SUM_DIL8) {
         float2 ln[8];
 #pragma unroll
@@ -173,20 +208,21 @@ AVS_FN float2 fir_one(const X& x, const int off, const float* t) {
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
                 const float2 v = f2mul(t[g * 8 + q], x[off + g * 8 + q]);
-                ln[q] = (g == 0) ? v : f2add(ln[q], v);
+                ln[q] = (g == 0) ? v : f2add(ln[q], v, one);
             }
         }
-        return f2hadd8(ln);
+        return f2hadd8(ln, one);
     }
     constexpr int L = S::NT / 2;
     float2 s = f2mul(t[L], x[off + L]);
 #pragma unroll
-    for (int i = 1; i <= L; ++i) s = f2add(s, f2mul(t[L + i], f2add(x[off + L + i], x[off + L - i])));
+    for (int i = 1; i <= L; ++i) s = f2add(s, f2mul(t[L + i], f2add(x[off + L + i], x[off + L - i], one)), one);
     return s;
 }
 
 template <class S, class X>
-AVS_FN float2 resize_one(const X& x, const int off, const float* t, int zero_start) {
+AVS_FN float2 resize_one(const X& x, const int off, const StreamTap* t, int zero_start) {
+    const StreamTap& one = t[kTapOne];
     float2 r;
     if (S::SUM == AVIRB200_SUM_DIL8) {
         float2 ln[8];
@@ -195,26 +231,27 @@ AVS_FN float2 resize_one(const X& x, const int off, const float* t, int zero_sta
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
                 const float2 v = f2mul(t[g * 8 + q], x[off + g * 8 + q]);
-                ln[q] = (g == 0) ? v : f2add(ln[q], v);
+                ln[q] = (g == 0) ? v : f2add(ln[q], v, one);
             }
         }
-        r = f2hadd8(ln);
+        r = f2hadd8(ln, one);
     } else {
         r = f2mul(t[0], x[off]);
 #pragma unroll
-        for (int i = 1; i < S::NT; ++i) r = f2add(r, f2mul(t[i], x[off + i]));
+        for (int i = 1; i < S::NT; ++i) r = f2add(r, f2mul(t[i], x[off + i]), one);
     }
-    if (zero_start) r = f2add(r, make_float2(0.0f, 0.0f));
+    if (zero_start) r = f2add(r, make_float2(0.0f, 0.0f), one);
     return r;
 }
 
 // fo = parity of the output's first virtual position = index of its first tap
 template <class S, class X>
-AVS_FN float2 resize2_one(const X& x, const int off, const int fo, const float* t, int zero_start) {
+AVS_FN float2 resize2_one(const X& x, const int off, const int fo, const StreamTap* t, int zero_start) {
+    const StreamTap& one = t[kTapOne];
     float2 r = f2mul(t[fo], x[off]);
 #pragma unroll
-    for (int k = 1; k < S::NT / 2; ++k) r = f2add(r, f2mul(t[fo + 2 * k], x[off + k]));
-    if (zero_start) r = f2add(r, make_float2(0.0f, 0.0f));
+    for (int k = 1; k < S::NT / 2; ++k) r = f2add(r, f2mul(t[fo + 2 * k], x[off + k]), one);
+    if (zero_start) r = f2add(r, make_float2(0.0f, 0.0f), one);
     return r;
 }
 

@@ -16,12 +16,19 @@ constexpr int kMaxSteps = 3;
 enum { K_FIR = 0, K_RESIZE = 1, K_RESIZE2 = 2, K_NONE = 3 };
 
 // Run-time description of one step (kernel parameters: taps are constant-bank operands).
+// A tap is stored as the pair (t, t): one operand of the packed two-lane multiply
+// (mul.rn.f32x2, a lane pair = the two channels a thread owns).  taps[kTapOne] = (1, 1) is
+// the multiplier of the packed add, see f2add() in stream_kernel.cuh.
+constexpr int kTapOne = 64;
+struct StreamTap {
+    float lo, hi;
+};
 struct StreamStep {
     int out_len, in_len;
     int edge, latency;  // FIR
     int sp_first;       // RESIZE/RESIZE2: source position of output 0 (position j: sp_first + ADV*j)
     int zero_start;
-    float taps[64];
+    StreamTap taps[kTapOne + 1];
 };
 
 struct StreamParams {
@@ -83,12 +90,13 @@ inline bool stream_match_step(const avirb200_step_desc& d, const StepSpec& sp, S
     out.out_len = d.out_len;
     out.in_len = d.in_len;
     out.zero_start = d.zero_start;
+    out.taps[kTapOne].lo = out.taps[kTapOne].hi = 1.0f;
     if (sp.kind == K_FIR) {
         if (d.kind != AVIRB200_STEP_FIR || d.ntaps != sp.nt || d.resample != sp.adv) return false;
         if (sp.sum == AVIRB200_SUM_INL && d.ntaps != 2 * d.latency + 1) return false;
         out.edge = d.edge;
         out.latency = d.latency;
-        for (int t = 0; t < d.ntaps; ++t) out.taps[t] = d.taps[t];
+        for (int t = 0; t < d.ntaps; ++t) out.taps[t].lo = out.taps[t].hi = d.taps[t];
         return true;
     }
     if (d.kind != AVIRB200_STEP_RESIZE || d.ntaps != sp.nt || d.ntaps > 64 || d.out_len < 1) return false;
@@ -113,10 +121,11 @@ inline bool stream_match_step(const avirb200_step_desc& d, const StepSpec& sp, S
     for (int t = 0; t < d.ntaps; ++t) {
         if (d.order) {
             volatile float prod = c0[d.ntaps + t] * d.frac[0];
-            out.taps[t] = c0[t] + prod;
+            out.taps[t].lo = c0[t] + prod;
         } else {
-            out.taps[t] = c0[t];
+            out.taps[t].lo = c0[t];
         }
+        out.taps[t].hi = out.taps[t].lo;
     }
     return true;
 }

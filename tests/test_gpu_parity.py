@@ -112,6 +112,43 @@ def test_generic_and_fast_kernels_agree_on_medium():
     assert cs.count_mismatch(a, b) == 0
 
 
+# ---- pipelined host call: row bands over copy-in / compute / copy-out streams ----------------
+
+@pytest.mark.parametrize("bands", [2, 3, 7, 16])
+@pytest.mark.parametrize("case", [MEDIUM[0], MEDIUM[2], MEDIUM[3], MEDIUM[4], MEDIUM[6],
+                                  (0, 300, 200, 431, 287, 3, np.uint8, np.uint8, 8, {})], ids=cs.case_id)
+def test_banded_host_call_matches_single_band(case, bands):
+    """avirb200_resize_host cuts large images into row bands so that PCIe transfers overlap the
+    kernels; the band count must not change a bit (AVIRB200_HOST_BANDS forces it)."""
+    src = cs.make_input(case, seed=23)
+    os.environ["AVIRB200_HOST_BANDS"] = "1"
+    try:
+        one = cs.gpu_output(case, src)
+        os.environ["AVIRB200_HOST_BANDS"] = str(bands)
+        many = cs.gpu_output(case, src)
+    finally:
+        del os.environ["AVIRB200_HOST_BANDS"]
+    assert cs.count_mismatch(one, many) == 0
+    if o.have_ref():
+        assert cs.count_mismatch(expected(case, src), many) == 0
+
+
+def test_banded_host_call_in_place():
+    """NewBuf may alias SrcBuf (avir.h:4650-4652): the banded path must not be taken then."""
+    case = (1, 512, 512, 256, 256, 4, np.uint8, np.uint8, 8, {})
+    src = cs.make_input(case, seed=29)
+    want = cs.gpu_output(case, src)
+    os.environ["AVIRB200_HOST_BANDS"] = "4"  # the overlap check must win over the forced banding
+    try:
+        buf = src.copy()
+        rs = ab.CImageResizer(8, 0, 0, ab.FP_FLOAT4)
+        dst = buf.reshape(-1)[:256 * 256 * 4].reshape(256, 256, 4)
+        out = rs.resizeImage(buf, 256, 256, NewBuf=dst)
+    finally:
+        del os.environ["AVIRB200_HOST_BANDS"]
+    assert cs.count_mismatch(want, out) == 0
+
+
 # ---- BASELINE.json full sizes ----------------------------------------------------------------
 
 def _device_run(case, src, sharded_local=0):
