@@ -318,9 +318,12 @@ int run_row_pass(const avirb200_plan* pl, const void* d_src, size_t src_pitch, f
     if (rows <= 0) return 0;
     const avirb200_plan_desc& d = pl->desc;
     if (g_kernel_mode == 0 && env_stream_enabled() && pl->stream_h.chain != 0 &&
-        ((uintptr_t)d_src % 16) == 0 && (src_pitch % 4) == 0 && ((uintptr_t)d_mid % 16) == 0) {
+        ((uintptr_t)d_src % (4 * dtype_size(d.in_type))) == 0 && (src_pitch % 4) == 0 &&
+        ((uintptr_t)d_mid % 16) == 0) {
+        // (every pixel of the source must be aligned to its own size: the copies move whole pixels)
         avs::StreamParams sp;
         avs::stream_fill_params(sp, pl->stream_h, d);
+        sp.src_type = d.in_type;
         sp.n_lines = rows;
         sp.out0 = 0;
         sp.out1 = d.dst_w;
@@ -612,8 +615,11 @@ int avirb200_plan_create(const avirb200_plan_desc* desc, avirb200_plan** out) {
     pl->cfg_h = choose_generic_config(pl->h.hostdev, desc->channels, 0, desc->dst_w);
     pl->cfg_v = choose_generic_config(pl->v.hostdev, desc->channels, 0, desc->dst_h);
     fast_plan_init(pl->fast, pl->h.hostdev, pl->v.hostdev, *desc);
-    if (avs::stream_row_source_ok(*desc)) avs::stream_plan_axis(desc->h, desc->sum_mode, desc->channels, pl->stream_h);
-    avs::stream_plan_axis(desc->v, desc->sum_mode, desc->channels, pl->stream_v);
+    const char* up2e = getenv("AVIRB200_STREAM_UP2"); // tuning switch, see stream_plan_axis()
+    const bool up2 = up2e && up2e[0] == '1';
+    if (avs::stream_row_source_ok(*desc))
+        avs::stream_plan_axis(desc->h, desc->sum_mode, desc->channels, pl->stream_h, up2);
+    avs::stream_plan_axis(desc->v, desc->sum_mode, desc->channels, pl->stream_v, up2);
     *out = pl.release();
     return 0;
 }

@@ -84,14 +84,18 @@ constexpr int cdiv(int a, int b) { return (a + b - 1) / b; }
 //   reps[i]  batches of step i per round
 //   delay[i] rounds step i lags behind step 0
 //   rsp[i]   positions in the ring step i reads (ring 0 = source)
-template <class S0, class S1, class S2, int REPS_LAST, int LA, int STEADY_ = 1, int PRE_ = 0>
+//   SRCT     element type of the row pass's source image (AVIRB200_F32 / _U8 / _U16): integer
+//            pixels stream into the source ring as they are (4 / 8 bytes per pixel) and are
+//            converted -- upstream's packScanline cast, avir.h:2777-2971 -- in the lanes' reads
+template <class S0, class S1, class S2, int REPS_LAST, int LA, int STEADY_ = 1, int PRE_ = 0, int SRCT_ = AVIRB200_F32>
 struct ChainC {
     using T0 = S0;
     using T1 = S1;
     using T2 = S2;
+    static constexpr int SRCT = SRCT_;
+    static constexpr int PIXB = (SRCT == AVIRB200_F32) ? 16 : (SRCT == AVIRB200_U16 ? 8 : 4); // bytes per source pixel
     static constexpr int NS = (S2::KIND == K_NONE) ? 2 : 3;
     static constexpr int LOOKAHEAD = LA;
-    static constexpr int NWARPS = 8; // warps per block (one block per SM)
     static constexpr bool STEADY_LOOP = (STEADY_ != 0); // straight-line code for the interior rounds of a run
     static constexpr int reps2 = (NS == 3) ? REPS_LAST : 0;
     static constexpr int reps1 = (NS == 3) ? (S2::CH * reps2) / S1::M : REPS_LAST;
@@ -120,10 +124,17 @@ struct ChainC {
     static constexpr int MLAST = (NS == 3) ? S2::M : S1::M;
 
     // shared memory of one warp, in float2 units
-    static constexpr int LINE_F2 = rsp0 * 2 + 2; // row pass: float2 units per line of the source ring
+    static constexpr int LINE_B = (rsp0 + 1) * PIXB; // row pass: bytes per line of the source ring (one pixel of padding)
+    static constexpr int SRC_RING_F2 = (kLines * LINE_B + 15) / 16 * 2;
     static constexpr int STAGE_LINE = MLAST * 2 + 2;
-    static constexpr int WARP_F2_H = kLines * LINE_F2 + (rsp1 + rsp2) * kPitchL + kLines * STAGE_LINE;
+    static constexpr int WARP_F2_H = SRC_RING_F2 + (rsp1 + rsp2) * kPitchL + kLines * STAGE_LINE;
     static constexpr int WARP_F2_V = rsp0 * kPitchL + (rsp1 + rsp2) * kPitchL;
+    // warps per block (one block per SM): 8 (two per scheduler; the register windows leave room
+    // for no more), fewer where the rings of 8 warps exceed the shared memory of an SM
+    static constexpr int kSmemF2 = 227 * 1024 / 8;
+    static constexpr int NWARPS_H = (8 * WARP_F2_H <= kSmemF2) ? 8 : kSmemF2 / WARP_F2_H;
+    static constexpr int NWARPS_V = (8 * WARP_F2_V <= kSmemF2) ? 8 : kSmemF2 / WARP_F2_V;
+    static_assert(NWARPS_H >= 4 && NWARPS_V >= 4, "per-warp rings too large");
 };
 
 // ---- small helpers ---------------------------------------------------------------------------------
@@ -177,11 +188,23 @@ AVS_FN void cp_async16(void* smem, const void* gmem) {
     const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
 }
+// N bytes (4, 8: one integer pixel; through L1, the only form the small sizes have)
+template <int N>
+AVS_FN void cp_async_px(void* smem, const void* gmem) {
+    if (N == 16) {
+        cp_async16(smem, gmem);
+    } else {
+        const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(sa), "l"(gmem), "n"(N) : "memory");
+    }
+}
 AVS_FN void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 AVS_FN void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 #else
 AVS_FN void cp_async16(void* smem, const void* gmem) { memcpy(smem, gmem, 16); }
+template <int N>
+AVS_FN void cp_async_px(void* smem, const void* gmem) { memcpy(smem, gmem, N); }
 AVS_FN void cp_async_commit() {}
 template <int N>
 AVS_FN void cp_async_wait() {}
@@ -288,7 +311,7 @@ struct WarpRun {
     // (they point one sweep behind and are advanced BEFORE use: the copies read them in place
     // and the next write to them is a whole round away -- no write-after-read wait on the
     // copy queue)
-    const float4* gp[8];
+    const unsigned char* gp[8];
     // row pass: the previous final batch, read back from the staging rows, waiting to be stored
     float4 pend[C::MLAST / 2];
     int pend_j0;
@@ -300,10 +323,36 @@ struct WarpRun {
 template <class C, bool IS_V, int I>
 struct RingOf {
     static constexpr int RSP = (I == 0) ? C::rsp0 : (I == 1 ? C::rsp1 : C::rsp2);
-    // float2 units between consecutive positions, and the lane's own offset
-    static constexpr int PITCH = (I == 0 && !IS_V) ? 2 : kPitchL;
-    static AVS_FN int lane_off(int lane) {
-        return (I == 0 && !IS_V) ? (lane >> 1) * C::LINE_F2 + (lane & 1) : lane;
+    // the row pass's source ring holds raw pixels [line][position]; every other ring float2 [position][lane]
+    static constexpr bool RAW = (I == 0 && !IS_V);
+    static constexpr int SRCT = RAW ? C::SRCT : AVIRB200_F32;
+    // bytes between consecutive positions, and the lane's own offset
+    static constexpr int PITCH_B = RAW ? C::PIXB : kPitchL * 8;
+    static AVS_FN int lane_off_b(int lane) {
+        return RAW ? (lane >> 1) * C::LINE_B + (lane & 1) * (C::PIXB / 2) : lane * 8;
+    }
+    // the lane's channel pair at `p`; integer pixels convert exactly ((float) cast)
+    static AVS_FN float2 load(const unsigned char* p) {
+        if (SRCT == AVIRB200_U8) {
+            const unsigned v = *reinterpret_cast<const unsigned short*>(p);
+#if defined(__CUDACC__)
+            // byte b -> bits of 2^23 + b (mantissa insert), minus 2^23: exact, no I2F
+            return make_float2(__fsub_rn(__uint_as_float(__byte_perm(v, 0x4B000000u, 0x7540)), 8388608.0f),
+                               __fsub_rn(__uint_as_float(__byte_perm(v, 0x4B000000u, 0x7541)), 8388608.0f));
+#else
+            return make_float2((float)(v & 255u), (float)(v >> 8));
+#endif
+        }
+        if (SRCT == AVIRB200_U16) {
+            const unsigned v = *reinterpret_cast<const unsigned*>(p);
+#if defined(__CUDACC__)
+            return make_float2(__fsub_rn(__uint_as_float(__byte_perm(v, 0x4B000000u, 0x7410)), 8388608.0f),
+                               __fsub_rn(__uint_as_float(__byte_perm(v, 0x4B000000u, 0x7432)), 8388608.0f));
+#else
+            return make_float2((float)(v & 65535u), (float)(v >> 16));
+#endif
+        }
+        return *reinterpret_cast<const float2*>(p);
     }
 };
 
@@ -311,18 +360,20 @@ struct RingOf {
 
 template <class C, bool IS_V>
 AVS_FN void loader_init(const StreamParams& p, WarpRun<C, IS_V>& w) {
-    const float4* src = static_cast<const float4*>(p.src);
-    const size_t pitch4 = (size_t)(p.src_pitch / 4); // float4 units between rows
+    constexpr int PIXB = IS_V ? 16 : C::PIXB;
+    const unsigned char* src = static_cast<const unsigned char*>(p.src);
+    const size_t rowb = (size_t)p.src_pitch * (PIXB / 4); // bytes between rows (pitch is in elements)
     const int lane = w.lane;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
         if (IS_V) {
             const int piece = lane & 15, rsub = lane >> 4;
-            w.gp[k] = src + (ptrdiff_t)(w.o0 - 16 + rsub + 2 * k - p.src_row_base) * (ptrdiff_t)pitch4 + w.line0 +
-                      imin_(piece, w.nlines - 1);
+            w.gp[k] = src + (ptrdiff_t)(w.o0 - 16 + rsub + 2 * k - p.src_row_base) * (ptrdiff_t)rowb +
+                      (size_t)(w.line0 + imin_(piece, w.nlines - 1)) * 16;
         } else {
             const int pos = lane & 15, lsub = lane >> 4;
-            w.gp[k] = src + (size_t)(w.line0 + imin_(lsub + 2 * k, w.nlines - 1)) * pitch4 + (ptrdiff_t)(w.o0 - 16 + pos);
+            w.gp[k] = src + (size_t)(w.line0 + imin_(lsub + 2 * k, w.nlines - 1)) * rowb +
+                      (ptrdiff_t)(w.o0 - 16 + pos) * PIXB;
         }
     }
 }
@@ -331,48 +382,49 @@ AVS_FN void loader_init(const StreamParams& p, WarpRun<C, IS_V>& w) {
 // STEADY: the caller guarantees issue && every sweep interior (no branches around the copies).
 template <class C, bool IS_V, bool STEADY>
 AVS_FN void load_group(const StreamParams& p, WarpRun<C, IS_V>& w, int g, int gslot, bool issue) {
-    constexpr int PITCH = RingOf<C, IS_V, 0>::PITCH;
+    constexpr int PITCH_B = RingOf<C, IS_V, 0>::PITCH_B;
+    constexpr int PIXB = IS_V ? 16 : C::PIXB;
     const int lane = w.lane;
-    const float4* src = static_cast<const float4*>(p.src);
-    const size_t pitch4 = (size_t)(p.src_pitch / 4);
+    const unsigned char* src = static_cast<const unsigned char*>(p.src);
+    const size_t rowb = (size_t)p.src_pitch * (PIXB / 4);
 #pragma unroll
     for (int q = 0; q < C::SRC_N / 16; ++q) {
         const int pos0 = w.o0 + g * C::SRC_N + q * 16; // first source position of the sweep
-        float2* ring = w.ring0 + (size_t)(gslot + q * 16) * PITCH;
+        unsigned char* ring = reinterpret_cast<unsigned char*>(w.ring0) + (size_t)(gslot + q * 16) * PITCH_B;
         const bool interior = STEADY || ((pos0 >= 0) && (pos0 + 16 <= p.src_len));
         if (STEADY) issue = true;
         if (IS_V) {
             // a position is an intermediate row; the warp's 16 pixel columns are 256 contiguous bytes
             const int piece = lane & 15, rsub = lane >> 4;
-            float2* d = ring + rsub * PITCH + piece * 2;
+            unsigned char* d = ring + rsub * PITCH_B + piece * 16;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) w.gp[k] += 16 * pitch4;
+            for (int k = 0; k < 8; ++k) w.gp[k] += 16 * rowb;
             if (STEADY || (issue && interior)) {
 #pragma unroll
-                for (int k = 0; k < 8; ++k) cp_async16(d + 2 * k * PITCH, w.gp[k]);
+                for (int k = 0; k < 8; ++k) cp_async16(d + 2 * k * PITCH_B, w.gp[k]);
             } else if (issue) {
-                const float4* col = src + w.line0 + imin_(piece, w.nlines - 1);
+                const unsigned char* col = src + (size_t)(w.line0 + imin_(piece, w.nlines - 1)) * 16;
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
                     const int y = imin_(imax_(pos0 + rsub + 2 * k, 0), p.src_len - 1) - p.src_row_base;
-                    cp_async16(d + 2 * k * PITCH, col + (size_t)y * pitch4);
+                    cp_async16(d + 2 * k * PITCH_B, col + (ptrdiff_t)y * (ptrdiff_t)rowb);
                 }
             }
         } else {
             // a position is a pixel of a row: 16 consecutive pixels of one row per half warp
             const int pos = lane & 15, lsub = lane >> 4;
-            float2* d = ring + pos * PITCH + lsub * C::LINE_F2; // line lsub + 2k: + 2k * LINE_F2
+            unsigned char* d = ring + pos * PIXB + lsub * C::LINE_B; // line lsub + 2k: + 2k * LINE_B
 #pragma unroll
-            for (int k = 0; k < 8; ++k) w.gp[k] += 16;
+            for (int k = 0; k < 8; ++k) w.gp[k] += 16 * PIXB;
             if (STEADY || (issue && interior)) {
 #pragma unroll
-                for (int k = 0; k < 8; ++k) cp_async16(d + 2 * k * C::LINE_F2, w.gp[k]);
+                for (int k = 0; k < 8; ++k) cp_async_px<PIXB>(d + 2 * k * C::LINE_B, w.gp[k]);
             } else if (issue) {
                 const int x = imin_(imax_(pos0 + pos, 0), p.src_len - 1);
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
                     const int line = imin_(lsub + 2 * k, w.nlines - 1);
-                    cp_async16(d + 2 * k * C::LINE_F2, src + (size_t)(w.line0 + line) * pitch4 + x);
+                    cp_async_px<PIXB>(d + 2 * k * C::LINE_B, src + (size_t)(w.line0 + line) * rowb + (size_t)x * PIXB);
                 }
             }
         }
@@ -383,15 +435,15 @@ AVS_FN void load_group(const StreamParams& p, WarpRun<C, IS_V>& w, int g, int gs
 // Reads the input ring by absolute position, each tap clamped to [lo, hi].
 
 template <class C, bool IS_V, int I, class S>
-AVS_FN float2 slow_one(const StreamStep& sp, const float2* ring, int origin, int j, int lo, int hi) {
-    constexpr int RSP = RingOf<C, IS_V, I>::RSP;
-    constexpr int PITCH = RingOf<C, IS_V, I>::PITCH;
+AVS_FN float2 slow_one(const StreamStep& sp, const unsigned char* ring, int origin, int j, int lo, int hi) {
+    using R = RingOf<C, IS_V, I>;
+    constexpr int RSP = R::RSP;
     float2 x[S::NTW];
     const int p0 = in_first<S>(sp, j);
 #pragma unroll
     for (int t = 0; t < S::NTW; ++t) {
         const int pos = imin_(imax_(p0 + t, lo), hi);
-        x[t] = ring[(size_t)((unsigned)(pos - origin) % (unsigned)RSP) * PITCH];
+        x[t] = R::load(ring + (size_t)((unsigned)(pos - origin) % (unsigned)RSP) * R::PITCH_B);
     }
     if (S::KIND == K_FIR) return fir_one<S>(x, 0, sp.taps);
     if (S::KIND == K_RESIZE) return resize_one<S>(x, 0, sp.taps, sp.zero_start);
@@ -486,36 +538,36 @@ AVS_FN void sink_h_stage(WarpRun<C, false>& w, int j0, const float2* o) {
 
 // Outputs of one in-domain batch whose whole window lies inside its input line.
 template <class C, bool IS_V, int I, class S>
-AVS_FN void window_bases(const float2* ring, int rd, const float2** base) {
+AVS_FN void window_bases(const unsigned char* ring, int rd, const unsigned char** base) {
     constexpr int RSP = RingOf<C, IS_V, I>::RSP;
-    constexpr int PITCH = RingOf<C, IS_V, I>::PITCH;
+    constexpr int PITCH_B = RingOf<C, IS_V, I>::PITCH_B;
     // the window never wraps inside a piece of CH positions: pieces are ring-aligned
 #pragma unroll
     for (int k = 0; k < (S::W + S::CH - 1) / S::CH; ++k) {
         int s = rd + k * S::CH;
         if (s >= RSP) s -= RSP;
-        base[k] = ring + (size_t)s * PITCH;
+        base[k] = ring + (size_t)s * PITCH_B;
     }
 }
 
 // Reads the window of step I's next batch into registers (straight-line rounds, PRE chains).
 template <class C, bool IS_V, int I, class S>
 AVS_FN void preload_window(WarpRun<C, IS_V>& w) {
-    constexpr int PITCH = RingOf<C, IS_V, I>::PITCH;
-    const float2* ring = ((I == 1) ? w.ring1 : w.ring2) + RingOf<C, IS_V, I>::lane_off(w.lane);
-    const float2* base[(S::W + S::CH - 1) / S::CH + 1];
+    using R = RingOf<C, IS_V, I>;
+    const unsigned char* ring = reinterpret_cast<const unsigned char*>((I == 1) ? w.ring1 : w.ring2) + R::lane_off_b(w.lane);
+    const unsigned char* base[(S::W + S::CH - 1) / S::CH + 1];
     window_bases<C, IS_V, I, S>(ring, w.rd[I], base);
     float2* xp = (I == 1) ? w.xp1 : w.xp2;
 #pragma unroll
-    for (int i = 0; i < S::W; ++i) xp[i] = base[i / S::CH][(i % S::CH) * PITCH];
+    for (int i = 0; i < S::W; ++i) xp[i] = R::load(base[i / S::CH] + (i % S::CH) * R::PITCH_B);
 }
 
 // PRELOADED: the window is already in w.xp1 / w.xp2 (preload_window).
 template <class C, bool IS_V, int I, class S, bool PRELOADED = false>
-AVS_FN void fast_batch(const StreamParams& p, WarpRun<C, IS_V>& w, const float2* ring, int rd, int kbcur,
+AVS_FN void fast_batch(const StreamParams& p, WarpRun<C, IS_V>& w, const unsigned char* ring, int rd, int kbcur,
                        int j0, float2* o) {
-    constexpr int RSP = RingOf<C, IS_V, I>::RSP;
-    constexpr int PITCH = RingOf<C, IS_V, I>::PITCH;
+    using R = RingOf<C, IS_V, I>;
+    constexpr int PITCH_B = R::PITCH_B;
     constexpr int M = S::M;
     const StreamStep& sp = p.s[I];
     if constexpr (PRELOADED) {
@@ -527,12 +579,12 @@ AVS_FN void fast_batch(const StreamParams& p, WarpRun<C, IS_V>& w, const float2*
         }
         return;
     }
-    const float2* base[(S::W + S::CH - 1) / S::CH + 1];
+    const unsigned char* base[(S::W + S::CH - 1) / S::CH + 1];
     window_bases<C, IS_V, I, S>(ring, rd, base);
     if constexpr (S::KIND == K_RESIZE2) {
         float2 x[S::W];
 #pragma unroll
-        for (int i = 0; i < S::W; ++i) x[i] = base[i / S::CH][(i % S::CH) * PITCH];
+        for (int i = 0; i < S::W; ++i) x[i] = R::load(base[i / S::CH] + (i % S::CH) * PITCH_B);
         const int pv = sp.sp_first + j0 - (S::NT / 2 - 1);
         if (pv & 1) {
 #pragma unroll
@@ -545,7 +597,7 @@ AVS_FN void fast_batch(const StreamParams& p, WarpRun<C, IS_V>& w, const float2*
         // whole window of the batch in registers
         float2 x[S::W];
 #pragma unroll
-        for (int i = 0; i < S::W; ++i) x[i] = base[i / S::CH][(i % S::CH) * PITCH];
+        for (int i = 0; i < S::W; ++i) x[i] = R::load(base[i / S::CH] + (i % S::CH) * PITCH_B);
 #pragma unroll
         for (int m = 0; m < M; ++m) {
             if (S::KIND == K_FIR) o[m] = fir_one<S>(x, m * S::ADV, sp.taps);
@@ -564,7 +616,8 @@ AVS_FN void run_batch(const StreamParams& p, WarpRun<C, IS_V>& w) {
     const StreamStep& sp = p.s[I];
     const int kbcur = w.kb[I];
     const int j0 = w.a[I] + M * kbcur;
-    const float2* ring = ((I == 0) ? w.ring0 : (I == 1 ? w.ring1 : w.ring2)) + RingOf<C, IS_V, I>::lane_off(w.lane);
+    const unsigned char* ring = reinterpret_cast<const unsigned char*>((I == 0) ? w.ring0 : (I == 1 ? w.ring1 : w.ring2)) +
+                                RingOf<C, IS_V, I>::lane_off_b(w.lane);
     const int origin = (I == 0) ? w.o0 : w.a[I - 1];
     const int rd = w.rd[I];
     const int wr = w.wr[I];
@@ -605,7 +658,7 @@ AVS_FN void run_batch(const StreamParams& p, WarpRun<C, IS_V>& w) {
 
     if constexpr (!LAST) {
         constexpr int RSPO = RingOf<C, IS_V, I + 1>::RSP;
-        constexpr int PITCHO = RingOf<C, IS_V, I + 1>::PITCH;
+        constexpr int PITCHO = kPitchL; // intermediate rings: float2 [position][lane]
         w.wr[I] = (wr + M == RSPO) ? 0 : wr + M;
         if (STEADY || have) {
             float2* out = ((I == 0) ? w.ring1 : w.ring2) + w.lane + (size_t)wr * PITCHO;
@@ -735,7 +788,7 @@ AVS_FN void stream_warp_main(const StreamParams& p, long long gw, long long nwar
     WarpRun<C, IS_V> w;
     w.lane = lane;
     w.ring0 = sm;
-    w.ring1 = w.ring0 + (IS_V ? (size_t)C::rsp0 * kPitchL : (size_t)kLines * C::LINE_F2);
+    w.ring1 = w.ring0 + (IS_V ? (size_t)C::rsp0 * kPitchL : (size_t)C::SRC_RING_F2);
     w.ring2 = w.ring1 + (size_t)C::rsp1 * kPitchL;
     w.stage = w.ring2 + (size_t)C::rsp2 * kPitchL;
     const int rho_first = p.out0 / C::B, rho_last = (p.out1 - 1) / C::B;
@@ -756,11 +809,13 @@ AVS_FN void stream_warp_main(const StreamParams& p, long long gw, long long nwar
 
 #if defined(__CUDACC__)
 template <class C, bool IS_V, int EPI>
-__global__ void __launch_bounds__(C::NWARPS * 32, 1) stream_pass_kernel(const __grid_constant__ StreamParams p) {
+__global__ void __launch_bounds__((IS_V ? C::NWARPS_V : C::NWARPS_H) * 32, 1)
+stream_pass_kernel(const __grid_constant__ StreamParams p) {
+    constexpr int NW = IS_V ? C::NWARPS_V : C::NWARPS_H;
     extern __shared__ __align__(16) unsigned char stream_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float2* sm = reinterpret_cast<float2*>(stream_smem) + (size_t)warp * (IS_V ? C::WARP_F2_V : C::WARP_F2_H);
-    stream_warp_main<C, IS_V, EPI>(p, (long long)blockIdx.x * C::NWARPS + warp, (long long)gridDim.x * C::NWARPS, lane, sm);
+    stream_warp_main<C, IS_V, EPI>(p, (long long)blockIdx.x * NW + warp, (long long)gridDim.x * NW, lane, sm);
 }
 #endif
 
@@ -770,35 +825,40 @@ __global__ void __launch_bounds__(C::NWARPS * 32, 1) stream_pass_kernel(const __
 // Scheduling variants (same arithmetic): bit 0 = later steps' windows read ahead at the top of
 // a round (one more round of delay and ring; the source look-ahead shrinks by a round to stay
 // within shared memory), bit 1 = no separate straight-line loop for the interior rounds.
-// Measured on cfg3 (profiles/r01_variant_sweeps.jsonl): the row pass is fastest with the
-// straight-line loop (variant 0), the column pass without it and with read-ahead (variant 3).
+// Measured on cfg3 with the packed arithmetic (profiles/r01_variant_sweeps_packed.jsonl): both
+// passes are fastest with the straight-line loop and without read-ahead (variant 0); with the
+// scalar arithmetic the column pass preferred variant 3 (profiles/r01_variant_sweeps.jsonl).
 constexpr int kStreamVariants = 4;
-constexpr int kStreamDefaultVariantH = 0, kStreamDefaultVariantV = 3;
+constexpr int kStreamDefaultVariantH = 0, kStreamDefaultVariantV = 0;
 
 // Source look-ahead in rounds (LAH row pass, LAV column pass) is what shared memory affords at
 // 8 warps per SM: the row pass carries the staging rows, three-step chains a second
 // intermediate ring.  PRE_OK: the chain has room for the read-ahead variant (one more chunk
 // of every intermediate ring, paid for with one round of source look-ahead).
-template <class S0, class S1, class S2, int REPS_LAST, int LAH, int LAV, bool PRE_OK, int VAR, bool IS_V>
+template <class S0, class S1, class S2, int REPS_LAST, int LAH, int LAV, bool PRE_OK, int VAR, bool IS_V, int SRCT>
 using ChainV = ChainC<S0, S1, S2, REPS_LAST, (IS_V ? LAV : LAH) - ((PRE_OK && (VAR & 1)) ? 1 : 0), !((VAR >> 1) & 1),
-                      (PRE_OK && (VAR & 1)) ? 1 : 0>;
+                      (PRE_OK && (VAR & 1)) ? 1 : 0, IS_V ? AVIRB200_F32 : SRCT>;
 
 // cfg3, float8_dil mirror (k = 2): RESIZE(24 taps, source step 2) -> 8-tap correction FIR
-template <int VAR, bool IS_V>
+template <int VAR, bool IS_V, int SRCT = AVIRB200_F32>
 using ChainDil24 = ChainV<StepC<K_RESIZE, AVIRB200_SUM_DIL8, 24, 2>, StepC<K_FIR, AVIRB200_SUM_DIL8, 8, 1>, NoStep,
-                          1, 2, 3, true, VAR, IS_V>;
+                          1, 2, 3, true, VAR, IS_V, SRCT>;
 // k = 2 in build mode 1, interleaved classes (fpclass_def<float>, fpclass_float4): RESIZE(24) -> FIR(7)
-template <int VAR, bool IS_V>
+template <int VAR, bool IS_V, int SRCT = AVIRB200_F32>
 using ChainInl24 = ChainV<StepC<K_RESIZE, AVIRB200_SUM_INL, 24, 2>, StepC<K_FIR, AVIRB200_SUM_INL, 7, 1>, NoStep,
-                          1, 2, 3, true, VAR, IS_V>;
+                          1, 2, 3, true, VAR, IS_V, SRCT>;
 // cfg3, float4 mirror (k = 2, build mode 0): FIR(7) -> RESIZE(18, source step 2) -> FIR(7)
-template <int VAR, bool IS_V>
+template <int VAR, bool IS_V, int SRCT = AVIRB200_F32>
 using ChainInl3 = ChainV<StepC<K_FIR, AVIRB200_SUM_INL, 7, 1>, StepC<K_RESIZE, AVIRB200_SUM_INL, 18, 2>,
-                         StepC<K_FIR, AVIRB200_SUM_INL, 7, 1>, 1, 1, 2, false, VAR, IS_V>;
+                         StepC<K_FIR, AVIRB200_SUM_INL, 7, 1>, 1, 1, 2, false, VAR, IS_V, SRCT>;
+// cfg4 (k = 4, build mode 0): FIR(15, decimation 2) -> RESIZE(18, source step 2) -> FIR(7)
+template <int VAR, bool IS_V, int SRCT = AVIRB200_F32>
+using ChainInl3D = ChainV<StepC<K_FIR, AVIRB200_SUM_INL, 15, 2>, StepC<K_RESIZE, AVIRB200_SUM_INL, 18, 2>,
+                          StepC<K_FIR, AVIRB200_SUM_INL, 7, 1>, 1, 1, 1, false, VAR, IS_V, SRCT>;
 // cfg2 (k = 0.5): FIR(7) -> RESIZE(24) over the virtual 2X line; 32 final outputs per round
-template <int VAR, bool IS_V>
+template <int VAR, bool IS_V, int SRCT = AVIRB200_F32>
 using ChainUp2 = ChainV<StepC<K_FIR, AVIRB200_SUM_INL, 7, 1>, StepC<K_RESIZE2, AVIRB200_SUM_INL, 24, 1>, NoStep,
-                        2, 1, 3, false, VAR, IS_V>;
+                        2, 1, 3, false, VAR, IS_V, SRCT>;
 
 template <class C>
 struct ChainTag {
@@ -811,23 +871,34 @@ struct PassTag {
 };
 
 // Calls f(ChainTag<Chain>(), PassTag<is_v>()) with the description of chain `id` in scheduling
-// variant `variant` for the row pass (is_v false) or the column pass.
+// variant `variant` for the row pass (is_v false) or the column pass.  Integer sources (row
+// pass only) run the default row-pass variant whatever `variant` says: one instantiation each.
 template <class F>
-inline bool stream_dispatch(int id, bool is_v, int variant, F&& f) {
+inline bool stream_dispatch(int id, bool is_v, int variant, int src_type, F&& f) {
 #define AVS_V(NAME, N)                                                                    \
     case N:                                                                               \
         if (is_v) f(ChainTag<NAME<N, true> >(), PassTag<true>());                         \
         else f(ChainTag<NAME<N, false> >(), PassTag<false>());                            \
         return true;
 #define AVS_VARIANTS(NAME)                                                                \
+    if (!is_v && src_type == AVIRB200_U8) {                                               \
+        f(ChainTag<NAME<kStreamDefaultVariantH, false, AVIRB200_U8> >(), PassTag<false>()); \
+        return true;                                                                      \
+    }                                                                                     \
+    if (!is_v && src_type == AVIRB200_U16) {                                              \
+        f(ChainTag<NAME<kStreamDefaultVariantH, false, AVIRB200_U16> >(), PassTag<false>()); \
+        return true;                                                                      \
+    }                                                                                     \
     switch (variant) {                                                                    \
         AVS_V(NAME, 0) AVS_V(NAME, 1) AVS_V(NAME, 2) AVS_V(NAME, 3)                       \
     default: return false;                                                                \
     }
+    if (variant < 0 || variant >= kStreamVariants) return false;
     switch (id) {
     case kChainDil24: AVS_VARIANTS(ChainDil24)
     case kChainInl24: AVS_VARIANTS(ChainInl24)
     case kChainInl3: AVS_VARIANTS(ChainInl3)
+    case kChainInl3D: AVS_VARIANTS(ChainInl3D)
     case kChainUp2: AVS_VARIANTS(ChainUp2)
     default: return false;
     }

@@ -23,7 +23,7 @@ int sm_count() {
 
 template <class C, bool IS_V, int EPI>
 int launch_one(const StreamParams& p, cudaStream_t st) {
-    constexpr int NW = C::NWARPS;
+    constexpr int NW = IS_V ? C::NWARPS_V : C::NWARPS_H;
     constexpr size_t smem = (size_t)NW * (IS_V ? C::WARP_F2_V : C::WARP_F2_H) * sizeof(float2);
     static_assert(smem <= 227 * 1024, "per-warp rings do not fit the shared memory of an SM");
     auto kern = stream_pass_kernel<C, IS_V, EPI>;
@@ -63,7 +63,7 @@ int stream_variant(bool is_v) {
 int stream_launch(int chain, bool is_v, bool plain_f32, const StreamParams& p, void* stream) {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     int rc = -2;
-    const bool known = stream_dispatch(chain, is_v, stream_variant(is_v), [&](auto tag, auto pass) {
+    const bool known = stream_dispatch(chain, is_v, stream_variant(is_v), p.src_type, [&](auto tag, auto pass) {
         using C = typename decltype(tag)::type;
         if constexpr (!decltype(pass)::is_v) rc = launch_one<C, false, 0>(p, st);
         else rc = plain_f32 ? launch_one<C, true, 1>(p, st) : launch_one<C, true, 0>(p, st);

@@ -36,7 +36,8 @@ struct StreamParams {
     int n_lines;          // rows (row pass) or pixel columns (column pass)
     int src_len;          // positions of the source line
     int out0, out1;       // final outputs [out0, out1) to produce
-    const void* src;      // fp32, 4 interleaved channels
+    const void* src;      // 4 interleaved channels; fp32, or (row pass) the caller's u8 / u16 pixels
+    int src_type;         // AVIRB200_F32 / _U8 / _U16: selects the kernel instantiation (row pass)
     long long src_pitch;  // elements between rows
     int src_row_base;     // column pass: global row held by source row 0 (shards)
     void* dst;
@@ -53,6 +54,7 @@ enum StreamChainId {
     kChainDil24, // RESIZE(24, D2) -> FIR8                 cfg3, float8_dil mirror (k = 2)
     kChainInl24, // RESIZE(24, D2) -> FIR7                 k = 2, build mode 1, interleaved classes
     kChainInl3,  // FIR7 -> RESIZE(18, D2) -> FIR7         cfg3, float4 mirror (k = 2, build mode 0)
+    kChainInl3D, // FIR15/2 -> RESIZE(18, D2) -> FIR7      cfg4 (k = 4, build mode 0)
     kChainUp2,   // FIR7 -> RESIZE2(24)                    cfg2 (k = 0.5, build mode 1)
     kChainCount
 };
@@ -74,11 +76,14 @@ inline const StepSpec* chain_spec(int id, int* nsteps) {
     static const StepSpec inl24[] = {{K_RESIZE, AVIRB200_SUM_INL, 24, 2}, {K_FIR, AVIRB200_SUM_INL, 7, 1}};
     static const StepSpec inl3[] = {{K_FIR, AVIRB200_SUM_INL, 7, 1}, {K_RESIZE, AVIRB200_SUM_INL, 18, 2},
                                     {K_FIR, AVIRB200_SUM_INL, 7, 1}};
+    static const StepSpec inl3d[] = {{K_FIR, AVIRB200_SUM_INL, 15, 2}, {K_RESIZE, AVIRB200_SUM_INL, 18, 2},
+                                     {K_FIR, AVIRB200_SUM_INL, 7, 1}};
     static const StepSpec up2[] = {{K_FIR, AVIRB200_SUM_INL, 7, 1}, {K_RESIZE2, AVIRB200_SUM_INL, 24, 1}};
     switch (id) {
     case kChainDil24: *nsteps = 2; return dil24;
     case kChainInl24: *nsteps = 2; return inl24;
     case kChainInl3: *nsteps = 3; return inl3;
+    case kChainInl3D: *nsteps = 3; return inl3d;
     case kChainUp2: *nsteps = 2; return up2;
     default: *nsteps = 0; return nullptr;
     }
@@ -132,10 +137,15 @@ inline bool stream_match_step(const avirb200_step_desc& d, const StepSpec& sp, S
 
 // Decides whether the axis runs on the streaming kernel; on success `out` holds everything
 // the kernel parameters need.
-inline bool stream_plan_axis(const avirb200_axis_desc& ad, int sum_mode, int channels, StreamAxisPlan& out) {
+inline bool stream_plan_axis(const avirb200_axis_desc& ad, int sum_mode, int channels, StreamAxisPlan& out,
+                             bool allow_up2 = false) {
     out.chain = kChainNone;
     if (channels != 4) return false;
+    // allow_up2: the upsizing chain is instantiated and checked (emulation; AVIRB200_STREAM_UP2=1
+    // on the GPU) but not selected by default: on B200 the tile kernel's blocked skip-odd resize
+    // is 2.4x faster on cfg2's column pass (profiles/r01_variant_sweeps_packed.jsonl).
     for (int id = 1; id < kChainCount; ++id) {
+        if (id == kChainUp2 && !allow_up2) continue;
         int ns = 0;
         const StepSpec* spec = chain_spec(id, &ns);
         if (ns != ad.nsteps) continue;
@@ -156,10 +166,12 @@ inline bool stream_plan_axis(const avirb200_axis_desc& ad, int sum_mode, int cha
     return false;
 }
 
-// The row pass streams raw fp32 pixels into shared memory (cp.async): sources that need a
-// conversion on the way in (integer types, sRGB linearisation) stay on the tile kernel.
+// The row pass streams the caller's pixels into shared memory as they are (cp.async); integer
+// pixels are cast in the compute lanes' own reads.  Sources that need the sRGB linearisation
+// on the way in stay on the tile kernel (it converts every sample once, in double).
 inline bool stream_row_source_ok(const avirb200_plan_desc& d) {
-    return d.in_type == AVIRB200_F32 && !(d.use_gamma & 1);
+    return (d.in_type == AVIRB200_F32 || d.in_type == AVIRB200_U8 || d.in_type == AVIRB200_U16) &&
+           !(d.use_gamma & 1);
 }
 
 // Kernel parameters of one pass (the caller fills the image pointers / bases).
@@ -167,6 +179,7 @@ inline void stream_fill_params(StreamParams& p, const StreamAxisPlan& ap, const 
     memset(&p, 0, sizeof p);
     for (int i = 0; i < ap.nsteps; ++i) p.s[i] = ap.s[i];
     p.src_len = ap.src_len;
+    p.src_type = AVIRB200_F32;
     p.gamma_out = (d.use_gamma & 2) ? 1 : 0;
     p.alpha_index = d.alpha_index;
     p.out_gamma_mult = d.out_gamma_mult;

@@ -44,7 +44,7 @@ __global__ void __launch_bounds__(384, 1) k(const __grid_constant__ P p) {
             }
         }
 #pragma unroll
-        for (int a = 0; a < NACC; ++a) x[a].x = acc[(a + 1) % NACC].y; // keep the chains data dependent on the loop
+        for (int a = 0; a < NACC; ++a) x[a] = make_float2(acc[(a + 1) % NACC].y, acc[(a + 2) % NACC].x); // both lanes loop-carried: no product is loop invariant
     }
     float2 s = acc[0];
 #pragma unroll
@@ -75,16 +75,16 @@ int main() {
     int khz = 0; cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, dev);
     const double mhz = khz / 1000.0;
     const int blocks = pr.multiProcessorCount;
-    for (int threads : {128, 256, 384, 512, 768}) {
+    for (int threads : {128, 256, 384}) {
         const int n = blocks * threads;
-        P p; for (int t = 0; t < NT; ++t) p.tap[t] = make_float2(0.01f * (t + 1), 0.01f * (t + 1));
+        P p; for (int t = 0; t < NT; ++t) { const float v = ((t & 1) ? -0.01f : 0.01f) * (t / 2 * 2 + 1); p.tap[t] = make_float2(v, v); } // taps sum to zero: values stay bounded
         p.one = make_float2(1.0f, 1.0f); p.iters = 4000;
         float2* hx = (float2*)malloc((size_t)n * NACC * sizeof(float2));
         for (int i = 0; i < n * NACC; ++i) hx[i] = make_float2((i % 97) * 0.013f, (i % 89) * 0.017f);
         float2 *dx, *dout; cudaMalloc(&dx, (size_t)n * NACC * sizeof(float2)); cudaMalloc(&dout, n * sizeof(float2));
         cudaMemcpy(dx, hx, (size_t)n * NACC * sizeof(float2), cudaMemcpyHostToDevice);
         p.x = dx; p.out = dout;
-        if (threads <= 384 || true) { run<0>(p, blocks, threads, mhz); run<1>(p, blocks, threads, mhz); run<2>(p, blocks, threads, mhz); run<3>(p, blocks, threads, mhz); }
+        { run<0>(p, blocks, threads, mhz); run<1>(p, blocks, threads, mhz); run<2>(p, blocks, threads, mhz); run<3>(p, blocks, threads, mhz); }
         cudaFree(dx); cudaFree(dout); free(hx);
     }
     printf("{\"sm_count\": %d, \"clock_mhz\": %.0f}\n", blocks, mhz);

@@ -49,7 +49,7 @@ void emul_pass(const StreamParams& p, int nwarps) {
 
 template <bool IS_V>
 bool emul_dispatch(int chain, int variant, const StreamParams& p, int nwarps, bool plain) {
-    return stream_dispatch(chain, IS_V, variant, [&](auto tag, auto pass) {
+    return stream_dispatch(chain, IS_V, variant, p.src_type, [&](auto tag, auto pass) {
         using C = typename decltype(tag)::type;
         if constexpr (decltype(pass)::is_v != IS_V) {
             (void)p; // (the dispatcher instantiates the callback for both passes)
@@ -69,17 +69,17 @@ extern "C" {
 // 1 when both axes of the descriptor run on the streaming kernel (f32 source only).
 int stream_emul_applicable(const avirb200_plan_desc* d) {
     StreamAxisPlan h, v;
-    return stream_row_source_ok(*d) && stream_plan_axis(d->h, d->sum_mode, d->channels, h) &&
-           stream_plan_axis(d->v, d->sum_mode, d->channels, v);
+    return stream_row_source_ok(*d) && stream_plan_axis(d->h, d->sum_mode, d->channels, h, true) &&
+           stream_plan_axis(d->v, d->sum_mode, d->channels, v, true);
 }
 
 // Row pass with `warps_h` emulated warps, then the column pass in `bands` destination bands
 // (as the sharded schedule runs it) with `warps_v` warps each.
-int stream_emul_resize(const avirb200_plan_desc* d, const float* src, size_t src_pitch, void* dst,
+int stream_emul_resize(const avirb200_plan_desc* d, const void* src, size_t src_pitch, void* dst,
                        size_t dst_pitch, int warps_h, int warps_v, int bands, int variant) {
     StreamAxisPlan h, v;
-    if (!stream_row_source_ok(*d) || !stream_plan_axis(d->h, d->sum_mode, d->channels, h) ||
-        !stream_plan_axis(d->v, d->sum_mode, d->channels, v))
+    if (!stream_row_source_ok(*d) || !stream_plan_axis(d->h, d->sum_mode, d->channels, h, true) ||
+        !stream_plan_axis(d->v, d->sum_mode, d->channels, v, true))
         return -4;
     std::vector<float> mid((size_t)d->src_h * d->dst_w * 4);
     StreamParams p;
@@ -88,6 +88,7 @@ int stream_emul_resize(const avirb200_plan_desc* d, const float* src, size_t src
     p.out0 = 0;
     p.out1 = d->dst_w;
     p.src = src;
+    p.src_type = d->in_type;
     p.src_pitch = (long long)src_pitch;
     p.dst = mid.data();
     p.dst_pitch = (long long)d->dst_w * 4;

@@ -54,6 +54,22 @@ EMUL_CASES = [
     ((1, 50, 35, 100, 70, 4, f32, u8, 8, {"buildmode": 1}), 4, 3, 2),
     ((1, 10, 9, 20, 18, 4, f32, f32, 8, {"buildmode": 1}), 2, 2, 2),
     ((1, 320, 20, 640, 40, 4, f32, u8, 8, {"buildmode": 1}), 9, 2, 5),
+    # integer sources: raw pixels in the row pass's source ring, cast in the lanes' reads
+    ((1, 96, 54, 192, 108, 4, u8, u8, 8, {"buildmode": 1}), 3, 2, 1),      # cfg2 as quoted (u8 -> u8)
+    ((1, 50, 35, 100, 70, 4, u8, u8, 8, {"buildmode": 1}), 4, 3, 2),
+    ((1, 10, 9, 20, 18, 4, u16, u16, 16, {"buildmode": 1}), 2, 2, 2),
+    ((2, 192, 108, 96, 54, 4, u8, u8, 8, {"buildmode": 1}), 3, 2, 1),
+    ((2, 100, 70, 50, 35, 4, u16, u16, 16, {"buildmode": 1}), 4, 3, 2),
+    ((1, 100, 70, 50, 35, 4, u16, f32, 16, {"buildmode": 1}), 2, 5, 3),
+    ((1, 100, 70, 50, 35, 4, u8, u8, 8, {"buildmode": 0}), 4, 3, 2),
+    ((1, 640, 40, 320, 20, 4, u16, u16, 16, {"buildmode": 0}), 9, 2, 5),
+    ((0, 20, 18, 10, 9, 4, u8, u16, 16, {"buildmode": 1}), 2, 2, 2),
+    # cfg4 chain (k = 4, build mode 0): FIR(15, decimation 2) -> RESIZE(18) -> FIR(7)
+    ((1, 384, 216, 96, 54, 4, u16, u16, 16, {"buildmode": 0}), 3, 2, 1),
+    ((1, 200, 140, 50, 35, 4, u16, u16, 16, {"buildmode": 0}), 4, 3, 2),
+    ((1, 200, 140, 50, 35, 4, f32, f32, 16, {"buildmode": 0}), 2, 5, 3),
+    ((0, 40, 36, 10, 9, 4, u8, u8, 16, {"buildmode": 0}), 2, 2, 2),
+    ((1, 1280, 80, 320, 20, 4, u16, u16, 16, {"buildmode": 0}), 9, 2, 5),
 ]
 
 
