@@ -63,7 +63,7 @@ int fail(int code, const std::string& msg) {
                         std::string(#expr) + ": " + cudaGetErrorString(e_));                 \
     } while (0)
 
-size_t dtype_size(int t) { return t == AVIRB200_U8 ? 1 : (t == AVIRB200_U16 ? 2 : 4); }
+size_t dtype_size(int t) { return t == AVIRB200_U8 ? 1 : (t == AVIRB200_U16 ? 2 : (t == AVIRB200_F64 ? 8 : 4)); }
 
 // The u8 sRGB->linear table: upstream ships 256 float literals (avir.h:234-286) that equal
 // the double-precision linearisation formula printed with 7 significant digits.  Regenerated
@@ -108,7 +108,8 @@ struct HostAxis {
 } // namespace
 
 struct avirb200_plan {
-    avirb200_plan_desc desc;
+    avirb200_plan_desc desc;     // in_type / out_type: what the KERNELS read and write (F64 -> F32)
+    int io_in_type = 0, io_out_type = 0; // the caller's element types
     HostAxis h, v;
     void* arena = nullptr;
     float* d_lut = nullptr;
@@ -529,6 +530,40 @@ DevAxis host_axis_view(const avirb200_axis_desc& ad) {
     return d;
 }
 
+// ---- double image buffers: the casts upstream's pack / unpack perform, as two small kernels ----
+
+__global__ void __launch_bounds__(256) narrow_f64_kernel(const double* __restrict__ src, long long src_pitch,
+                                                        float* __restrict__ dst, int row_elems, int rows) {
+    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+    const long long n = (long long)row_elems * rows;
+    if (i >= n) return;
+    const int y = (int)(i / row_elems), x = (int)(i - (long long)y * row_elems);
+    dst[i] = __double2float_rn(src[(long long)y * src_pitch + x]); // (fptypeatom) ip[c], avir.h:2803-2806
+}
+
+__global__ void __launch_bounds__(256) widen_f32_kernel(const float* __restrict__ src, double* __restrict__ dst,
+                                                       long long dst_pitch, int row_elems, int rows) {
+    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+    const long long n = (long long)row_elems * rows;
+    if (i >= n) return;
+    const int y = (int)(i / row_elems), x = (int)(i - (long long)y * row_elems);
+    dst[(long long)y * dst_pitch + x] = (double)src[i]; // (Tout) v[c], avir.h:3168-3171
+}
+
+size_t f64_in_bytes(const avirb200_plan* pl) {
+    const avirb200_plan_desc& d = pl->desc;
+    return pl->io_in_type == AVIRB200_F64 ? align_up((size_t)d.src_w * d.src_h * d.channels * 4, 256) : 0;
+}
+
+size_t f64_out_bytes(const avirb200_plan* pl) {
+    const avirb200_plan_desc& d = pl->desc;
+    return pl->io_out_type == AVIRB200_F64 ? align_up((size_t)d.dst_w * d.dst_h * d.channels * 4, 256) : 0;
+}
+
+bool plan_has_f64(const avirb200_plan* pl) {
+    return pl->io_in_type == AVIRB200_F64 || pl->io_out_type == AVIRB200_F64;
+}
+
 } // namespace
 
 extern "C" {
@@ -576,7 +611,7 @@ int avirb200_plan_create(const avirb200_plan_desc* desc, avirb200_plan** out) {
     if (desc->channels < 1 || desc->channels > 4 || desc->src_w < 1 || desc->src_h < 1 ||
         desc->dst_w < 1 || desc->dst_h < 1)
         return fail(AVIRB200_ERR_BAD_ARG, "bad image geometry");
-    if (desc->in_type < 0 || desc->in_type > 2 || desc->out_type < 0 || desc->out_type > 2)
+    if (desc->in_type < 0 || desc->in_type > 3 || desc->out_type < 0 || desc->out_type > 3)
         return fail(AVIRB200_ERR_BAD_ARG, "bad element type");
     if (desc->h.src_len != desc->src_w || desc->h.dst_len != desc->dst_w ||
         desc->v.src_len != desc->src_h || desc->v.dst_len != desc->dst_h)
@@ -591,6 +626,10 @@ int avirb200_plan_create(const avirb200_plan_desc* desc, avirb200_plan** out) {
     std::unique_ptr<avirb200_plan> pl(new (std::nothrow) avirb200_plan());
     if (!pl) return fail(AVIRB200_ERR_ALLOC, "host allocation failed");
     pl->desc = *desc;
+    pl->io_in_type = desc->in_type;
+    pl->io_out_type = desc->out_type;
+    if (desc->in_type == AVIRB200_F64) pl->desc.in_type = AVIRB200_F32;   // cast on the device first
+    if (desc->out_type == AVIRB200_F64) pl->desc.out_type = AVIRB200_F32; // widened on the device last
     int r = copy_axis_host(pl->h, desc->h);
     if (r != 0) return r;
     r = copy_axis_host(pl->v, desc->v);
@@ -642,7 +681,8 @@ void avirb200_plan_destroy(avirb200_plan* pl) {
 int avirb200_plan_workspace_bytes(const avirb200_plan* pl, size_t* bytes) {
     if (pl == nullptr || bytes == nullptr) return fail(AVIRB200_ERR_BAD_ARG, "null argument");
     const avirb200_plan_desc& d = pl->desc;
-    *bytes = (size_t)d.dst_w * d.src_h * d.channels * sizeof(float);
+    *bytes = align_up((size_t)d.dst_w * d.src_h * d.channels * sizeof(float), 256) + f64_in_bytes(pl) +
+             f64_out_bytes(pl);
     return 0;
 }
 
@@ -657,10 +697,39 @@ int avirb200_resize_device(const avirb200_plan* pl, const void* d_src, size_t sr
         return fail(AVIRB200_ERR_BAD_ARG, "pitch smaller than a row");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     int launches = 0;
-    int r = run_row_pass(pl, d_src, src_pitch, static_cast<float*>(d_ws), d.src_h, st, &launches);
+    // double buffers: float copies live behind the intermediate in the workspace
+    char* wsb = static_cast<char*>(d_ws);
+    float* in32 = reinterpret_cast<float*>(wsb + align_up((size_t)d.dst_w * d.src_h * d.channels * 4, 256));
+    float* out32 = reinterpret_cast<float*>(reinterpret_cast<char*>(in32) + f64_in_bytes(pl));
+    const void* ksrc = d_src;
+    size_t ksrc_pitch = src_pitch;
+    void* kdst = d_dst;
+    size_t kdst_pitch = dst_pitch;
+    if (pl->io_in_type == AVIRB200_F64) {
+        const int re = d.src_w * d.channels;
+        const long long n = (long long)re * d.src_h;
+        narrow_f64_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(static_cast<const double*>(d_src),
+                                                                       (long long)src_pitch, in32, re, d.src_h);
+        ++launches;
+        ksrc = in32;
+        ksrc_pitch = (size_t)re;
+    }
+    if (pl->io_out_type == AVIRB200_F64) {
+        kdst = out32;
+        kdst_pitch = (size_t)d.dst_w * d.channels;
+    }
+    int r = run_row_pass(pl, ksrc, ksrc_pitch, static_cast<float*>(d_ws), d.src_h, st, &launches);
     if (r != 0) return r;
-    r = run_col_pass(pl, static_cast<const float*>(d_ws), 0, d_dst, dst_pitch, 0, d.dst_h, st,
+    r = run_col_pass(pl, static_cast<const float*>(d_ws), 0, kdst, kdst_pitch, 0, d.dst_h, st,
                      &launches);
+    if (r == 0 && pl->io_out_type == AVIRB200_F64) {
+        const int re = d.dst_w * d.channels;
+        const long long n = (long long)re * d.dst_h;
+        widen_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(out32, static_cast<double*>(d_dst),
+                                                                      (long long)dst_pitch, re, d.dst_h);
+        ++launches;
+        CUDA_TRY(cudaGetLastError());
+    }
     pl->last_launches = launches;
     return r;
 }
@@ -669,6 +738,7 @@ int avirb200_row_pass_device(const avirb200_plan* pl, const void* d_src, size_t 
                              void* d_ws, void* stream) {
     if (pl == nullptr || d_src == nullptr || d_ws == nullptr)
         return fail(AVIRB200_ERR_BAD_ARG, "null argument");
+    if (plan_has_f64(pl)) return fail(AVIRB200_ERR_UNSUPPORTED, "per-pass entry points take u8 / u16 / f32 buffers");
     int launches = 0;
     return run_row_pass(pl, d_src, src_pitch, static_cast<float*>(d_ws), pl->desc.src_h,
                         static_cast<cudaStream_t>(stream), &launches);
@@ -678,6 +748,7 @@ int avirb200_col_pass_device(const avirb200_plan* pl, const void* d_ws, void* d_
                              size_t dst_pitch, void* stream) {
     if (pl == nullptr || d_dst == nullptr || d_ws == nullptr)
         return fail(AVIRB200_ERR_BAD_ARG, "null argument");
+    if (plan_has_f64(pl)) return fail(AVIRB200_ERR_UNSUPPORTED, "per-pass entry points take u8 / u16 / f32 buffers");
     int launches = 0;
     return run_col_pass(pl, static_cast<const float*>(d_ws), 0, d_dst, dst_pitch, 0,
                         pl->desc.dst_h, static_cast<cudaStream_t>(stream), &launches);
@@ -690,8 +761,8 @@ int avirb200_resize_host(avirb200_plan* pl, const void* h_src, size_t src_pitch,
     const avirb200_plan_desc& d = pl->desc;
     std::lock_guard<std::mutex> lk(pl->mx);
     CUDA_TRY(cudaSetDevice(pl->device));
-    const size_t in_row = (size_t)d.src_w * d.channels * dtype_size(d.in_type);
-    const size_t out_row = (size_t)d.dst_w * d.channels * dtype_size(d.out_type);
+    const size_t in_row = (size_t)d.src_w * d.channels * dtype_size(pl->io_in_type);
+    const size_t out_row = (size_t)d.dst_w * d.channels * dtype_size(pl->io_out_type);
     const size_t in_bytes = in_row * d.src_h, out_bytes = out_row * d.dst_h;
     size_t ws = 0;
     avirb200_plan_workspace_bytes(pl, &ws);
@@ -711,7 +782,7 @@ int avirb200_resize_host(avirb200_plan* pl, const void* h_src, size_t src_pitch,
         CUDA_TRY(cudaMalloc(&pl->d_ws, ws));
         pl->d_ws_bytes = ws;
     }
-    const size_t in_el = dtype_size(d.in_type), out_el = dtype_size(d.out_type);
+    const size_t in_el = dtype_size(pl->io_in_type), out_el = dtype_size(pl->io_out_type);
     // Pipelined form for large images: the image is cut into row bands (the multi-GPU band
     // arithmetic, one shared intermediate buffer instead of a halo exchange).  Band b's rows
     // travel host->device on the copy-in stream while the kernels of band b-1 run on the
@@ -729,6 +800,7 @@ int avirb200_resize_host(avirb200_plan* pl, const void* h_src, size_t src_pitch,
         const char* d1 = d0 + ((size_t)(d.dst_h - 1) * dst_pitch + (size_t)d.dst_w * d.channels) * out_el;
         if (s0 < d1 && d0 < s1) nb = 1;
     }
+    if (plan_has_f64(pl)) nb = 1; // the casts run over the whole image
     std::vector<avirb200_shard_info> si;
     while (nb >= 2) { // fewer bands until every band's column pass needs only its neighbours' rows
         si.assign(nb, avirb200_shard_info());
@@ -837,6 +909,7 @@ int avirb200_resize_sharded(const avirb200_plan* pl, void* comm, int rank, int n
                             void* d_ws, void* stream) {
     if (pl == nullptr || d_src == nullptr || d_dst == nullptr || d_ws == nullptr)
         return fail(AVIRB200_ERR_BAD_ARG, "null argument");
+    if (plan_has_f64(pl)) return fail(AVIRB200_ERR_UNSUPPORTED, "sharded calls take u8 / u16 / f32 buffers");
     avirb200_shard_info si;
     int r = shard_compute(pl, rank, nranks, &si);
     if (r != 0) return r;
@@ -884,6 +957,7 @@ int avirb200_resize_sharded_local(const avirb200_plan* pl, int nranks, const voi
                                   void* stream) {
     if (pl == nullptr || d_src == nullptr || d_dst == nullptr || d_ws == nullptr)
         return fail(AVIRB200_ERR_BAD_ARG, "null argument");
+    if (plan_has_f64(pl)) return fail(AVIRB200_ERR_UNSUPPORTED, "sharded calls take u8 / u16 / f32 buffers");
     const avirb200_plan_desc& d = pl->desc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const size_t rowf = (size_t)d.dst_w * d.channels;

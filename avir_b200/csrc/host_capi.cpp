@@ -92,6 +92,7 @@ void run2(const CallArgs& a, OpArgs& o) {
     switch (a.tout) {
     case AVIRB200_U8: run3<fpclass, Tin, uint8_t>(a, o); break;
     case AVIRB200_U16: run3<fpclass, Tin, uint16_t>(a, o); break;
+    case AVIRB200_F64: run3<fpclass, Tin, double>(a, o); break;
     default: run3<fpclass, Tin, float>(a, o); break;
     }
 }
@@ -101,6 +102,7 @@ void run1(const CallArgs& a, OpArgs& o) {
     switch (a.tin) {
     case AVIRB200_U8: run2<fpclass, uint8_t>(a, o); break;
     case AVIRB200_U16: run2<fpclass, uint16_t>(a, o); break;
+    case AVIRB200_F64: run2<fpclass, double>(a, o); break;
     default: run2<fpclass, float>(a, o); break;
     }
 }

@@ -144,6 +144,7 @@ template <typename T> struct dtype_of;
 template <> struct dtype_of<uint8_t> { static constexpr int value = AVIRB200_U8; };
 template <> struct dtype_of<uint16_t> { static constexpr int value = AVIRB200_U16; };
 template <> struct dtype_of<float> { static constexpr int value = AVIRB200_F32; };
+template <> struct dtype_of<double> { static constexpr int value = AVIRB200_F64; };
 
 inline void check(int status, const char* what) {
     if (status == AVIRB200_OK) return;
@@ -270,8 +271,6 @@ public:
                     const int NewHeight, const int ElCountIO, const double k,
                     CImageResizerVars& Vars) const {
         using namespace avirb200::plan;
-        static_assert(!std::is_same<Tin, double>::value && !std::is_same<Tout, double>::value,
-                      "avir_b200: double image buffers are not supported on the GPU path");
         if (ElCountIO < 1 || ElCountIO > 4)
             throw std::runtime_error("avir_b200: ElCountIO must be 1..4");
         CallDesc c;
@@ -298,7 +297,9 @@ public:
         d.round_mode = fpclass::round_mode;
         // Upstream's interleaved float-intermediate class writes float output straight from
         // the column pass and thereby skips applySRGBGamma (avir.h:4956-4979); mirrored.
-        const bool SkipOutGamma = (fpclass::id == 0 && c.out_float);
+        // (only when Tout has the intermediate's own size: double output takes the ordinary
+        // output stage, avir.h:4956)
+        const bool SkipOutGamma = (fpclass::id == 0 && c.out_float && sizeof(Tout) == sizeof(float));
         d.use_gamma = Vars.UseSRGBGamma ? (SkipOutGamma ? 1 : 3) : 0;
         d.alpha_index = (ElCountIO == 4 && (Vars.AlphaIndex == 0 || Vars.AlphaIndex == 3))
                             ? Vars.AlphaIndex : -1;

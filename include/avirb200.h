@@ -36,8 +36,12 @@ typedef enum avirb200_status {
     AVIRB200_ERR_ALLOC = -6
 } avirb200_status;
 
-/* Element types of the caller's image buffers (upstream Tin/Tout, avir.h:4670-4677). */
-typedef enum avirb200_dtype { AVIRB200_U8 = 0, AVIRB200_U16 = 1, AVIRB200_F32 = 2 } avirb200_dtype;
+/* Element types of the caller's image buffers (upstream Tin/Tout, avir.h:4670-4677).
+ * F64: upstream narrows double input with a (float) cast in packScanline and widens the float
+ * result with a (double) cast in unpackScanline (avir.h:2803-2806, 3168-3171); the library
+ * does the same casts on the device (resize_device / resize_host; the sharded calls and the
+ * per-pass entry points take U8 / U16 / F32 only). */
+typedef enum avirb200_dtype { AVIRB200_U8 = 0, AVIRB200_U16 = 1, AVIRB200_F32 = 2, AVIRB200_F64 = 3 } avirb200_dtype;
 
 /* Step kinds of a 1-D filtering chain (upstream CImageResizerFilterStep, avir.h:2568-2728). */
 typedef enum avirb200_step_kind {

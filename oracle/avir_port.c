@@ -278,6 +278,7 @@ static float load_elem(const void* src, int type, size_t idx)
     switch (type) {
     case AVIRB200_U8: return (float)((const uint8_t*)src)[idx];
     case AVIRB200_U16: return (float)((const uint16_t*)src)[idx];
+    case AVIRB200_F64: return (float)((const double*)src)[idx]; /* (fptypeatom) ip[c], avir.h:2803-2806 */
     default: return ((const float*)src)[idx];
     }
 }
@@ -376,6 +377,10 @@ int avir_port_col_pass(const avirb200_plan_desc* d, const float* mid, int mid_ro
                 const size_t idx = (size_t)(y - out0) * dst_pitch + (size_t)x * C + c;
                 if (d->out_type == AVIRB200_F32) {
                     ((float*)dst)[idx] = v;
+                    continue;
+                }
+                if (d->out_type == AVIRB200_F64) { /* (Tout) v[c], avir.h:3168-3171 */
+                    ((double*)dst)[idx] = (double)v;
                     continue;
                 }
                 if (d->tr_mul == 1.0f) v = round_mode(v, d->round_mode);

@@ -361,6 +361,7 @@ int run2( const Call& c, const int tout )
 		case 0: run3< fpclass, Tin, uint8_t >( c ); return 0;
 		case 1: run3< fpclass, Tin, uint16_t >( c ); return 0;
 		case 2: run3< fpclass, Tin, float >( c ); return 0;
+		case 3: run3< fpclass, Tin, double >( c ); return 0;
 	}
 
 	return -1;
@@ -374,6 +375,7 @@ int run1( const Call& c, const int tin, const int tout )
 		case 0: return run2< fpclass, uint8_t >( c, tout );
 		case 1: return run2< fpclass, uint16_t >( c, tout );
 		case 2: return run2< fpclass, float >( c, tout );
+		case 3: return run2< fpclass, double >( c, tout );
 	}
 
 	return -1;
@@ -411,7 +413,7 @@ void put( std::vector< double >& o, double v ) { o.push_back( v ); }
 extern "C" {
 
 // fpclass: 0 = fpclass_def<float>, 1 = fpclass_float4, 2 = fpclass_float8_dil.
-// tin/tout: 0 = uint8_t, 1 = uint16_t, 2 = float.
+// tin/tout: 0 = uint8_t, 1 = uint16_t, 2 = float, 3 = double.
 int avir_ref_resize( int fpclass, int tin, int tout,
 	const void* src, int sw, int sh, int sls, void* dst, int nw, int nh, int C,
 	double k, int resbits, int srcbits, double ox, double oy, int gamma,

@@ -14,7 +14,7 @@ import oracle_ref as o
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
-u8, u16, f32 = np.uint8, np.uint16, np.float32
+u8, u16, f32, f64 = np.uint8, np.uint16, np.float32, np.float64
 
 # Scaled-down versions of the BASELINE.json configs first, then coverage of every chain
 # shape, type combination, channel count and option.
@@ -65,6 +65,14 @@ SMALL_CASES = [
     (2, 90, 70, 60, 45, 4, f32, f32, 16, {"k": -1.5}),
     (1, 96, 64, 48, 32, 4, u8, u8, 8, {"params": 1}),
     (2, 96, 64, 48, 32, 4, u8, u8, 8, {"params": 5}),
+    # double image buffers: (float) cast in, (double) cast out (avir.h:2803-2806, 3168-3171);
+    # double output of the default class takes the ordinary output stage, gamma included
+    (1, 192, 108, 96, 54, 4, f64, f64, 16, {}),
+    (2, 192, 108, 96, 54, 4, f64, f32, 16, {"buildmode": 1}),
+    (0, 120, 80, 60, 40, 3, u8, f64, 8, {"gamma": True}),
+    (0, 120, 80, 60, 40, 3, f32, f64, 16, {"gamma": True}),
+    (1, 100, 60, 150, 77, 4, f64, u16, 16, {"gamma": True, "alpha": 3}),
+    (2, 150, 90, 100, 55, 2, f64, u8, 8, {}),
     # tiny / ragged
     (1, 1, 1, 5, 7, 4, u8, u8, 8, {}),
     (1, 7, 5, 1, 1, 4, u8, u8, 8, {}),
@@ -77,7 +85,7 @@ def make_input(case, seed=7, structured=None):
     fp, sw, sh, nw, nh, ch, ti, to, rb, kw = case
     if structured is None:
         return o.lcg_image(sh, sw, ch, ti, seed=seed)
-    mx = {u8: 255, u16: 65535, f32: 1.0}[ti]
+    mx = {u8: 255, u16: 65535, f32: 1.0, f64: 1.0}[ti]
     img = np.zeros((sh, sw, ch), dtype=ti)
     if structured == "ramp":
         xs = (np.arange(sw) / max(sw - 1, 1))[None, :, None]

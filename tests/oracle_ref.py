@@ -18,7 +18,8 @@ REF_SO = os.path.join(ROOT, "oracle", "_ref", "libavir_ref.so")
 FP_DEF, FP_FLOAT4, FP_FLOAT8_DIL = 0, 1, 2
 T_U8, T_U16, T_F32 = 0, 1, 2
 NP_T = {T_U8: np.uint8, T_U16: np.uint16, T_F32: np.float32}
-T_OF = {np.dtype(np.uint8): T_U8, np.dtype(np.uint16): T_U16, np.dtype(np.float32): T_F32}
+T_OF = {np.dtype(np.uint8): T_U8, np.dtype(np.uint16): T_U16, np.dtype(np.float32): T_F32,
+        np.dtype(np.float64): 3}
 
 _ref = None
 
@@ -76,6 +77,8 @@ def _scale_draws(draws, dtype):
         return lo.astype(np.uint16)
     if dtype == np.uint8:
         return (lo * (1.0 / 257)).astype(np.uint8)
+    if dtype == np.float64:
+        return lo * (1.0 / 65535)  # not representable in float: the (float) cast of the path rounds
     return (lo * (1.0 / 65535)).astype(np.float32)
 
 
