@@ -8,6 +8,6 @@ benchmark and torch-side buffer management; it performs no image arithmetic and 
 fallback -- every call goes to the CUDA library and raises if that fails.
 """
 from .api import (  # noqa: F401
-    FP_DEF, FP_FLOAT4, FP_FLOAT8_DIL, CImageResizer, CImageResizerVars, CLancIR,
+    FP_DEF, FP_FLOAT4, FP_FLOAT8_DIL, FP_DEF_ERRD, FP_FLOAT4_ERRD, FP_FLOAT8_DIL_ERRD, CImageResizer, CImageResizerVars, CLancIR,
     CLancIRParams, AvirB200Error, lib, host_lib, device_count,
 )

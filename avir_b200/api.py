@@ -13,6 +13,8 @@ import numpy as np
 _PKG = os.path.dirname(os.path.abspath(__file__))
 
 FP_DEF, FP_FLOAT4, FP_FLOAT8_DIL = 0, 1, 2
+# the same classes composed with upstream's error-diffusion ditherer (CImageResizerDithererErrdINL/DIL)
+FP_DEF_ERRD, FP_FLOAT4_ERRD, FP_FLOAT8_DIL_ERRD = 3, 4, 5
 _T = {np.dtype(np.uint8): 0, np.dtype(np.uint16): 1, np.dtype(np.float32): 2, np.dtype(np.float64): 3}
 
 

@@ -110,6 +110,7 @@ struct HostAxis {
 struct avirb200_plan {
     avirb200_plan_desc desc;     // in_type / out_type: what the KERNELS read and write (F64 -> F32)
     int io_in_type = 0, io_out_type = 0; // the caller's element types
+    bool errd = false;                   // integer output through the error-diffusion ditherer
     HostAxis h, v;
     void* arena = nullptr;
     float* d_lut = nullptr;
@@ -530,6 +531,123 @@ DevAxis host_axis_view(const avirb200_axis_desc& ad) {
     return d;
 }
 
+// ---- error-diffusion ditherer (upstream CImageResizerDithererErrdINL / ErrdDIL) ---------------
+// avir.h:4485-4525, avir_dil.h:927-986, driven row by row from resizeImage (avir.h:5046-5064).
+// Per channel, pixel j of row y:   R = (v[j] + D_y[j]) [+ 0.364842 * Noise(j-1)];
+//   z = round(R * TrMulI) * TrMul;  Noise = R - z;  out = clamp(z, 0, PkOut);
+// and the row below adds D_{y+1}[q] = ((0 + 0.063011*Noise(q-1)) + 0.364842*Noise(q)) + 0.207305*Noise(q+1)
+// (the order in which upstream's three "+=" reach the element).  The recursion runs along the
+// row AND down the rows, so the parallel form is a wavefront: row y+1 may process pixel q once
+// row y has finished pixel q+1.  One warp takes 32 consecutive rows as a systolic array -- lane =
+// row, lane l works on pixel t - 2l at step t and hands D_{y+1}[q] to lane l+1 by shuffle, one
+// step before it is needed; lane 31 hands its values to lane 0 of the next warp (another block)
+// through a row of boundary values in global memory plus a progress counter.  Every block is
+// resident at once (one warp each); a block only ever waits for the block before it.
+// Quirk kept: the de-interleaved class stores a row as consecutive channel planes and runs them
+// one after the other, so the "Dith[j-1] +=" of pixel 0 of plane c+1 lands on the last pixel of
+// plane c (avir_dil.h:964, rsdj[-1] with j = 0):  D_{y+1}[c][W-1] gains + 0.207305*Noise_{c+1}(0).
+struct ErrdParams {
+    const float* src;     // [H][W*C] gamma-corrected floats (the column pass's output)
+    void* dst;
+    long long dst_pitch;  // elements
+    int W, H, dst_type, round_mode;
+    int planar;           // de-interleaved class: channel c+1's pixel 0 also feeds channel c's last D (see below)
+    float tr_mul, tr_mul_inv, pk_out;
+    float* boundary;      // [groups][W*C]
+    int* progress;        // [groups]: pixels of the group's last row whose D values are published
+};
+
+template <int C>
+__global__ void __launch_bounds__(32) errd_kernel(const __grid_constant__ ErrdParams p) {
+    const int g = blockIdx.x, lane = threadIdx.x;
+    const int W = p.W, y = g * 32 + lane;
+    const bool rowok = y < p.H;
+    const float* row = p.src + (size_t)(rowok ? y : p.H - 1) * W * C;
+    const float* bnd_in = p.boundary + (size_t)(g > 0 ? g - 1 : 0) * W * C;
+    float* bnd_out = p.boundary + (size_t)g * W * C;
+    volatile int* prog_in = p.progress + (g > 0 ? g - 1 : 0);
+    volatile int* prog_out = p.progress + g;
+    const bool publish = (lane == 31) && ((g + 1) * 32 < p.H);
+    int seen = 0; // lane 0: pixels the group above is known to have published
+    float nm1[C], c3p[C], part[C], dn[C], v[C], vn[C], n2first[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) { nm1[c] = c3p[c] = part[c] = dn[c] = n2first[c] = 0.0f; v[c] = vn[c] = 0.0f; }
+    if (lane == 0 && W > 0) {
+#pragma unroll
+        for (int c = 0; c < C; ++c) vn[c] = __ldg(row + c);
+    }
+    const int steps = W + 2 * 31 + 1;
+    for (int t = 0; t < steps; ++t) {
+        const int pix = t - 2 * lane;
+        const bool on = rowok && pix >= 0 && pix < W;
+        // D of this pixel: from the lane above (finalised there during the previous step) ...
+        float din[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) din[c] = __shfl_up_sync(0xffffffffu, dn[c], 1);
+        // ... or, for the group's first row, from the group above (row 0 of the image: zero)
+        if (lane == 0 && on) {
+            if (g == 0) {
+#pragma unroll
+                for (int c = 0; c < C; ++c) din[c] = 0.0f;
+            } else {
+                while (seen <= pix) seen = *prog_in;
+                __threadfence();
+#pragma unroll
+                for (int c = 0; c < C; ++c) din[c] = __ldcg(bnd_in + (size_t)pix * C + c);
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < C; ++c) v[c] = vn[c];
+        // the next pixel's input does not depend on the recursion: fetch it now
+        if (rowok && pix + 1 >= 0 && pix + 1 < W) {
+#pragma unroll
+            for (int c = 0; c < C; ++c) vn[c] = __ldg(row + (size_t)(pix + 1) * C + c);
+        }
+        if (on) {
+            float o[C];
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                float R = __fadd_rn(v[c], din[c]);
+                if (pix > 0) R = __fadd_rn(R, nm1[c]);
+                const float z0 = __fmul_rn(avb::round_out(__fmul_rn(R, p.tr_mul_inv), p.round_mode), p.tr_mul);
+                const float noise = __fsub_rn(R, z0);
+                o[c] = z0 < 0.0f ? 0.0f : (z0 > p.pk_out ? p.pk_out : z0);
+                const float n1 = __fmul_rn(noise, 0.364842f);
+                const float n2 = __fmul_rn(noise, 0.207305f);
+                const float n3 = __fmul_rn(noise, 0.063011f);
+                if (pix == 0) n2first[c] = n2;
+                dn[c] = __fadd_rn(part[c], n2); // D_{y+1}[pix-1] is complete (unused for pix == 0)
+                part[c] = (pix == 0) ? __fadd_rn(0.0f, n1) : __fadd_rn(__fadd_rn(0.0f, c3p[c]), n1);
+                c3p[c] = n3;
+                nm1[c] = n1;
+            }
+            const size_t oi = (size_t)y * (size_t)p.dst_pitch + (size_t)pix * C;
+            if (p.dst_type == AVIRB200_U8) {
+#pragma unroll
+                for (int c = 0; c < C; ++c) static_cast<unsigned char*>(p.dst)[oi + c] = (unsigned char)o[c];
+            } else {
+#pragma unroll
+                for (int c = 0; c < C; ++c) static_cast<unsigned short*>(p.dst)[oi + c] = (unsigned short)o[c];
+            }
+        } else if (rowok && pix == W) {
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                dn[c] = part[c]; // D_{y+1}[W-1]: no pixel to its right ...
+                if (p.planar && c + 1 < C) dn[c] = __fadd_rn(dn[c], n2first[c + 1]); // ... but the next plane's pixel 0
+            }
+        }
+        if (publish) {
+            const int q = (on && pix >= 1) ? pix - 1 : ((pix == W) ? W - 1 : -1);
+            if (q >= 0) {
+#pragma unroll
+                for (int c = 0; c < C; ++c) __stcg(bnd_out + (size_t)q * C + c, dn[c]);
+                __threadfence();
+                *prog_out = q + 1;
+            }
+        }
+    }
+}
+
 // ---- double image buffers: the casts upstream's pack / unpack perform, as two small kernels ----
 
 __global__ void __launch_bounds__(256) narrow_f64_kernel(const double* __restrict__ src, long long src_pitch,
@@ -555,13 +673,21 @@ size_t f64_in_bytes(const avirb200_plan* pl) {
     return pl->io_in_type == AVIRB200_F64 ? align_up((size_t)d.src_w * d.src_h * d.channels * 4, 256) : 0;
 }
 
-size_t f64_out_bytes(const avirb200_plan* pl) {
+size_t f64_out_bytes(const avirb200_plan* pl) { // float copy of the destination (double output, error diffusion)
     const avirb200_plan_desc& d = pl->desc;
-    return pl->io_out_type == AVIRB200_F64 ? align_up((size_t)d.dst_w * d.dst_h * d.channels * 4, 256) : 0;
+    return (pl->io_out_type == AVIRB200_F64 || pl->errd) ? align_up((size_t)d.dst_w * d.dst_h * d.channels * 4, 256) : 0;
 }
 
-bool plan_has_f64(const avirb200_plan* pl) {
-    return pl->io_in_type == AVIRB200_F64 || pl->io_out_type == AVIRB200_F64;
+// error diffusion: per 32-row group one row of boundary values + one progress counter
+int errd_groups(const avirb200_plan* pl) { return (pl->desc.dst_h + 31) / 32; }
+size_t errd_bytes(const avirb200_plan* pl) {
+    if (!pl->errd) return 0;
+    const avirb200_plan_desc& d = pl->desc;
+    return align_up((size_t)errd_groups(pl) * d.dst_w * d.channels * 4, 256) + align_up((size_t)errd_groups(pl) * 4, 256);
+}
+
+bool plan_has_f64(const avirb200_plan* pl) { // plans that only run as a whole image through resize_device / _host
+    return pl->io_in_type == AVIRB200_F64 || pl->io_out_type == AVIRB200_F64 || pl->errd;
 }
 
 } // namespace
@@ -630,6 +756,11 @@ int avirb200_plan_create(const avirb200_plan_desc* desc, avirb200_plan** out) {
     pl->io_out_type = desc->out_type;
     if (desc->in_type == AVIRB200_F64) pl->desc.in_type = AVIRB200_F32;   // cast on the device first
     if (desc->out_type == AVIRB200_F64) pl->desc.out_type = AVIRB200_F32; // widened on the device last
+    if (desc->dither == 1 && (desc->out_type == AVIRB200_U8 || desc->out_type == AVIRB200_U16)) {
+        // the column pass delivers the gamma-corrected float rows; errd_kernel rounds them in row order
+        pl->errd = true;
+        pl->desc.out_type = AVIRB200_F32;
+    }
     int r = copy_axis_host(pl->h, desc->h);
     if (r != 0) return r;
     r = copy_axis_host(pl->v, desc->v);
@@ -653,10 +784,11 @@ int avirb200_plan_create(const avirb200_plan_desc* desc, avirb200_plan** out) {
 
     pl->cfg_h = choose_generic_config(pl->h.hostdev, desc->channels, 0, desc->dst_w);
     pl->cfg_v = choose_generic_config(pl->v.hostdev, desc->channels, 0, desc->dst_h);
-    fast_plan_init(pl->fast, pl->h.hostdev, pl->v.hostdev, *desc);
+    // (pl->desc, not *desc: the kernels' element types, see io_in_type / io_out_type)
+    fast_plan_init(pl->fast, pl->h.hostdev, pl->v.hostdev, pl->desc);
     const char* up2e = getenv("AVIRB200_STREAM_UP2"); // tuning switch, see stream_plan_axis()
     const bool up2 = up2e && up2e[0] == '1';
-    if (avs::stream_row_source_ok(*desc))
+    if (avs::stream_row_source_ok(pl->desc))
         avs::stream_plan_axis(desc->h, desc->sum_mode, desc->channels, pl->stream_h, up2);
     avs::stream_plan_axis(desc->v, desc->sum_mode, desc->channels, pl->stream_v, up2);
     *out = pl.release();
@@ -682,7 +814,7 @@ int avirb200_plan_workspace_bytes(const avirb200_plan* pl, size_t* bytes) {
     if (pl == nullptr || bytes == nullptr) return fail(AVIRB200_ERR_BAD_ARG, "null argument");
     const avirb200_plan_desc& d = pl->desc;
     *bytes = align_up((size_t)d.dst_w * d.src_h * d.channels * sizeof(float), 256) + f64_in_bytes(pl) +
-             f64_out_bytes(pl);
+             f64_out_bytes(pl) + errd_bytes(pl);
     return 0;
 }
 
@@ -714,7 +846,7 @@ int avirb200_resize_device(const avirb200_plan* pl, const void* d_src, size_t sr
         ksrc = in32;
         ksrc_pitch = (size_t)re;
     }
-    if (pl->io_out_type == AVIRB200_F64) {
+    if (pl->io_out_type == AVIRB200_F64 || pl->errd) {
         kdst = out32;
         kdst_pitch = (size_t)d.dst_w * d.channels;
     }
@@ -730,6 +862,29 @@ int avirb200_resize_device(const avirb200_plan* pl, const void* d_src, size_t sr
         ++launches;
         CUDA_TRY(cudaGetLastError());
     }
+    if (r == 0 && pl->errd) {
+        ErrdParams ep;
+        ep.src = out32;
+        ep.dst = d_dst;
+        ep.dst_pitch = (long long)dst_pitch;
+        ep.W = d.dst_w; ep.H = d.dst_h;
+        ep.dst_type = pl->io_out_type;
+        ep.round_mode = d.round_mode;
+        ep.planar = (d.sum_mode == AVIRB200_SUM_DIL8) ? 1 : 0;
+        ep.tr_mul = d.tr_mul; ep.tr_mul_inv = d.tr_mul_inv; ep.pk_out = d.pk_out;
+        char* eb = reinterpret_cast<char*>(out32) + f64_out_bytes(pl);
+        ep.boundary = reinterpret_cast<float*>(eb);
+        ep.progress = reinterpret_cast<int*>(eb + align_up((size_t)errd_groups(pl) * d.dst_w * d.channels * 4, 256));
+        CUDA_TRY(cudaMemsetAsync(ep.progress, 0, (size_t)errd_groups(pl) * 4, st));
+        switch (d.channels) {
+        case 1: errd_kernel<1><<<errd_groups(pl), 32, 0, st>>>(ep); break;
+        case 2: errd_kernel<2><<<errd_groups(pl), 32, 0, st>>>(ep); break;
+        case 3: errd_kernel<3><<<errd_groups(pl), 32, 0, st>>>(ep); break;
+        default: errd_kernel<4><<<errd_groups(pl), 32, 0, st>>>(ep); break;
+        }
+        ++launches;
+        CUDA_TRY(cudaGetLastError());
+    }
     pl->last_launches = launches;
     return r;
 }
@@ -738,7 +893,7 @@ int avirb200_row_pass_device(const avirb200_plan* pl, const void* d_src, size_t 
                              void* d_ws, void* stream) {
     if (pl == nullptr || d_src == nullptr || d_ws == nullptr)
         return fail(AVIRB200_ERR_BAD_ARG, "null argument");
-    if (plan_has_f64(pl)) return fail(AVIRB200_ERR_UNSUPPORTED, "per-pass entry points take u8 / u16 / f32 buffers");
+    if (plan_has_f64(pl)) return fail(AVIRB200_ERR_UNSUPPORTED, "per-pass entry points: no double buffers, no error diffusion");
     int launches = 0;
     return run_row_pass(pl, d_src, src_pitch, static_cast<float*>(d_ws), pl->desc.src_h,
                         static_cast<cudaStream_t>(stream), &launches);
@@ -748,7 +903,7 @@ int avirb200_col_pass_device(const avirb200_plan* pl, const void* d_ws, void* d_
                              size_t dst_pitch, void* stream) {
     if (pl == nullptr || d_dst == nullptr || d_ws == nullptr)
         return fail(AVIRB200_ERR_BAD_ARG, "null argument");
-    if (plan_has_f64(pl)) return fail(AVIRB200_ERR_UNSUPPORTED, "per-pass entry points take u8 / u16 / f32 buffers");
+    if (plan_has_f64(pl)) return fail(AVIRB200_ERR_UNSUPPORTED, "per-pass entry points: no double buffers, no error diffusion");
     int launches = 0;
     return run_col_pass(pl, static_cast<const float*>(d_ws), 0, d_dst, dst_pitch, 0,
                         pl->desc.dst_h, static_cast<cudaStream_t>(stream), &launches);
@@ -800,7 +955,7 @@ int avirb200_resize_host(avirb200_plan* pl, const void* h_src, size_t src_pitch,
         const char* d1 = d0 + ((size_t)(d.dst_h - 1) * dst_pitch + (size_t)d.dst_w * d.channels) * out_el;
         if (s0 < d1 && d0 < s1) nb = 1;
     }
-    if (plan_has_f64(pl)) nb = 1; // the casts run over the whole image
+    if (plan_has_f64(pl)) nb = 1; // the casts / the row-recursive ditherer run over the whole image
     std::vector<avirb200_shard_info> si;
     while (nb >= 2) { // fewer bands until every band's column pass needs only its neighbours' rows
         si.assign(nb, avirb200_shard_info());
@@ -909,7 +1064,7 @@ int avirb200_resize_sharded(const avirb200_plan* pl, void* comm, int rank, int n
                             void* d_ws, void* stream) {
     if (pl == nullptr || d_src == nullptr || d_dst == nullptr || d_ws == nullptr)
         return fail(AVIRB200_ERR_BAD_ARG, "null argument");
-    if (plan_has_f64(pl)) return fail(AVIRB200_ERR_UNSUPPORTED, "sharded calls take u8 / u16 / f32 buffers");
+    if (plan_has_f64(pl)) return fail(AVIRB200_ERR_UNSUPPORTED, "sharded calls: no double buffers, no error diffusion");
     avirb200_shard_info si;
     int r = shard_compute(pl, rank, nranks, &si);
     if (r != 0) return r;
@@ -957,7 +1112,7 @@ int avirb200_resize_sharded_local(const avirb200_plan* pl, int nranks, const voi
                                   void* stream) {
     if (pl == nullptr || d_src == nullptr || d_dst == nullptr || d_ws == nullptr)
         return fail(AVIRB200_ERR_BAD_ARG, "null argument");
-    if (plan_has_f64(pl)) return fail(AVIRB200_ERR_UNSUPPORTED, "sharded calls take u8 / u16 / f32 buffers");
+    if (plan_has_f64(pl)) return fail(AVIRB200_ERR_UNSUPPORTED, "sharded calls: no double buffers, no error diffusion");
     const avirb200_plan_desc& d = pl->desc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const size_t rowf = (size_t)d.dst_w * d.channels;

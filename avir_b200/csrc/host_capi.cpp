@@ -112,6 +112,10 @@ int run0(const CallArgs& a, OpArgs& o) {
         switch (a.mirror) {
         case 1: run1<avir::fpclass_float4>(a, o); break;
         case 2: run1<avir::fpclass_float8_dil>(a, o); break;
+        // the same three classes with upstream's error-diffusion ditherer
+        case 3: run1<avir::fpclass_def<float, float, avir::CImageResizerDithererErrdINL<float> > >(a, o); break;
+        case 4: run1<avir::fpclass_def<avir::float4, float, avir::CImageResizerDithererErrdINL<avir::float4> > >(a, o); break;
+        case 5: run1<avir::fpclass_def_dil<float, avir::float8, avir::CImageResizerDithererErrdDIL<float, avir::float8> > >(a, o); break;
         default: run1<avir::fpclass_def<float> >(a, o); break;
         }
     } catch (const std::exception& e) {
@@ -145,8 +149,8 @@ void put_axis(std::vector<double>& o, const AxisPlan& a) {
 
 Mirror mirror_of(int id) {
     switch (id) {
-    case 1: return kMirrorFloat4;
-    case 2: return kMirrorFloat8Dil;
+    case 1: case 4: return kMirrorFloat4;
+    case 2: case 5: return kMirrorFloat8Dil;
     default: return kMirrorDef;
     }
 }
@@ -162,7 +166,7 @@ extern "C" {
 const char* avirb200_host_last_error() { return g_err.c_str(); }
 
 // Serialises the plan the host would build for one resizeImage() call.
-// mirror: 0 def, 1 float4, 2 float8_dil.  Returns doubles needed (size with cap = 0).
+// mirror: 0 def, 1 float4, 2 float8_dil (+3: the same class with the error-diffusion ditherer).  Returns doubles needed (size with cap = 0).
 long avirb200_host_plan_dump(int mirror, int res_bits, int src_bits, int params_id, int src_w,
                              int src_h, int new_w, int new_h, int channels, double k, double ox,
                              double oy, int in_float, int out_float, int in_bytes, int out_bytes,

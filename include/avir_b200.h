@@ -114,29 +114,66 @@ struct b200_mirror_def {
     static constexpr int sum_mode = AVIRB200_SUM_INL;
     static constexpr int round_mode = AVIRB200_ROUND_HALFUP_INT;
     static constexpr int id = 0;
+    static constexpr int dither = 0;
 };
 struct b200_mirror_float4 {
     static constexpr avirb200::plan::Mirror mirror() { return avirb200::plan::kMirrorFloat4; }
     static constexpr int sum_mode = AVIRB200_SUM_INL;
     static constexpr int round_mode = AVIRB200_ROUND_RNE_I32;
     static constexpr int id = 1;
+    static constexpr int dither = 0;
 };
 struct b200_mirror_float8_dil {
     static constexpr avirb200::plan::Mirror mirror() { return avirb200::plan::kMirrorFloat8Dil; }
     static constexpr int sum_mode = AVIRB200_SUM_DIL8;
     static constexpr int round_mode = AVIRB200_ROUND_RNE;
     static constexpr int id = 2;
+    static constexpr int dither = 0;
 };
 
-template <typename afptype = float, typename afptypeatom = afptype, class adith = void>
-class fpclass_def : public b200_mirror_def {
-    static_assert(std::is_same<afptype, float>::value,
-                  "avir_b200: only float intermediates exist on the GPU path (no double fptype)");
-    static_assert(std::is_void<adith>::value,
-                  "avir_b200: custom ditherers (error diffusion) are not available on the GPU path");
+// Upstream's SIMD value types and ditherer classes, as tags: they only select what the GPU
+// path mirrors (avir_float4_sse.h:35, avir_float8_avx.h:36; avir.h:4334, 4442; avir_dil.h:770, 882).
+struct float4 {};
+struct float8 {};
+template <typename fptype> class CImageResizerDithererDefINL {};
+template <typename fptype> class CImageResizerDithererErrdINL {};
+template <typename fptype, typename fptypesimd> class CImageResizerDithererDefDIL {};
+template <typename fptype, typename fptypesimd> class CImageResizerDithererErrdDIL {};
+
+namespace b200_detail {
+template <class T> struct mirror_for;      // interleaved classes by their fptype
+template <> struct mirror_for<float> { typedef b200_mirror_def type; };
+template <> struct mirror_for<float4> { typedef b200_mirror_float4 type; };
+template <class D> struct dither_of;       // 0 = per-sample rounding, 1 = error diffusion
+template <class T> struct dither_of<CImageResizerDithererDefINL<T> > { static constexpr int value = 0; };
+template <class T> struct dither_of<CImageResizerDithererErrdINL<T> > { static constexpr int value = 1; };
+template <class T, class S> struct dither_of<CImageResizerDithererDefDIL<T, S> > { static constexpr int value = 0; };
+template <class T, class S> struct dither_of<CImageResizerDithererErrdDIL<T, S> > { static constexpr int value = 1; };
+} // namespace b200_detail
+
+// avir.h:4569-4592.  afptype float or float4 (the tag above); other types, e.g. double
+// intermediates, do not exist on the GPU path.
+template <typename afptype = float, typename afptypeatom = afptype,
+          class adith = CImageResizerDithererDefINL<afptype> >
+class fpclass_def : public b200_detail::mirror_for<afptype>::type {
+public:
+    static constexpr int dither = b200_detail::dither_of<adith>::value;
 };
-typedef b200_mirror_float4 fpclass_float4;
-typedef b200_mirror_float8_dil fpclass_float8_dil;
+// avir_dil.h:1000-1023 with float8 (avir_float8_avx.h:370).
+template <typename afptype, typename afptypesimd,
+          class adith = CImageResizerDithererDefDIL<afptype, afptypesimd> >
+class fpclass_def_dil : public b200_mirror_float8_dil {
+    static_assert(std::is_same<afptype, float>::value && std::is_same<afptypesimd, float8>::value,
+                  "avir_b200: the de-interleaved class mirrored on the GPU path is <float, float8>");
+public:
+    static constexpr int dither = b200_detail::dither_of<adith>::value;
+    // ErrdDIL rounds one scalar at a time: `rsj[0] * TrMulI` converts the float8 constant to
+    // float (float8::operator float, avir_float8_avx.h:85), so round() is avir::round<float>,
+    // (int)(v + 0.5) (avir_dil.h:958, avir.h:130-135) -- not float8's nearest-even
+    static constexpr int round_mode = dither ? AVIRB200_ROUND_HALFUP_INT : AVIRB200_ROUND_RNE;
+};
+typedef fpclass_def<float4, float> fpclass_float4;
+typedef fpclass_def_dil<float, float8> fpclass_float8_dil;
 
 namespace b200_detail {
 
@@ -295,6 +332,7 @@ public:
         d.out_type = b200_detail::dtype_of<Tout>::value;
         d.sum_mode = fpclass::sum_mode;
         d.round_mode = fpclass::round_mode;
+        d.dither = c.out_float ? 0 : fpclass::dither; // float output skips dithering (avir.h:5002-5023)
         // Upstream's interleaved float-intermediate class writes float output straight from
         // the column pass and thereby skips applySRGBGamma (avir.h:4956-4979); mirrored.
         // (only when Tout has the intermediate's own size: double output takes the ordinary

@@ -113,6 +113,9 @@ typedef struct avirb200_plan_desc {
     float out_gamma_mult;    /* (float)Vars.OutGammaMult (avir.h:2987) */
     float tr_mul, tr_mul_inv; /* bit-depth truncation multipliers (avir.h:4408-4417); 1 = off */
     float pk_out;            /* output clamp ceiling (avir.h:5043) */
+    int32_t dither;          /* integer output: 0 = per-sample rounding (CImageResizerDithererDefINL/DIL,
+                                avir.h:4392-4419), 1 = error diffusion (CImageResizerDithererErrdINL/DIL,
+                                avir.h:4442-4530, avir_dil.h:882-986): row-recursive, whole image only */
     avirb200_axis_desc h, v; /* row pass, column pass */
 } avirb200_plan_desc;
 

@@ -348,6 +348,60 @@ int avir_port_row_pass(const avirb200_plan_desc* d, const void* src, size_t src_
     return 0;
 }
 
+/* Error-diffusion dithering of the finished (gamma-corrected) float rows, top to bottom:
+ * CImageResizerDithererErrdINL::dither (avir.h:4485-4525) / ErrdDIL (avir_dil.h:927-986),
+ * driven row by row from resizeImage (avir.h:5046-5064).  Per channel, pixel j of a row:
+ *   R = (v[j] + Dith[j]) [+ 0.364842 * Noise(j-1)];  z = round(R * TrMulI) * TrMul;
+ *   Noise = R - z;  out = clamp(z, 0, PkOut);
+ *   Dith'[j-1] += 0.207305 * Noise;  Dith'[j] += 0.364842 * Noise;  Dith'[j+1] += 0.063011 * Noise
+ * where Dith' (zeroed when the row begins) is what the NEXT row adds.  Contributions reach a
+ * Dith' element in the order (from j-1: 0.063011) -> (own: 0.364842) -> (from j+1: 0.207305),
+ * starting from 0; the additions are kept in that order.  round() is the class's own.
+ * The de-interleaved class keeps the channels of a row as consecutive planes and runs them
+ * one after the other, so its "Dith'[j-1] +=" of pixel 0 of channel c+1 lands on the LAST
+ * pixel of channel c (avir_dil.h:964: rsdj[-1] with j = 0): mirrored. */
+static void errd_rows(const avirb200_plan_desc* d, float* res, void* dst, size_t dst_pitch)
+{
+    const int C = d->channels, W = d->dst_w, H = d->dst_h;
+    const float c1 = 0.364842f, c2 = 0.207305f, c3 = 0.063011f;
+    float* dith = (float*)calloc((size_t)(W + 2) * C, sizeof(float)); /* one pixel of slack either side */
+    float* D = dith + C;
+    const int planar = (d->sum_mode == AVIRB200_SUM_DIL8);
+    for (int y = 0; y < H; y++) {
+        float* r = res + (size_t)y * W * C;
+        float first_n2[4] = {0, 0, 0, 0};
+        int leak[4] = {0, 0, 0, 0};
+        for (int j = 0; j < W * C; j++) { /* avir.h:4493-4497 */
+            r[j] = r[j] + D[j];
+            D[j] = 0.0f;
+        }
+        for (int j = 0; j < W * C; j++) {
+            const float z0 = round_mode(r[j] * d->tr_mul_inv, d->round_mode) * d->tr_mul;
+            const float noise = r[j] - z0;
+            r[j] = z0 < 0.0f ? 0.0f : (z0 > d->pk_out ? d->pk_out : z0);
+            if (j < C) first_n2[j] = noise * c2;
+            if (j < (W - 1) * C) { /* avir.h:4499-4513 */
+                const float nm1 = noise * c1;
+                r[j + C] = r[j + C] + nm1;
+                D[j - C] = D[j - C] + noise * c2;
+                D[j] = D[j] + nm1;
+                D[j + C] = D[j + C] + noise * c3;
+            } else { /* the last pixel, avir.h:4515-4524 */
+                D[j - C] = D[j - C] + noise * c2;
+                D[j] = D[j] + noise * c1;
+            }
+            if (planar && j >= (W - 1) * C && j % C + 1 < C) /* leak from the next plane's pixel 0 */
+                leak[j % C] = 1;
+            const size_t idx = (size_t)y * dst_pitch + j;
+            if (d->out_type == AVIRB200_U8) ((uint8_t*)dst)[idx] = (uint8_t)r[j];
+            else ((uint16_t*)dst)[idx] = (uint16_t)r[j];
+        }
+        for (int c = 0; c + 1 < C; c++) /* after the whole row: plane c+1 ran after plane c */
+            if (leak[c]) D[(size_t)(W - 1) * C + c] = D[(size_t)(W - 1) * C + c] + first_n2[c + 1];
+    }
+    free(dith);
+}
+
 /* Column pass + epilogue for destination rows [out0, out1).  `mid` holds intermediate rows
  * [mid_row0, mid_row0 + mid_rows) of the image; rows outside are poisoned with NaN, so a
  * band that does not contain everything the outputs depend on is detected (returns
@@ -359,7 +413,15 @@ int avir_port_col_pass(const avirb200_plan_desc* d, const float* mid, int mid_ro
 {
     const int C = d->channels, sh = d->src_h, dw = d->dst_w;
     scratch sc;
-    if (scratch_init(&sc, d) != 0) return AVIRB200_ERR_ALLOC;
+    /* error diffusion (integer output): row-recursive from row 0, whole image only */
+    const int errd = (d->dither == 1 && d->out_type != AVIRB200_F32 && d->out_type != AVIRB200_F64);
+    float* res = NULL;
+    if (errd) {
+        if (out0 != 0 || out1 != d->dst_h) return AVIRB200_ERR_UNSUPPORTED;
+        res = (float*)malloc((size_t)d->dst_h * dw * C * sizeof(float));
+        if (!res) return AVIRB200_ERR_ALLOC;
+    }
+    if (scratch_init(&sc, d) != 0) { free(res); return AVIRB200_ERR_ALLOC; }
     int bad = 0;
     for (int x = 0; x < dw; x++) {
         for (int c = 0; c < C; c++) {
@@ -375,6 +437,10 @@ int avir_port_col_pass(const avirb200_plan_desc* d, const float* mid, int mid_ro
                     else v = lin2srgb(v) * d->out_gamma_mult;
                 }
                 const size_t idx = (size_t)(y - out0) * dst_pitch + (size_t)x * C + c;
+                if (errd) {
+                    res[((size_t)y * dw + x) * C + c] = v;
+                    continue;
+                }
                 if (d->out_type == AVIRB200_F32) {
                     ((float*)dst)[idx] = v;
                     continue;
@@ -392,6 +458,10 @@ int avir_port_col_pass(const avirb200_plan_desc* d, const float* mid, int mid_ro
         }
     }
     scratch_free(&sc);
+    if (errd) {
+        errd_rows(d, res, dst, dst_pitch);
+        free(res);
+    }
     return bad;
 }
 

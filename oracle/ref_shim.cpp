@@ -400,6 +400,13 @@ int run0( const int fpc, const Call& c, const int tin, const int tout,
 			case 0: return run1< avir::fpclass_def< float > >( c, tin, tout );
 			case 1: return run1< avir::fpclass_float4 >( c, tin, tout );
 			case 2: return run1< avir::fpclass_float8_dil >( c, tin, tout );
+			// the same classes composed with upstream's error-diffusion ditherer
+			case 3: return run1< avir::fpclass_def< float, float,
+				avir::CImageResizerDithererErrdINL< float > > >( c, tin, tout );
+			case 4: return run1< avir::fpclass_def< avir::float4, float,
+				avir::CImageResizerDithererErrdINL< avir::float4 > > >( c, tin, tout );
+			case 5: return run1< avir::fpclass_def_dil< float, avir::float8,
+				avir::CImageResizerDithererErrdDIL< float, avir::float8 > > >( c, tin, tout );
 		}
 	}
 

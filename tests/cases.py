@@ -73,6 +73,18 @@ SMALL_CASES = [
     (0, 120, 80, 60, 40, 3, f32, f64, 16, {"gamma": True}),
     (1, 100, 60, 150, 77, 4, f64, u16, 16, {"gamma": True, "alpha": 3}),
     (2, 150, 90, 100, 55, 2, f64, u8, 8, {}),
+    # error-diffusion ditherer (upstream CImageResizerDithererErrdINL / ErrdDIL composed into the
+    # three classes: fpclass codes 3..5), integer output only; row-recursive
+    (3, 120, 80, 60, 40, 4, u8, u8, 8, {}),
+    (4, 120, 80, 60, 40, 4, u8, u8, 8, {}),
+    (5, 120, 80, 60, 40, 4, u8, u8, 8, {}),
+    (3, 100, 60, 150, 77, 3, u8, u8, 6, {}),                 # bit-depth truncation: TrMul != 1
+    (4, 100, 60, 150, 97, 1, u16, u16, 12, {}),              # 3 row groups, one channel
+    (5, 192, 108, 48, 27, 4, u8, u8, 5, {"gamma": True, "alpha": 3}),
+    (3, 64, 48, 33, 70, 2, f32, u16, 16, {"gamma": True}),
+    (4, 40, 30, 1, 65, 4, u8, u8, 8, {}),                    # one-pixel rows
+    (5, 40, 30, 77, 1, 4, u8, u8, 8, {}),                    # one row
+    (3, 120, 80, 60, 40, 4, u8, f32, 8, {}),                 # float output: the ditherer is skipped
     # tiny / ragged
     (1, 1, 1, 5, 7, 4, u8, u8, 8, {}),
     (1, 7, 5, 1, 1, 4, u8, u8, 8, {}),
@@ -164,7 +176,7 @@ def count_mismatch(a, b):
 
 def case_id(case):
     fp, sw, sh, nw, nh, ch, ti, to, rb, kw = case
-    s = "%s-%dx%d-%dx%d-c%d-%s-%s-b%d" % (("def", "f4", "dil")[fp], sw, sh, nw, nh, ch,
+    s = "%s-%dx%d-%dx%d-c%d-%s-%s-b%d" % (("def", "f4", "dil", "defE", "f4E", "dilE")[fp], sw, sh, nw, nh, ch,
                                           np.dtype(ti).name, np.dtype(to).name, rb)
     for k_, v_ in sorted(kw.items()):
         s += "-%s%s" % (k_, v_)
