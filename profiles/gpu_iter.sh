@@ -5,7 +5,7 @@
 tag=${1:-x}; shift
 mkdir -p gpurun_out
 for mb in "$@"; do timeout 120 $mb > gpurun_out/${tag}_$(basename $mb).jsonl 2>&1; cat gpurun_out/${tag}_$(basename $mb).jsonl; done
-(time timeout 1500 python -m pytest tests -x -q -m gpu) 2>&1 | tail -8 | tee gpurun_out/${tag}_pytest.txt
+(time timeout 1500 python -m pytest tests -q -m gpu --maxfail=5 --tb=short) > gpurun_out/${tag}_pytest_full.txt 2>&1; tail -30 gpurun_out/${tag}_pytest_full.txt | cut -c1-300 | tee gpurun_out/${tag}_pytest.txt
 timeout 600 python bench.py --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err
 cat gpurun_out/${tag}_bench.json; tail -3 gpurun_out/${tag}_bench.err
 timeout 600 python profiles/bench_configs.py > gpurun_out/${tag}_configs.jsonl 2> gpurun_out/${tag}_configs.err
