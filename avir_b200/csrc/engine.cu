@@ -325,7 +325,8 @@ int run_row_pass(const avirb200_plan* pl, const void* d_src, size_t src_pitch, f
         // (every pixel of the source must be aligned to its own size: the copies move whole pixels)
         avs::StreamParams sp;
         avs::stream_fill_params(sp, pl->stream_h, d);
-        sp.src_type = d.in_type;
+        sp.src_type = avs::stream_row_source_code(d);
+        sp.srgb_lut = pl->d_lut;
         sp.n_lines = rows;
         sp.out0 = 0;
         sp.out1 = d.dst_w;

@@ -68,11 +68,13 @@ constexpr int kPitchL = 32;     // float2 units: [position][lane] rows of 256 by
 // ADV = input positions per output (FIR decimation R, RESIZE source step D).
 // RESIZE2 = resize over the virtual 2X zero-stuffed line, odd taps skipped (upstream
 // doResize2, avir.h:4114-4328): two outputs per input position.
-template <int KIND_, int SUM_, int NT_, int ADV_>
+// MB = outputs per batch (0: 8, or 16 for RESIZE2; 4 for the long cfg5 filter: its window would
+// not fit the register file otherwise).
+template <int KIND_, int SUM_, int NT_, int ADV_, int MB_ = 0>
 struct StepC {
     static constexpr int KIND = KIND_, SUM = SUM_, NT = NT_, ADV = ADV_;
-    static constexpr int M = (KIND == K_RESIZE2) ? 16 : 8;          // outputs per batch
-    static constexpr int CH = (KIND == K_RESIZE2) ? 8 : 8 * ADV;    // input positions per batch
+    static constexpr int M = (KIND == K_RESIZE2) ? 16 : (MB_ ? MB_ : 8); // outputs per batch
+    static constexpr int CH = (KIND == K_RESIZE2) ? 8 : M * ADV;    // input positions per batch
     static constexpr int NTW = (KIND == K_RESIZE2) ? NT / 2 : NT;   // inputs one output reads
     static constexpr int W = (KIND == K_RESIZE2) ? 20 : NT + (M - 1) * ADV; // window of a batch
 };
@@ -93,7 +95,7 @@ struct ChainC {
     using T1 = S1;
     using T2 = S2;
     static constexpr int SRCT = SRCT_;
-    static constexpr int PIXB = (SRCT == AVIRB200_F32) ? 16 : (SRCT == AVIRB200_U16 ? 8 : 4); // bytes per source pixel
+    static constexpr int PIXB = (SRCT == AVIRB200_F32) ? 16 : (SRCT == AVIRB200_U16 ? 8 : 4); // bytes per source pixel (u8, u8 sRGB: 4)
     static constexpr int NS = (S2::KIND == K_NONE) ? 2 : 3;
     static constexpr int LOOKAHEAD = LA;
     static constexpr bool STEADY_LOOP = (STEADY_ != 0); // straight-line code for the interior rounds of a run
@@ -295,6 +297,12 @@ AVS_FN float epilogue_value(const StreamParams& p, float v, int c) {
 
 // ---- per-warp state of a run -------------------------------------------------------------------------
 
+struct SrcConv {
+    const float* lut;
+    float gm;
+    bool alpha0, alpha1;
+};
+
 template <class C, bool IS_V>
 struct WarpRun {
     float2* ring0;  // source ring
@@ -302,6 +310,7 @@ struct WarpRun {
     float2* ring2;
     float2* stage;  // row pass: transposition buffer of the final batch
     int lane, line0, nlines;
+    SrcConv cv;     // row pass, sRGB source
     int o0;         // source position held by slot 0 of ring 0
     int a[kMaxSteps];   // output index of batch 0 of every step (= origin of the next ring)
     int rd[kMaxSteps];  // read slot (positions) of each step in its input ring
@@ -331,8 +340,16 @@ struct RingOf {
     static AVS_FN int lane_off_b(int lane) {
         return RAW ? (lane >> 1) * C::LINE_B + (lane & 1) * (C::PIXB / 2) : lane * 8;
     }
-    // the lane's channel pair at `p`; integer pixels convert exactly ((float) cast)
-    static AVS_FN float2 load(const unsigned char* p) {
+    // the lane's channel pair at `p`; integer pixels convert exactly ((float) cast); cv: what the
+    // sRGB source needs (table, alpha multiplier, whether each of the lane's two channels is alpha)
+    static AVS_FN float2 load(const unsigned char* p, const SrcConv& cv) {
+        if (SRCT == kSrcU8Srgb) {
+            const unsigned v = *reinterpret_cast<const unsigned short*>(p);
+            const unsigned b0 = v & 255u, b1 = v >> 8;
+            // packScanline with UseSRGBGamma (avir.h:2843-2931): table for colour, (float) b * gm for alpha
+            return make_float2(cv.alpha0 ? __fmul_rn((float)b0, cv.gm) : cv.lut[b0],
+                               cv.alpha1 ? __fmul_rn((float)b1, cv.gm) : cv.lut[b1]);
+        }
         if (SRCT == AVIRB200_U8) {
             const unsigned v = *reinterpret_cast<const unsigned short*>(p);
 #if defined(__CUDACC__)
@@ -435,7 +452,7 @@ AVS_FN void load_group(const StreamParams& p, WarpRun<C, IS_V>& w, int g, int gs
 // Reads the input ring by absolute position, each tap clamped to [lo, hi].
 
 template <class C, bool IS_V, int I, class S>
-AVS_FN float2 slow_one(const StreamStep& sp, const unsigned char* ring, int origin, int j, int lo, int hi) {
+AVS_FN float2 slow_one(const StreamStep& sp, const SrcConv& cv, const unsigned char* ring, int origin, int j, int lo, int hi) {
     using R = RingOf<C, IS_V, I>;
     constexpr int RSP = R::RSP;
     float2 x[S::NTW];
@@ -443,7 +460,7 @@ AVS_FN float2 slow_one(const StreamStep& sp, const unsigned char* ring, int orig
 #pragma unroll
     for (int t = 0; t < S::NTW; ++t) {
         const int pos = imin_(imax_(p0 + t, lo), hi);
-        x[t] = R::load(ring + (size_t)((unsigned)(pos - origin) % (unsigned)RSP) * R::PITCH_B);
+        x[t] = R::load(ring + (size_t)((unsigned)(pos - origin) % (unsigned)RSP) * R::PITCH_B, cv);
     }
     if (S::KIND == K_FIR) return fir_one<S>(x, 0, sp.taps);
     if (S::KIND == K_RESIZE) return resize_one<S>(x, 0, sp.taps, sp.zero_start);
@@ -559,7 +576,7 @@ AVS_FN void preload_window(WarpRun<C, IS_V>& w) {
     window_bases<C, IS_V, I, S>(ring, w.rd[I], base);
     float2* xp = (I == 1) ? w.xp1 : w.xp2;
 #pragma unroll
-    for (int i = 0; i < S::W; ++i) xp[i] = R::load(base[i / S::CH] + (i % S::CH) * R::PITCH_B);
+    for (int i = 0; i < S::W; ++i) xp[i] = R::load(base[i / S::CH] + (i % S::CH) * R::PITCH_B, w.cv);
 }
 
 // PRELOADED: the window is already in w.xp1 / w.xp2 (preload_window).
@@ -584,7 +601,7 @@ AVS_FN void fast_batch(const StreamParams& p, WarpRun<C, IS_V>& w, const unsigne
     if constexpr (S::KIND == K_RESIZE2) {
         float2 x[S::W];
 #pragma unroll
-        for (int i = 0; i < S::W; ++i) x[i] = R::load(base[i / S::CH] + (i % S::CH) * PITCH_B);
+        for (int i = 0; i < S::W; ++i) x[i] = R::load(base[i / S::CH] + (i % S::CH) * PITCH_B, w.cv);
         const int pv = sp.sp_first + j0 - (S::NT / 2 - 1);
         if (pv & 1) {
 #pragma unroll
@@ -593,11 +610,41 @@ AVS_FN void fast_batch(const StreamParams& p, WarpRun<C, IS_V>& w, const unsigne
 #pragma unroll
             for (int m = 0; m < M; ++m) o[m] = resize2_one<S>(x, (m + 1) >> 1, m & 1, sp.taps, sp.zero_start);
         }
+    } else if constexpr (S::KIND == K_RESIZE && S::SUM == AVIRB200_SUM_DIL8 && (S::NT > 32)) {
+        // long filter: the window (NT + (M-1)*ADV positions) does not fit the register file next to
+        // the M x 8 lane sums; walk the taps in their groups of 8 (the order resize_one() adds them
+        // in anyway) and read each group's inputs when it is their turn
+        const StreamTap* t = sp.taps;
+        const StreamTap& one = t[kTapOne];
+        float2 ln[M][8];
+#pragma unroll
+        for (int g = 0; g < S::NT / 8; ++g) {
+            constexpr int GW = (M - 1) * S::ADV + 8;
+            float2 xg[GW];
+#pragma unroll
+            for (int i = 0; i < GW; ++i) {
+                const int pos = g * 8 + i;
+                xg[i] = R::load(base[pos / S::CH] + (pos % S::CH) * PITCH_B, w.cv);
+            }
+#pragma unroll
+            for (int m = 0; m < M; ++m) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const float2 v = f2mul(t[g * 8 + q], xg[m * S::ADV + q]);
+                    ln[m][q] = (g == 0) ? v : f2add(ln[m][q], v, one);
+                }
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < M; ++m) {
+            o[m] = f2hadd8(ln[m], one);
+            if (sp.zero_start) o[m] = f2add(o[m], make_float2(0.0f, 0.0f), one);
+        }
     } else {
         // whole window of the batch in registers
         float2 x[S::W];
 #pragma unroll
-        for (int i = 0; i < S::W; ++i) x[i] = R::load(base[i / S::CH] + (i % S::CH) * PITCH_B);
+        for (int i = 0; i < S::W; ++i) x[i] = R::load(base[i / S::CH] + (i % S::CH) * PITCH_B, w.cv);
 #pragma unroll
         for (int m = 0; m < M; ++m) {
             if (S::KIND == K_FIR) o[m] = fir_one<S>(x, m * S::ADV, sp.taps);
@@ -647,7 +694,7 @@ AVS_FN void run_batch(const StreamParams& p, WarpRun<C, IS_V>& w) {
             for (int m = 0; m < M; ++m) {
                 const int j = j0 + m;
                 float2 v = make_float2(0.0f, 0.0f);
-                if (j >= 0 && j < sp.out_len) v = slow_one<C, IS_V, I, S>(sp, ring, origin, j, lo, hi);
+                if (j >= 0 && j < sp.out_len) v = slow_one<C, IS_V, I, S>(sp, w.cv, ring, origin, j, lo, hi);
                 // (a register array indexed by the loop counter: keep the loop rolled, select by value)
 #pragma unroll
                 for (int mm = 0; mm < M; ++mm)
@@ -784,9 +831,14 @@ AVS_FN void run_warp(const StreamParams& p, WarpRun<C, IS_V>& w, int strip, int 
 // Units = rounds of B final outputs, strip-major; every warp takes an equal contiguous share.
 
 template <class C, bool IS_V, int EPI>
-AVS_FN void stream_warp_main(const StreamParams& p, long long gw, long long nwarps, int lane, float2* sm) {
+AVS_FN void stream_warp_main(const StreamParams& p, long long gw, long long nwarps, int lane, float2* sm,
+                             const float* lut) {
     WarpRun<C, IS_V> w;
     w.lane = lane;
+    w.cv.lut = lut; // (sRGB source only) the linearisation table, in shared memory on the device
+    w.cv.gm = p.in_gamma_mult;
+    w.cv.alpha0 = (p.alpha_index == (lane & 1) * 2);
+    w.cv.alpha1 = (p.alpha_index == (lane & 1) * 2 + 1);
     w.ring0 = sm;
     w.ring1 = w.ring0 + (IS_V ? (size_t)C::rsp0 * kPitchL : (size_t)C::SRC_RING_F2);
     w.ring2 = w.ring1 + (size_t)C::rsp1 * kPitchL;
@@ -812,10 +864,16 @@ template <class C, bool IS_V, int EPI>
 __global__ void __launch_bounds__((IS_V ? C::NWARPS_V : C::NWARPS_H) * 32, 1)
 stream_pass_kernel(const __grid_constant__ StreamParams p) {
     constexpr int NW = IS_V ? C::NWARPS_V : C::NWARPS_H;
+    constexpr bool SRGB = !IS_V && (C::SRCT == kSrcU8Srgb);
+    __shared__ float slut[SRGB ? 256 : 1];
+    if constexpr (SRGB) {
+        for (int i = threadIdx.x; i < 256; i += NW * 32) slut[i] = __ldg(p.srgb_lut + i);
+        __syncthreads();
+    }
     extern __shared__ __align__(16) unsigned char stream_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float2* sm = reinterpret_cast<float2*>(stream_smem) + (size_t)warp * (IS_V ? C::WARP_F2_V : C::WARP_F2_H);
-    stream_warp_main<C, IS_V, EPI>(p, (long long)blockIdx.x * NW + warp, (long long)gridDim.x * NW, lane, sm);
+    stream_warp_main<C, IS_V, EPI>(p, (long long)blockIdx.x * NW + warp, (long long)gridDim.x * NW, lane, sm, slut);
 }
 #endif
 
@@ -855,6 +913,10 @@ using ChainInl3 = ChainV<StepC<K_FIR, AVIRB200_SUM_INL, 7, 1>, StepC<K_RESIZE, A
 template <int VAR, bool IS_V, int SRCT = AVIRB200_F32>
 using ChainInl3D = ChainV<StepC<K_FIR, AVIRB200_SUM_INL, 15, 2>, StepC<K_RESIZE, AVIRB200_SUM_INL, 18, 2>,
                           StepC<K_FIR, AVIRB200_SUM_INL, 7, 1>, 1, 1, 1, false, VAR, IS_V, SRCT>;
+// cfg5, float8_dil mirror (k = 4, build mode 1): RESIZE(56 taps, source step 4; 4-output batches) -> FIR(8)
+template <int VAR, bool IS_V, int SRCT = AVIRB200_F32>
+using ChainDil56 = ChainV<StepC<K_RESIZE, AVIRB200_SUM_DIL8, 56, 4, 4>, StepC<K_FIR, AVIRB200_SUM_DIL8, 8, 1>, NoStep,
+                          1, 1, 1, false, VAR, IS_V, SRCT>;
 // cfg2 (k = 0.5): FIR(7) -> RESIZE(24) over the virtual 2X line; 32 final outputs per round
 template <int VAR, bool IS_V, int SRCT = AVIRB200_F32>
 using ChainUp2 = ChainV<StepC<K_FIR, AVIRB200_SUM_INL, 7, 1>, StepC<K_RESIZE2, AVIRB200_SUM_INL, 24, 1>, NoStep,
@@ -889,6 +951,10 @@ inline bool stream_dispatch(int id, bool is_v, int variant, int src_type, F&& f)
         f(ChainTag<NAME<kStreamDefaultVariantH, false, AVIRB200_U16> >(), PassTag<false>()); \
         return true;                                                                      \
     }                                                                                     \
+    if (!is_v && src_type == kSrcU8Srgb) {                                                \
+        f(ChainTag<NAME<kStreamDefaultVariantH, false, kSrcU8Srgb> >(), PassTag<false>()); \
+        return true;                                                                      \
+    }                                                                                     \
     switch (variant) {                                                                    \
         AVS_V(NAME, 0) AVS_V(NAME, 1) AVS_V(NAME, 2) AVS_V(NAME, 3)                       \
     default: return false;                                                                \
@@ -899,6 +965,7 @@ inline bool stream_dispatch(int id, bool is_v, int variant, int src_type, F&& f)
     case kChainInl24: AVS_VARIANTS(ChainInl24)
     case kChainInl3: AVS_VARIANTS(ChainInl3)
     case kChainInl3D: AVS_VARIANTS(ChainInl3D)
+    case kChainDil56: AVS_VARIANTS(ChainDil56)
     case kChainUp2: AVS_VARIANTS(ChainUp2)
     default: return false;
     }

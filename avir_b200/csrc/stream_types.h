@@ -13,6 +13,9 @@
 namespace avs {
 
 constexpr int kMaxSteps = 3;
+// Source code of the row pass beyond the plain element types: u8 pixels linearised on the way
+// in (sRGB table for the colour channels, (float) b * InGammaMult for alpha; avir.h:2843-2931).
+constexpr int kSrcU8Srgb = 4;
 enum { K_FIR = 0, K_RESIZE = 1, K_RESIZE2 = 2, K_NONE = 3 };
 
 // Run-time description of one step (kernel parameters: taps are constant-bank operands).
@@ -37,7 +40,9 @@ struct StreamParams {
     int src_len;          // positions of the source line
     int out0, out1;       // final outputs [out0, out1) to produce
     const void* src;      // 4 interleaved channels; fp32, or (row pass) the caller's u8 / u16 pixels
-    int src_type;         // AVIRB200_F32 / _U8 / _U16: selects the kernel instantiation (row pass)
+    int src_type;         // AVIRB200_F32 / _U8 / _U16 / kSrcU8Srgb: selects the kernel instantiation (row pass)
+    const float* srgb_lut; // kSrcU8Srgb: upstream's 256-entry linearisation table (device memory)
+    float in_gamma_mult;   // kSrcU8Srgb: multiplier of the alpha channel
     long long src_pitch;  // elements between rows
     int src_row_base;     // column pass: global row held by source row 0 (shards)
     void* dst;
@@ -55,6 +60,7 @@ enum StreamChainId {
     kChainInl24, // RESIZE(24, D2) -> FIR7                 k = 2, build mode 1, interleaved classes
     kChainInl3,  // FIR7 -> RESIZE(18, D2) -> FIR7         cfg3, float4 mirror (k = 2, build mode 0)
     kChainInl3D, // FIR15/2 -> RESIZE(18, D2) -> FIR7      cfg4 (k = 4, build mode 0)
+    kChainDil56, // RESIZE(56, D4) -> FIR8                 cfg5, float8_dil mirror (k = 4, build mode 1)
     kChainUp2,   // FIR7 -> RESIZE2(24)                    cfg2 (k = 0.5, build mode 1)
     kChainCount
 };
@@ -76,6 +82,7 @@ inline const StepSpec* chain_spec(int id, int* nsteps) {
     static const StepSpec inl24[] = {{K_RESIZE, AVIRB200_SUM_INL, 24, 2}, {K_FIR, AVIRB200_SUM_INL, 7, 1}};
     static const StepSpec inl3[] = {{K_FIR, AVIRB200_SUM_INL, 7, 1}, {K_RESIZE, AVIRB200_SUM_INL, 18, 2},
                                     {K_FIR, AVIRB200_SUM_INL, 7, 1}};
+    static const StepSpec dil56[] = {{K_RESIZE, AVIRB200_SUM_DIL8, 56, 4}, {K_FIR, AVIRB200_SUM_DIL8, 8, 1}};
     static const StepSpec inl3d[] = {{K_FIR, AVIRB200_SUM_INL, 15, 2}, {K_RESIZE, AVIRB200_SUM_INL, 18, 2},
                                      {K_FIR, AVIRB200_SUM_INL, 7, 1}};
     static const StepSpec up2[] = {{K_FIR, AVIRB200_SUM_INL, 7, 1}, {K_RESIZE2, AVIRB200_SUM_INL, 24, 1}};
@@ -84,6 +91,7 @@ inline const StepSpec* chain_spec(int id, int* nsteps) {
     case kChainInl24: *nsteps = 2; return inl24;
     case kChainInl3: *nsteps = 3; return inl3;
     case kChainInl3D: *nsteps = 3; return inl3d;
+    case kChainDil56: *nsteps = 2; return dil56;
     case kChainUp2: *nsteps = 2; return up2;
     default: *nsteps = 0; return nullptr;
     }
@@ -168,10 +176,14 @@ inline bool stream_plan_axis(const avirb200_axis_desc& ad, int sum_mode, int cha
 
 // The row pass streams the caller's pixels into shared memory as they are (cp.async); integer
 // pixels are cast in the compute lanes' own reads.  Sources that need the sRGB linearisation
-// on the way in stay on the tile kernel (it converts every sample once, in double).
+// on the way in stay on the tile kernel (it converts every sample once, in double) -- except
+// u8, whose linearisation is a 256-entry table.
 inline bool stream_row_source_ok(const avirb200_plan_desc& d) {
-    return (d.in_type == AVIRB200_F32 || d.in_type == AVIRB200_U8 || d.in_type == AVIRB200_U16) &&
-           !(d.use_gamma & 1);
+    if (d.use_gamma & 1) return d.in_type == AVIRB200_U8;
+    return d.in_type == AVIRB200_F32 || d.in_type == AVIRB200_U8 || d.in_type == AVIRB200_U16;
+}
+inline int stream_row_source_code(const avirb200_plan_desc& d) {
+    return (d.use_gamma & 1) ? kSrcU8Srgb : d.in_type;
 }
 
 // Kernel parameters of one pass (the caller fills the image pointers / bases).
@@ -180,6 +192,7 @@ inline void stream_fill_params(StreamParams& p, const StreamAxisPlan& ap, const 
     for (int i = 0; i < ap.nsteps; ++i) p.s[i] = ap.s[i];
     p.src_len = ap.src_len;
     p.src_type = AVIRB200_F32;
+    p.in_gamma_mult = d.in_gamma_mult;
     p.gamma_out = (d.use_gamma & 2) ? 1 : 0;
     p.alpha_index = d.alpha_index;
     p.out_gamma_mult = d.out_gamma_mult;

@@ -114,7 +114,7 @@ def pick_threads(o, src, fp, cores):
     first-touches its ~400 MB of scratch from all threads at once); use the thread count
     that is actually fastest on this host."""
     best, best_t = cores, None
-    cand = sorted({c for c in (cores, cores // 2, cores // 4, 32, 16, 8) if 1 <= c <= cores}, reverse=True)
+    cand = sorted({c for c in (cores, cores // 2, cores // 4, 32, 16, 8, 4) if 1 <= c <= cores}, reverse=True)
     o.ref_resize(src, DST_W, DST_H, np.float32, fpclass=fp, resbits=16, nthreads=cand[0])
     for c in cand:
         t0 = time.perf_counter()

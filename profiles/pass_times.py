@@ -24,6 +24,8 @@ CFG = {  # name: (fpclass, sw, sh, nw, nh, tin, tout, resbits, kwargs)
     "cfg2": (1, 1920, 1080, 3840, 2160, np.uint8, np.uint8, 8, {}),
     "cfg4": (1, 16384, 16384, 4096, 4096, np.uint16, np.uint16, 16, {}),
     "cfg5": (2, 7680, 4320, 1920, 1080, np.uint8, np.uint8, 8, {"gamma": True, "alpha": 3}),
+    "u8k": (1, 7680, 4320, 3840, 2160, np.uint8, np.uint8, 8, {}),
+    "u8kdil": (2, 7680, 4320, 3840, 2160, np.uint8, np.uint8, 8, {}),
 }
 TT = {np.uint8: torch.uint8, np.uint16: torch.uint16, np.float32: torch.float32}
 

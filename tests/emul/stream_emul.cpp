@@ -39,7 +39,7 @@ void emul_pass(const StreamParams& p, int nwarps) {
         for (int lane = 0; lane < 32; ++lane) {
             th.emplace_back([&, lane] {
                 g_bar = &bar;
-                stream_warp_main<C, IS_V, EPI>(p, gw, nwarps, lane, sm.data());
+                stream_warp_main<C, IS_V, EPI>(p, gw, nwarps, lane, sm.data(), p.srgb_lut);
             });
         }
         for (auto& t : th) t.join();
@@ -75,8 +75,9 @@ int stream_emul_applicable(const avirb200_plan_desc* d) {
 
 // Row pass with `warps_h` emulated warps, then the column pass in `bands` destination bands
 // (as the sharded schedule runs it) with `warps_v` warps each.
+// lut: the 256-entry u8 sRGB linearisation table (read for sRGB sources only).
 int stream_emul_resize(const avirb200_plan_desc* d, const void* src, size_t src_pitch, void* dst,
-                       size_t dst_pitch, int warps_h, int warps_v, int bands, int variant) {
+                       size_t dst_pitch, int warps_h, int warps_v, int bands, int variant, const float* lut) {
     StreamAxisPlan h, v;
     if (!stream_row_source_ok(*d) || !stream_plan_axis(d->h, d->sum_mode, d->channels, h, true) ||
         !stream_plan_axis(d->v, d->sum_mode, d->channels, v, true))
@@ -88,7 +89,8 @@ int stream_emul_resize(const avirb200_plan_desc* d, const void* src, size_t src_
     p.out0 = 0;
     p.out1 = d->dst_w;
     p.src = src;
-    p.src_type = d->in_type;
+    p.src_type = stream_row_source_code(*d);
+    p.srgb_lut = lut;
     p.src_pitch = (long long)src_pitch;
     p.dst = mid.data();
     p.dst_pitch = (long long)d->dst_w * 4;

@@ -22,7 +22,7 @@ def emul():
     from avir_b200 import build as b
     lib = C.CDLL(b.build_emul())
     lib.stream_emul_resize.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t,
-                                       C.c_int, C.c_int, C.c_int, C.c_int]
+                                       C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
     lib.stream_emul_resize.restype = C.c_int
     lib.stream_emul_applicable.argtypes = [C.c_void_p]
     lib.stream_emul_applicable.restype = C.c_int
@@ -70,6 +70,14 @@ EMUL_CASES = [
     ((1, 200, 140, 50, 35, 4, f32, f32, 16, {"buildmode": 0}), 2, 5, 3),
     ((0, 40, 36, 10, 9, 4, u8, u8, 16, {"buildmode": 0}), 2, 2, 2),
     ((1, 1280, 80, 320, 20, 4, u16, u16, 16, {"buildmode": 0}), 9, 2, 5),
+    # cfg5 chain (k = 4, build mode 1, float8_dil): RESIZE(56, step 4) in 4-output batches -> FIR(8);
+    # u8 source linearised through the sRGB table in the lanes' reads, alpha exempt
+    ((2, 384, 216, 96, 54, 4, u8, u8, 8, {"gamma": True, "alpha": 3, "buildmode": 1}), 3, 2, 1),
+    ((2, 200, 140, 50, 35, 4, u8, u8, 8, {"gamma": True, "alpha": 0, "buildmode": 1}), 4, 3, 2),
+    ((2, 200, 140, 50, 35, 4, f32, f32, 16, {"buildmode": 1}), 2, 5, 3),
+    ((2, 40, 36, 10, 9, 4, u8, u16, 16, {"gamma": True, "buildmode": 1}), 2, 2, 2),
+    ((2, 1280, 80, 320, 20, 4, u16, u16, 16, {"buildmode": 1}), 9, 2, 5),
+    ((2, 192, 108, 96, 54, 4, u8, u8, 8, {"gamma": True, "alpha": 3, "buildmode": 1}), 3, 2, 1),  # k = 2 + sRGB source
 ]
 
 
@@ -90,8 +98,10 @@ def test_stream_kernel_emulation_matches_port(emul, ec, variant):
     try:
         assert emul.stream_emul_applicable(dp) == 1, "chain not on the streaming kernel: %r" % (modes,)
         got = np.zeros((nh, nw, ch), to)
+        lut = np.zeros(256, np.float32)
+        cs.port().avir_port_srgb_lut(lut.ctypes.data)
         assert emul.stream_emul_resize(dp, src.ctypes.data, sw * ch, got.ctypes.data, nw * ch, wh, wv, bands,
-                                       variant) == 0
+                                       variant, lut.ctypes.data) == 0
     finally:
         rs.free_descriptor(h)
     want, _ = cs.port_output(case, src)
@@ -99,7 +109,7 @@ def test_stream_kernel_emulation_matches_port(emul, ec, variant):
 
 
 def test_converted_sources_stay_on_the_tile_kernel(emul):
-    # input gamma needs a conversion between global and shared memory: not a cp.async stream
+    # float / u16 input gamma is a double-precision polynomial per sample: not done in the lanes' reads
     case = (2, 100, 70, 50, 35, 4, f32, u16, 16, {"buildmode": 1, "gamma": True, "alpha": 3})
     rs, v = cs.resizer_and_vars(case)
     h, dp, modes = rs.descriptor((70, 100, 4), f32, 50, 35, u16, 0.0, v)
