@@ -19,7 +19,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 import cases as cs  # noqa: E402
 import oracle_ref as o  # noqa: E402
 
-u8, u16, f32 = np.uint8, np.uint16, np.float32
+u8, u16, f32, f64 = np.uint8, np.uint16, np.float32, np.float64
 
 GOLDEN_CASES = [
     (1, 60, 34, 120, 68, 4, u8, u8, 8, {"buildmode": 1}),          # cfg2 chain
@@ -34,6 +34,12 @@ GOLDEN_CASES = [
     (2, 50, 30, 33, 21, 2, u16, u16, 16, {"gamma": True}),
     (1, 40, 30, 20, 15, 4, u8, u8, 8, {"ox": 0.37, "oy": -0.21}),
     (0, 90, 60, 11, 7, 1, f32, f32, 16, {}),
+    # error-diffusion classes (fpclass codes 3..5), double image buffers
+    (3, 60, 40, 45, 50, 4, u8, u8, 8, {}),
+    (5, 60, 40, 45, 50, 4, u8, u8, 6, {"gamma": True, "alpha": 3}),   # planar class: cross-plane quirk
+    (4, 60, 40, 30, 70, 3, u16, u16, 12, {}),
+    (1, 60, 40, 30, 20, 4, f64, f64, 16, {}),
+    (0, 60, 40, 45, 50, 3, f64, u16, 16, {"gamma": True}),
 ]
 
 LANCIR_CASES = [
