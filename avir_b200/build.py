@@ -95,21 +95,32 @@ def _build_cuda(force=False, verbose=False):
     linked into libavirb200.so."""
     from concurrent.futures import ThreadPoolExecutor
     target = os.path.join(PKG, "libavirb200.so")
-    cus = [os.path.join(CSRC, "engine.cu"), os.path.join(CSRC, "lancir.cu"),
-           os.path.join(CSRC, "stream_pass.cu")]
-    objs = [os.path.join(PKG, os.path.basename(cu)[:-3] + ".o") for cu in cus]
-    todo = [(cu, ob) for cu, ob in zip(cus, objs) if force or _obj_stale(ob, cu)]
+    # (source, object, extra flags); stream_chain.cu holds the kernels of ONE streaming chain and is
+    # compiled once per chain id (stream_types.h: StreamChainId 1..6), in parallel
+    # Chain 5 (the 56-tap cfg5 chain) is left out unless AVIRB200_BUILD_ALL_CHAINS=1: it is not
+    # selected at run time (slower than the tile kernel) and takes ~18 minutes to compile.
+    all_chains = os.environ.get("AVIRB200_BUILD_ALL_CHAINS") == "1"
+    chains = [k for k in range(1, 7) if all_chains or k != 5]
+    jobs = [(os.path.join(CSRC, n + ".cu"), os.path.join(PKG, n + ".o"), [])
+            for n in ("engine", "lancir")]
+    jobs.append((os.path.join(CSRC, "stream_pass.cu"),
+                 os.path.join(PKG, "stream_pass_all.o" if all_chains else "stream_pass.o"),
+                 ["-DAVS_WITH_DIL56"] if all_chains else []))
+    jobs += [(os.path.join(CSRC, "stream_chain.cu"), os.path.join(PKG, "stream_chain_%d.o" % k),
+              ["-DAVS_CHAIN_ID=%d" % k]) for k in chains]
+    objs = [j[1] for j in jobs]
+    todo = [j for j in jobs if force or _obj_stale(j[1], j[0])]
 
     def compile_one(job):
-        cu, obj = job
+        cu, obj, extra = job
         tmp = "%s.%d.tmp" % (obj, os.getpid())  # atomic: parallel test workers may build at once
-        out = _run([_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) +
+        out = _run([_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) +
                    ["-MD", "-MF", tmp + ".d", "-MT", obj, "-c", cu, "-o", tmp])
         os.replace(tmp + ".d", obj + ".d")
         os.replace(tmp, obj)
         return out
 
-    with ThreadPoolExecutor(max_workers=4) as ex:
+    with ThreadPoolExecutor(max_workers=max(2, min(8, os.cpu_count() or 4))) as ex:
         for out in ex.map(compile_one, todo):
             if verbose:
                 print(out)

@@ -335,7 +335,7 @@ int run_row_pass(const avirb200_plan* pl, const void* d_src, size_t src_pitch, f
         sp.dst = d_mid;
         sp.dst_pitch = (long long)d.dst_w * 4;
         sp.dst_type = AVIRB200_F32;
-        const int r = avs::stream_launch(pl->stream_h.chain, false, false, sp, st);
+        const int r = avs::stream_launch(pl->stream_h.chain, false, 0, sp, st);
         if (r == -1) return fail(AVIRB200_ERR_CUDA, "streaming row pass launch failed");
         if (r == 0) { ++*launches; return 0; }
     }
@@ -386,8 +386,7 @@ int run_col_pass(const avirb200_plan* pl, const float* d_mid, int mid_row_base, 
             sp.dst_pitch = (long long)dst_pitch;
             sp.dst_type = d.out_type;
             sp.dst_row_base = out0;
-            const bool plain = (d.out_type == AVIRB200_F32) && !(d.use_gamma & 2);
-            const int r = avs::stream_launch(pl->stream_v.chain, true, plain, sp, st);
+            const int r = avs::stream_launch(pl->stream_v.chain, true, avs::stream_epilogue_code(d), sp, st);
             if (r == -1) return fail(AVIRB200_ERR_CUDA, "streaming column pass launch failed");
             if (r == 0) { ++*launches; return 0; }
         }
@@ -787,7 +786,7 @@ int avirb200_plan_create(const avirb200_plan_desc* desc, avirb200_plan** out) {
     pl->cfg_v = choose_generic_config(pl->v.hostdev, desc->channels, 0, desc->dst_h);
     // (pl->desc, not *desc: the kernels' element types, see io_in_type / io_out_type)
     fast_plan_init(pl->fast, pl->h.hostdev, pl->v.hostdev, pl->desc);
-    const char* up2e = getenv("AVIRB200_STREAM_UP2"); // tuning switch, see stream_plan_axis()
+    const char* up2e = getenv("AVIRB200_STREAM_ALL"); // tuning switch, see stream_plan_axis()
     const bool up2 = up2e && up2e[0] == '1';
     if (avs::stream_row_source_ok(pl->desc))
         avs::stream_plan_axis(desc->h, desc->sum_mode, desc->channels, pl->stream_h, up2);

@@ -282,16 +282,19 @@ AVS_FN float2 resize2_one(const X& x, const int off, const int fo, const StreamT
 
 // ---- output stage ---------------------------------------------------------------------------------------
 
+// integer destinations: round (the class's own round()), clamp (avir.h:4392-4419)
+AVS_FN float epilogue_round(const StreamParams& p, float v) {
+    if (p.tr_mul == 1.0f) v = round_out(v, p.round_mode);
+    else v = __fmul_rn(round_out(__fmul_rn(v, p.tr_mul_inv), p.round_mode), p.tr_mul);
+    return v < 0.0f ? 0.0f : (v > p.pk_out ? p.pk_out : v);
+}
+
 AVS_FN float epilogue_value(const StreamParams& p, float v, int c) {
     if (p.gamma_out) {
         if (c == p.alpha_index) v = __fmul_rn(v, p.out_gamma_mult);
         else v = __fmul_rn(lin2srgb(v), p.out_gamma_mult);
     }
-    if (p.dst_type != AVIRB200_F32) {
-        if (p.tr_mul == 1.0f) v = round_out(v, p.round_mode);
-        else v = __fmul_rn(round_out(__fmul_rn(v, p.tr_mul_inv), p.round_mode), p.tr_mul);
-        v = v < 0.0f ? 0.0f : (v > p.pk_out ? p.pk_out : v);
-    }
+    if (p.dst_type != AVIRB200_F32) v = epilogue_round(p, v);
     return v;
 }
 
@@ -474,8 +477,17 @@ AVS_FN float2 slow_one(const StreamStep& sp, const SrcConv& cv, const unsigned c
 // Column pass: lane = (pixel column, channel pair); a batch is M destination rows.
 template <int EPI>
 AVS_FN void store_v(const StreamParams& p, unsigned char* g, float2 v, int c0) {
-    if (EPI == 1) {
+    if (EPI == 1) { // float destination, no output gamma
         *reinterpret_cast<float2*>(g) = v;
+        return;
+    }
+    if (EPI == 2) { // integer destination, no output gamma (no double-precision code in the kernel)
+        v.x = epilogue_round(p, v.x);
+        v.y = epilogue_round(p, v.y);
+        if (p.dst_type == AVIRB200_U8)
+            *reinterpret_cast<uchar2*>(g) = make_uchar2((unsigned char)v.x, (unsigned char)v.y);
+        else
+            *reinterpret_cast<ushort2*>(g) = make_ushort2((unsigned short)v.x, (unsigned short)v.y);
         return;
     }
     v.x = epilogue_value(p, v.x, c0);
@@ -880,14 +892,7 @@ stream_pass_kernel(const __grid_constant__ StreamParams p) {
 // ---- the chains ------------------------------------------------------------------------------------------
 // (kind, summation, taps, advance) per step; final batches per round; source look-ahead in rounds.
 
-// Scheduling variants (same arithmetic): bit 0 = later steps' windows read ahead at the top of
-// a round (one more round of delay and ring; the source look-ahead shrinks by a round to stay
-// within shared memory), bit 1 = no separate straight-line loop for the interior rounds.
-// Measured on cfg3 with the packed arithmetic (profiles/r01_variant_sweeps_packed.jsonl): both
-// passes are fastest with the straight-line loop and without read-ahead (variant 0); with the
-// scalar arithmetic the column pass preferred variant 3 (profiles/r01_variant_sweeps.jsonl).
-constexpr int kStreamVariants = 4;
-constexpr int kStreamDefaultVariantH = 0, kStreamDefaultVariantV = 0;
+// (scheduling variants and their defaults: stream_types.h)
 
 // Source look-ahead in rounds (LAH row pass, LAV column pass) is what shared memory affords at
 // 8 warps per SM: the row pass carries the staging rows, three-step chains a second
@@ -932,11 +937,13 @@ struct PassTag {
     static constexpr bool is_v = V;
 };
 
-// Calls f(ChainTag<Chain>(), PassTag<is_v>()) with the description of chain `id` in scheduling
+// Calls f(ChainTag<Chain>(), PassTag<is_v>()) with the description of chain ID in scheduling
 // variant `variant` for the row pass (is_v false) or the column pass.  Integer sources (row
 // pass only) run the default row-pass variant whatever `variant` says: one instantiation each.
-template <class F>
-inline bool stream_dispatch(int id, bool is_v, int variant, int src_type, F&& f) {
+// One chain per call so that every chain's kernels can live in their own translation unit
+// (stream_chain.cu is compiled once per chain, in parallel).
+template <int ID, class F>
+inline bool stream_dispatch_chain(bool is_v, int variant, int src_type, F&& f) {
 #define AVS_V(NAME, N)                                                                    \
     case N:                                                                               \
         if (is_v) f(ChainTag<NAME<N, true> >(), PassTag<true>());                         \
@@ -960,17 +967,29 @@ inline bool stream_dispatch(int id, bool is_v, int variant, int src_type, F&& f)
     default: return false;                                                                \
     }
     if (variant < 0 || variant >= kStreamVariants) return false;
-    switch (id) {
-    case kChainDil24: AVS_VARIANTS(ChainDil24)
-    case kChainInl24: AVS_VARIANTS(ChainInl24)
-    case kChainInl3: AVS_VARIANTS(ChainInl3)
-    case kChainInl3D: AVS_VARIANTS(ChainInl3D)
-    case kChainDil56: AVS_VARIANTS(ChainDil56)
-    case kChainUp2: AVS_VARIANTS(ChainUp2)
-    default: return false;
-    }
+    if constexpr (ID == kChainDil24) { AVS_VARIANTS(ChainDil24) }
+    else if constexpr (ID == kChainInl24) { AVS_VARIANTS(ChainInl24) }
+    else if constexpr (ID == kChainInl3) { AVS_VARIANTS(ChainInl3) }
+    else if constexpr (ID == kChainInl3D) { AVS_VARIANTS(ChainInl3D) }
+    else if constexpr (ID == kChainDil56) { AVS_VARIANTS(ChainDil56) }
+    else if constexpr (ID == kChainUp2) { AVS_VARIANTS(ChainUp2) }
+    else return false;
 #undef AVS_VARIANTS
 #undef AVS_V
+}
+
+// The same for a run-time chain id (the host emulation: everything in one translation unit).
+template <class F>
+inline bool stream_dispatch(int id, bool is_v, int variant, int src_type, F&& f) {
+    switch (id) {
+    case kChainDil24: return stream_dispatch_chain<kChainDil24>(is_v, variant, src_type, f);
+    case kChainInl24: return stream_dispatch_chain<kChainInl24>(is_v, variant, src_type, f);
+    case kChainInl3: return stream_dispatch_chain<kChainInl3>(is_v, variant, src_type, f);
+    case kChainInl3D: return stream_dispatch_chain<kChainInl3D>(is_v, variant, src_type, f);
+    case kChainDil56: return stream_dispatch_chain<kChainDil56>(is_v, variant, src_type, f);
+    case kChainUp2: return stream_dispatch_chain<kChainUp2>(is_v, variant, src_type, f);
+    default: return false;
+    }
 }
 
 } // namespace avs

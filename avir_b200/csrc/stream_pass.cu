@@ -1,45 +1,10 @@
-// stream_pass.cu -- instantiations and launch of the warp-streaming pass kernel
-// (stream_kernel.cuh); kept in its own translation unit so that the chain kernels compile
-// in parallel with engine.cu.
-#include <cuda_runtime.h>
+// stream_pass.cu -- launch entry of the warp-streaming pass kernel: picks the scheduling variant
+// and routes to the chain's own translation unit (stream_chain.cu, compiled once per chain).
 #include <stdlib.h>
 
-#include "stream_kernel.cuh"
 #include "stream_launch.h"
 
 namespace avs {
-
-namespace {
-
-int sm_count() {
-    static const int sms = [] {
-        int d = 0, n = 0;
-        cudaGetDevice(&d);
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d);
-        return n > 0 ? n : 1;
-    }();
-    return sms;
-}
-
-template <class C, bool IS_V, int EPI>
-int launch_one(const StreamParams& p, cudaStream_t st) {
-    constexpr int NW = IS_V ? C::NWARPS_V : C::NWARPS_H;
-    constexpr size_t smem = (size_t)NW * (IS_V ? C::WARP_F2_V : C::WARP_F2_H) * sizeof(float2);
-    static_assert(smem <= 227 * 1024, "per-warp rings do not fit the shared memory of an SM");
-    auto kern = stream_pass_kernel<C, IS_V, EPI>;
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-        return -1;
-    // one persistent block per SM; fewer when the pass has fewer rounds than warps
-    const long long rps = (long long)(p.out1 - 1) / C::B - p.out0 / C::B + 1;
-    const long long units = rps * ((p.n_lines + kLines - 1) / kLines);
-    long long blocks = (units + NW - 1) / NW;
-    if (blocks > sm_count()) blocks = sm_count();
-    if (blocks < 1) return 0;
-    kern<<<(int)blocks, NW * 32, smem, st>>>(p);
-    return cudaGetLastError() == cudaSuccess ? 0 : -1;
-}
-
-} // namespace
 
 // Scheduling variant of a pass: AVIRB200_STREAM_VARIANT_H / _V (or AVIRB200_STREAM_VARIANT for
 // both) override the defaults; tuning and test switch, every variant computes the same bits.
@@ -60,15 +25,23 @@ int stream_variant(bool is_v) {
     return v[is_v ? 1 : 0];
 }
 
-int stream_launch(int chain, bool is_v, bool plain_f32, const StreamParams& p, void* stream) {
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    int rc = -2;
-    const bool known = stream_dispatch(chain, is_v, stream_variant(is_v), p.src_type, [&](auto tag, auto pass) {
-        using C = typename decltype(tag)::type;
-        if constexpr (!decltype(pass)::is_v) rc = launch_one<C, false, 0>(p, st);
-        else rc = plain_f32 ? launch_one<C, true, 1>(p, st) : launch_one<C, true, 0>(p, st);
-    });
-    return known ? rc : -2;
+int stream_launch(int chain, bool is_v, int epi, const StreamParams& p, void* stream) {
+    const int var = stream_variant(is_v);
+    switch (chain) {
+    case kChainDil24: return stream_launch_chain<kChainDil24>(is_v, var, epi, p, stream);
+    case kChainInl24: return stream_launch_chain<kChainInl24>(is_v, var, epi, p, stream);
+    case kChainInl3: return stream_launch_chain<kChainInl3>(is_v, var, epi, p, stream);
+    case kChainInl3D: return stream_launch_chain<kChainInl3D>(is_v, var, epi, p, stream);
+#ifdef AVS_WITH_DIL56
+    // Not in the default build: the chain loses to the tile kernel on B200 (stream_types.h) and its
+    // kernels take ~18 minutes to compile; AVIRB200_BUILD_ALL_CHAINS=1 python avir_b200/build.py
+    // builds them (then selectable with AVIRB200_STREAM_ALL=1).  Without them the engine falls
+    // back to the tile kernel (return -2 = no such instantiation).
+    case kChainDil56: return stream_launch_chain<kChainDil56>(is_v, var, epi, p, stream);
+#endif
+    case kChainUp2: return stream_launch_chain<kChainUp2>(is_v, var, epi, p, stream);
+    default: return -2;
+    }
 }
 
 } // namespace avs

@@ -65,6 +65,15 @@ enum StreamChainId {
     kChainCount
 };
 
+// Scheduling variants (same arithmetic): bit 0 = later steps' windows read ahead at the top of
+// a round (one more round of delay and ring; the source look-ahead shrinks by a round to stay
+// within shared memory), bit 1 = no separate straight-line loop for the interior rounds.
+// Measured on cfg3 with the packed arithmetic (profiles/r01_variant_sweeps_packed.jsonl): both
+// passes are fastest with the straight-line loop and without read-ahead (variant 0); with the
+// scalar arithmetic the column pass preferred variant 3 (profiles/r01_variant_sweeps.jsonl).
+constexpr int kStreamVariants = 4;
+constexpr int kStreamDefaultVariantH = 0, kStreamDefaultVariantV = 0;
+
 struct StreamAxisPlan {
     int chain = kChainNone;
     int nsteps = 0;
@@ -146,14 +155,16 @@ inline bool stream_match_step(const avirb200_step_desc& d, const StepSpec& sp, S
 // Decides whether the axis runs on the streaming kernel; on success `out` holds everything
 // the kernel parameters need.
 inline bool stream_plan_axis(const avirb200_axis_desc& ad, int sum_mode, int channels, StreamAxisPlan& out,
-                             bool allow_up2 = false) {
+                             bool allow_deselected = false) {
     out.chain = kChainNone;
     if (channels != 4) return false;
-    // allow_up2: the upsizing chain is instantiated and checked (emulation; AVIRB200_STREAM_UP2=1
-    // on the GPU) but not selected by default: on B200 the tile kernel's blocked skip-odd resize
-    // is 2.4x faster on cfg2's column pass (profiles/r01_variant_sweeps_packed.jsonl).
+    // allow_deselected: two chains are instantiated and checked (emulation; on the GPU with
+    // AVIRB200_STREAM_ALL=1) but not selected by default, because the tile kernel measured
+    // faster on B200: the upsizing chain (cfg2's column pass 0.40 vs 0.17 ms,
+    // profiles/r01_variant_sweeps_packed.jsonl) and the 56-tap chain (cfg5: row pass 0.92 vs
+    // 0.73 ms, column pass 0.28 vs 0.20 ms, profiles/r01_pass_times.jsonl).
     for (int id = 1; id < kChainCount; ++id) {
-        if (id == kChainUp2 && !allow_up2) continue;
+        if ((id == kChainUp2 || id == kChainDil56) && !allow_deselected) continue;
         int ns = 0;
         const StepSpec* spec = chain_spec(id, &ns);
         if (ns != ad.nsteps) continue;
@@ -181,6 +192,14 @@ inline bool stream_plan_axis(const avirb200_axis_desc& ad, int sum_mode, int cha
 inline bool stream_row_source_ok(const avirb200_plan_desc& d) {
     if (d.use_gamma & 1) return d.in_type == AVIRB200_U8;
     return d.in_type == AVIRB200_F32 || d.in_type == AVIRB200_U8 || d.in_type == AVIRB200_U16;
+}
+// Output stage of the column pass, a compile-time choice of the kernel: 1 = float
+// destination without output gamma (store as is), 2 = integer destination without output gamma
+// (round, clamp, narrow), 0 = everything (sRGB de-linearisation in double included -- its code
+// is large enough to slow the whole kernel down, hence the split).
+inline int stream_epilogue_code(const avirb200_plan_desc& d) {
+    if (d.use_gamma & 2) return 0;
+    return d.out_type == AVIRB200_F32 ? 1 : 2;
 }
 inline int stream_row_source_code(const avirb200_plan_desc& d) {
     return (d.use_gamma & 1) ? kSrcU8Srgb : d.in_type;

@@ -48,13 +48,14 @@ void emul_pass(const StreamParams& p, int nwarps) {
 }
 
 template <bool IS_V>
-bool emul_dispatch(int chain, int variant, const StreamParams& p, int nwarps, bool plain) {
+bool emul_dispatch(int chain, int variant, const StreamParams& p, int nwarps, int epi) {
     return stream_dispatch(chain, IS_V, variant, p.src_type, [&](auto tag, auto pass) {
         using C = typename decltype(tag)::type;
         if constexpr (decltype(pass)::is_v != IS_V) {
             (void)p; // (the dispatcher instantiates the callback for both passes)
         } else if constexpr (IS_V) {
-            if (plain) emul_pass<C, true, 1>(p, nwarps);
+            if (epi == 1) emul_pass<C, true, 1>(p, nwarps);
+            else if (epi == 2) emul_pass<C, true, 2>(p, nwarps);
             else emul_pass<C, true, 0>(p, nwarps);
         } else {
             emul_pass<C, false, 0>(p, nwarps);
@@ -95,9 +96,9 @@ int stream_emul_resize(const avirb200_plan_desc* d, const void* src, size_t src_
     p.dst = mid.data();
     p.dst_pitch = (long long)d->dst_w * 4;
     p.dst_type = AVIRB200_F32;
-    if (!emul_dispatch<false>(h.chain, variant, p, warps_h, false)) return -4;
+    if (!emul_dispatch<false>(h.chain, variant, p, warps_h, 0)) return -4;
 
-    const bool plain = (d->out_type == AVIRB200_F32) && !(d->use_gamma & 2);
+    const int epi = stream_epilogue_code(*d);
     for (int b = 0; b < bands; ++b) {
         stream_fill_params(p, v, *d);
         p.n_lines = d->dst_w;
@@ -111,7 +112,7 @@ int stream_emul_resize(const avirb200_plan_desc* d, const void* src, size_t src_
         p.dst_pitch = (long long)dst_pitch;
         p.dst_type = d->out_type;
         p.dst_row_base = 0;
-        if (!emul_dispatch<true>(v.chain, variant, p, warps_v, plain)) return -4;
+        if (!emul_dispatch<true>(v.chain, variant, p, warps_v, epi)) return -4;
     }
     return 0;
 }

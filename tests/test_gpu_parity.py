@@ -123,6 +123,27 @@ def test_generic_and_fast_kernels_agree_on_medium():
     assert cs.count_mismatch(a, b) == 0
 
 
+# ---- streaming chains that are instantiated but not selected by default -----------------------
+
+@pytest.mark.parametrize("case", [
+    # (cfg5 chain: only in builds made with AVIRB200_BUILD_ALL_CHAINS=1; else these run the tile kernel)
+    (2, 388, 220, 97, 55, 4, np.uint8, np.uint8, 8, {"gamma": True, "alpha": 3, "buildmode": 1}),
+    (2, 768, 432, 192, 108, 4, np.float32, np.float32, 16, {"buildmode": 1}),
+    (1, 242, 137, 484, 274, 4, np.uint8, np.uint8, 8, {"buildmode": 1}),                           # cfg2 chain
+    (1, 480, 270, 960, 540, 4, np.float32, np.uint16, 16, {"buildmode": 1}),
+], ids=cs.case_id)
+def test_deselected_streaming_chains_bit_exact(case):
+    """The upsizing and the 56-tap chain run on the tile kernel by default (it measured faster);
+    AVIRB200_STREAM_ALL=1 selects their streaming instantiations, which must give the same bits."""
+    src = cs.make_input(case, seed=31)
+    os.environ["AVIRB200_STREAM_ALL"] = "1"
+    try:
+        got = cs.gpu_output(case, src)  # (geometries no other test plans: plans are cached per call shape)
+    finally:
+        del os.environ["AVIRB200_STREAM_ALL"]
+    assert cs.count_mismatch(expected(case, src), got) == 0
+
+
 # ---- pipelined host call: row bands over copy-in / compute / copy-out streams ----------------
 
 @pytest.mark.parametrize("bands", [2, 3, 7, 16])
