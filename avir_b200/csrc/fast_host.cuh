@@ -389,7 +389,7 @@ inline size_t fast_elsize(int t) { return t == AVIRB200_U8 ? 1 : (t == AVIRB200_
 
 // Picks the (single) resize step whose one effective phase goes into the kernel parameters.
 inline void fast_set_const_taps(FastParams& p, const FastPass& fp) {
-    { const char* e = getenv("AVIRB200_DEBUG"); p.debug = e ? atoi(e) : 0; }
+    p.debug = 0; // (the kernels' perf-experiment branches are never enabled from the library)
     p.rtaps_step = -1;
     for (int i = 0; i < fp.hax.nsteps; ++i) {
         const FastStep& s = fp.hax.s[i];

@@ -86,7 +86,7 @@ struct FastParams {
     int uniform_taps[kFastMaxSteps]; // resize step whose outputs all share one effective phase
     int rtaps_step;                  // the step whose single effective phase is in rtaps (-1: none)
     float rtaps[64];                 // that phase: constant-bank operands for the blocked loops
-    int debug;                       // perf experiments: 1 = skip the arithmetic, 2 = skip source staging
+    int debug;                       // always 0 (perf experiments of round 1: 1 = skip the arithmetic, 2 = skip source staging)
     const void* src;
     long long src_pitch;  // elements
     int src_type;
