@@ -119,4 +119,16 @@ int stream_emul_resize(const avirb200_plan_desc* d, const void* src, size_t src_
 
 int stream_emul_variants(void) { return kStreamVariants; }
 
+// What the engine would choose for the descriptor: out[0] / out[1] = StreamChainId of the row /
+// column pass (0 = the pass runs on the tile or generic kernel), out[2] = row-pass source code,
+// out[3] = column-pass epilogue code.  all_chains: as with AVIRB200_STREAM_ALL=1.
+void stream_emul_selection(const avirb200_plan_desc* d, int all_chains, int* out) {
+    StreamAxisPlan h, v;
+    out[0] = (stream_row_source_ok(*d) && stream_plan_axis(d->h, d->sum_mode, d->channels, h, all_chains != 0))
+                 ? h.chain : 0;
+    out[1] = stream_plan_axis(d->v, d->sum_mode, d->channels, v, all_chains != 0) ? v.chain : 0;
+    out[2] = stream_row_source_code(*d);
+    out[3] = stream_epilogue_code(*d);
+}
+
 } // extern "C"

@@ -128,3 +128,37 @@ def test_irregular_chains_stay_on_the_tile_kernel(emul):
         assert emul.stream_emul_applicable(dp) == 0
     finally:
         rs.free_descriptor(h)
+
+
+def test_chain_selection_of_the_baseline_configs(emul):
+    """Which kernel family each BASELINE config's passes select (host logic shared with the
+    engine): streaming chain ids per stream_types.h, 0 = tile kernel."""
+    emul.stream_emul_selection.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int)]
+    DIL24, INL24, INL3, INL3D, DIL56, UP2 = 1, 2, 3, 4, 5, 6
+    U8, U16, F32, SRGB = 0, 1, 2, 4
+    table = [
+        # case (full BASELINE sizes; planning only)                                 default      all chains   src   epi
+        ((1, 1920, 1080, 3840, 2160, 4, u8, u8, 8, {}),                             (0, 0),      (UP2, UP2),   U8,   2),   # cfg2
+        ((2, 7680, 4320, 3840, 2160, 4, f32, f32, 16, {}),                          (DIL24,) * 2, (DIL24,) * 2, F32, 1),   # cfg3
+        ((1, 7680, 4320, 3840, 2160, 4, f32, f32, 16, {}),                          (INL3,) * 2, (INL3,) * 2,  F32,  1),
+        ((1, 16384, 16384, 4096, 4096, 4, u16, u16, 16, {}),                        (INL3D,) * 2, (INL3D,) * 2, U16, 2),   # cfg4
+        ((2, 7680, 4320, 1920, 1080, 4, u8, u8, 8, {"gamma": True, "alpha": 3}),    (0, 0),      (DIL56,) * 2, SRGB, 0),   # cfg5
+        ((1, 7680, 4320, 3840, 2160, 4, u8, u8, 8, {}),                             (INL24,) * 2, (INL24,) * 2, U8,  2),
+        ((2, 7680, 4320, 3840, 2160, 4, f32, u16, 16, {"gamma": True}),             (0, DIL24),  (0, DIL24),   SRGB, 0),   # float + gamma source: tile row pass
+        ((1, 1500, 1000, 1111, 741, 4, u8, u8, 8, {}),                              (0, 0),      (0, 0),       U8,   2),   # irregular ratio
+    ]
+    for case, want_def, want_all, src, epi in table:
+        fp, sw, sh, nw, nh, ch, ti, to, rb, kw = case
+        rs, v = cs.resizer_and_vars(case)
+        h, dp, modes = rs.descriptor((sh, sw, ch), ti, nw, nh, to, 0.0, v)
+        try:
+            out = (C.c_int * 4)()
+            emul.stream_emul_selection(dp, 0, out)
+            assert (out[0], out[1]) == want_def, (cs.case_id(case), list(out))
+            if out[0]:
+                assert out[2] == src, (cs.case_id(case), list(out))
+            assert out[3] == epi, (cs.case_id(case), list(out))
+            emul.stream_emul_selection(dp, 1, out)
+            assert (out[0], out[1]) == want_all, (cs.case_id(case), list(out))
+        finally:
+            rs.free_descriptor(h)
