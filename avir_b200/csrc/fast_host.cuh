@@ -316,12 +316,14 @@ inline int fast_launch(const FastParams& p, size_t smem, int sum_mode, cudaStrea
     if (!launched && !generic_only && sum_mode == SUMM && a.nsteps == NSS && v0 == A0 &&           \
         (NSS < 2 || v1 == A1) && (NSS < 3 || v2 == A2) && cs == CSS) {                             \
         if (p.is_v && plain_f32) AVB_LAUNCH_K(SUMM, true, NSS, A0, A1, A2, CSS, 1);                 \
+        else if (p.is_v && int_plain) AVB_LAUNCH_K(SUMM, true, NSS, A0, A1, A2, CSS, 2);            \
         else if (p.is_v) AVB_LAUNCH_K(SUMM, true, NSS, A0, A1, A2, CSS, 0);                         \
         else AVB_LAUNCH_K(SUMM, false, NSS, A0, A1, A2, CSS, 0);                                    \
         launched = true;                                                                           \
     }
     bool launched = false;
     const bool plain_f32 = (p.dst_type == AVIRB200_F32 && !p.gamma_out);
+    const bool int_plain = (p.dst_type != AVIRB200_F32 && !p.gamma_out); // integer destination, no output gamma
     AVB_TRY(AVIRB200_SUM_DIL8, 2, kVarResizeDil24D2, kVarFirDil8R1, -1, 0)        // cfg3 (float8_dil)
     AVB_TRY(AVIRB200_SUM_DIL8, 2, kVarResizeDil56D4, kVarFirDil8R1, -1, -1)       // cfg5
     AVB_TRY(AVIRB200_SUM_INL, 3, kVarFirInl7R1, kVarResizeInl18D2, kVarFirInl7R1, 1)   // cfg3 (float4)

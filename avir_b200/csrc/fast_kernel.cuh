@@ -152,17 +152,20 @@ __device__ __forceinline__ void cp_async_wait_all() {
     asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
 }
 
+// Integer destinations: round (the class's own round()), clamp (avir.h:4392-4419).
+__device__ __forceinline__ float epilogue_round_c4(const FastParams& p, float v) {
+    if (p.tr_mul == 1.0f) v = round_out(v, p.round_mode);
+    else v = __fmul_rn(round_out(__fmul_rn(v, p.tr_mul_inv), p.round_mode), p.tr_mul);
+    return v < 0.0f ? 0.0f : (v > p.pk_out ? p.pk_out : v);
+}
+
 // Output stage for one element (gamma -> round -> clamp), 4-channel images.
 __device__ __forceinline__ float epilogue_value_c4(const FastParams& p, float v, int c) {
     if (p.gamma_out) {
         if (c == p.alpha_index) v = __fmul_rn(v, p.out_gamma_mult);
         else v = __fmul_rn(lin2srgb(v), p.out_gamma_mult);
     }
-    if (p.dst_type != AVIRB200_F32) {
-        if (p.tr_mul == 1.0f) v = round_out(v, p.round_mode);
-        else v = __fmul_rn(round_out(__fmul_rn(v, p.tr_mul_inv), p.round_mode), p.tr_mul);
-        v = v < 0.0f ? 0.0f : (v > p.pk_out ? p.pk_out : v);
-    }
+    if (p.dst_type != AVIRB200_F32) v = epilogue_round_c4(p, v);
     return v;
 }
 
@@ -386,6 +389,9 @@ struct Sink {
 };
 
 // EPI 1 = destination is float and there is no output gamma: the value is stored as is.
+// EPI 2 = integer destination without output gamma: round, clamp, narrow -- and none of the
+// double-precision sRGB code in the kernel (inlined at every store site it slowed the whole
+// kernel down).  EPI 0 = everything, decided at run time.
 template <bool TO_GLOBAL, int EPI>
 __device__ __forceinline__ void sink_store(const FastParams& p, const Sink& k, int j, float2 v, int c0) {
     if (!TO_GLOBAL) {
@@ -394,6 +400,17 @@ __device__ __forceinline__ void sink_store(const FastParams& p, const Sink& k, i
     }
     if (EPI == 1) {
         if (k.gok) *reinterpret_cast<float2*>(k.gp + (size_t)(j - k.grow_base) * k.grow) = v;
+        return;
+    }
+    if (EPI == 2) {
+        v.x = epilogue_round_c4(p, v.x);
+        v.y = epilogue_round_c4(p, v.y);
+        if (!k.gok) return;
+        unsigned char* g2 = k.gp + (size_t)(j - k.grow_base) * k.grow;
+        if (p.dst_type == AVIRB200_U8)
+            *reinterpret_cast<uchar2*>(g2) = make_uchar2((unsigned char)v.x, (unsigned char)v.y);
+        else
+            *reinterpret_cast<ushort2*>(g2) = make_ushort2((unsigned short)v.x, (unsigned short)v.y);
         return;
     }
     v.x = epilogue_value_c4(p, v.x, c0);
