@@ -170,7 +170,7 @@ class CLancIRParams:
 
 
 class CLancIR:
-    """avir::CLancIR, lancir.h:311 (4-channel images on the GPU path)."""
+    """avir::CLancIR, lancir.h:311 (1-4 channel images, u8 / u16 / float buffers)."""
 
     def resizeImage(self, SrcBuf, NewWidth, NewHeight, aParams=None, out_dtype=None):
         src = np.ascontiguousarray(SrcBuf)

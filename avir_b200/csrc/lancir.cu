@@ -12,8 +12,9 @@
 // (lancir.h:1772-2056): optional multiply, clamp, round-to-nearest-even; the last
 // `(NewWidth*C) & 3` elements of a row round as (int)(v + 0.5f) instead.
 //
-// The column pass keeps threads along x (coalesced); the row pass stages a strip of the
-// fp32 intermediate in shared memory.
+// Both passes run one thread per output element: the column pass with threads along x
+// (coalesced reads of every tap's row), the row pass reading its taps' pixels from the fp32
+// intermediate through the caches (neighbouring threads share them).
 
 #include <cuda_runtime.h>
 

@@ -9,14 +9,16 @@
 //   * a WARP owns a run: 16 lines (lane = one channel pair of one line, as in the tile
 //     kernel) times a long contiguous range of positions, and streams along it;
 //   * every step of the chain works in batches of 8 outputs from a register window of its
-//     input (38 shared loads per 752 FP instructions for the 24-tap resize) and appends the
+//     input (38 shared loads per 376 packed FP instructions for the 24-tap resize) and appends the
 //     batch to a small per-warp ring in shared memory; the next step consumes that ring a
 //     fixed number of rounds later (software pipeline, all offsets compile-time);
 //   * a lane only ever reads back what it wrote itself ([position][lane] layout), so the
 //     intermediate rings need no synchronisation at all; only the source ring (filled by
-//     16-byte cp.async copies, transposing rows into lanes in the row pass, three rounds
-//     ahead of use) and the row pass's output staging use __syncwarp;
-//   * taps are kernel parameters (constant-bank operands of the multiplies): only chains
+//     cp.async copies of whole pixels -- float, or the caller's u8 / u16 pixels as they are,
+//     cast in the lanes' reads -- up to three rounds ahead of use) and the row pass's output
+//     staging use __syncwarp;
+//   * taps are kernel parameters (uniform-register operands of the packed multiplies, see
+//     f2mul / f2add below): only chains
 //     whose resize step has one effective phase and a constant source step -- all integer
 //     ratios, i.e. every BASELINE configuration -- run here, everything else stays on the
 //     tile kernel;
