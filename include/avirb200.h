@@ -146,7 +146,12 @@ int avirb200_col_pass_device(const avirb200_plan* plan, const void* d_workspace,
                              size_t dst_pitch, void* stream);
 
 /* Convenience used by the drop-in resizeImage(): host buffers in, host buffers out
- * (H2D, both passes, D2H, synchronise).  Device buffers are cached inside the plan. */
+ * (H2D, both passes, D2H, synchronise).  Device buffers are cached inside the plan.
+ * Images of 64 MiB and more are cut into row bands travelling on separate copy-in / compute /
+ * copy-out streams, so that the PCIe transfers of both directions overlap each other and the
+ * kernels (page-locked host memory lets them run asynchronously); the result bits do not
+ * depend on the banding.  h_dst may alias h_src (upstream allows NewBuf == SrcBuf when the
+ * destination is not larger, avir.h:4650-4652): such calls run unbanded. */
 int avirb200_resize_host(avirb200_plan* plan, const void* h_src, size_t src_pitch, void* h_dst,
                          size_t dst_pitch);
 
