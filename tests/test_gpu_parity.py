@@ -338,3 +338,44 @@ def test_lancir_golden_fixtures():
         sw, sh, nw, nh = [int(v) for v in z["geom"]]
         r, got = ab.CLancIR().resizeImage(z["src"], nw, nh, out_dtype=z["out"].dtype)
         assert r == nh and cs.count_mismatch(z["out"], got) == 0, f
+
+
+# ---- seeded random sweep over the whole call surface (same generator as the oracle's own) ------
+
+@pytest.mark.parametrize("seed", [11, 12, 13])
+def test_fuzz_product_matches_oracle(seed):
+    """All six classes, 1..4 channels, every Tin/Tout pair incl. double, bit depths, gamma / alpha,
+    offsets, explicit and negative k, presets, forced build modes, odd ratios: product path
+    (kernel family chosen by the engine) against the oracle, 0 mismatching elements."""
+    rng = np.random.default_rng(seed)
+    types = [np.uint8, np.uint16, np.float32, np.float64]
+    for it in range(40):
+        fp, ch = int(rng.integers(0, 6)), int(rng.integers(1, 5))
+        sw, sh = int(rng.integers(1, 160)), int(rng.integers(1, 160))
+        mode = int(rng.integers(0, 4))
+        if mode == 0:
+            nw, nh = max(1, sw // int(rng.integers(1, 9))), max(1, sh // int(rng.integers(1, 9)))
+        elif mode == 1:
+            nw, nh = sw * int(rng.integers(1, 4)), sh * int(rng.integers(1, 4))
+        else:
+            nw, nh = int(rng.integers(1, 240)), int(rng.integers(1, 240))
+        ti, to = types[int(rng.integers(0, 4))], types[int(rng.integers(0, 4))]
+        rb = int(rng.integers(4, 9)) if to == np.uint8 else (
+            int(rng.integers(8, 17)) if to == np.uint16 else int(rng.choice([8, 16])))
+        kw = {}
+        if rng.random() < 0.3:
+            kw["gamma"] = True
+        if ch == 4 and rng.random() < 0.5:
+            kw["alpha"] = int(rng.choice([0, 3]))
+        if rng.random() < 0.2:
+            kw["ox"], kw["oy"] = float(rng.uniform(-1, 1)), float(rng.uniform(-1, 1))
+        if rng.random() < 0.2:
+            kw["k"] = float(rng.choice([-2.5, -1.0, 0.7, 1.5, 3.0]))
+        if rng.random() < 0.2:
+            kw["params"] = int(rng.integers(0, 6))
+        if rng.random() < 0.3:
+            kw["buildmode"] = int(rng.integers(0, 4))
+        case = (fp, sw, sh, nw, nh, ch, ti, to, rb, kw)
+        src = cs.make_input(case, seed=1000 * seed + it)
+        got = cs.gpu_output(case, src)
+        assert cs.count_mismatch(expected(case, src), got) == 0, cs.case_id(case)
