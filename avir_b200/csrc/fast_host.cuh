@@ -237,6 +237,10 @@ inline void fast_plan_init(FastPlan& f, const DevAxis& h_host, const DevAxis& v_
     const DevAxis* hs[2] = {&h_host, &v_host};
     for (int a = 0; a < 2; ++a) {
         FastPass& fp = *ps[a];
+        // Float sources stream into the row pass's tile as they are (cp.async): a float source
+        // that needs the sRGB linearisation on the way in is the generic kernel's (found by
+        // tests/test_gpu_parity.py::test_fuzz_product_matches_oracle: this pass used to skip it).
+        if (a == 0 && d.in_type == AVIRB200_F32 && (d.use_gamma & 1)) continue;
         if (!fast_build_axis(fp, *hs[a], d.sum_mode)) continue;
         // host pointers for range arithmetic first, then upload
         for (int i = 0; i < fp.hax.nsteps; ++i)
