@@ -162,3 +162,51 @@ def test_chain_selection_of_the_baseline_configs(emul):
             assert (out[0], out[1]) == want_all, (cs.case_id(case), list(out))
         finally:
             rs.free_descriptor(h)
+
+
+def test_stream_kernel_emulation_fuzz(emul):
+    """Seeded random sweep over the streaming-eligible call shapes (k = 2, 4, 2x4, 0.5; the three
+    classes; both build modes; u8 / u16 / float sources and destinations; input / output gamma
+    and the alpha exemption) with random warp counts, destination bands and scheduling
+    variants: emulation == port on every call the streaming kernel accepts."""
+    lut = np.zeros(256, np.float32)
+    cs.port().avir_port_srgb_lut(lut.ctypes.data)
+    rng = np.random.default_rng(5)
+    types = [u8, u16, f32]
+    ran = 0
+    for it in range(110):
+        fp, fam = int(rng.integers(0, 3)), int(rng.integers(0, 4))
+        nw, nh = int(rng.integers(3, 90)), int(rng.integers(3, 60))
+        if fam == 0:
+            sw, sh, bm = nw * 2, nh * 2, int(rng.integers(0, 2))
+        elif fam == 1:
+            sw, sh, bm = nw * 4, nh * 4, int(rng.integers(0, 2))
+        elif fam == 2:
+            sw, sh, bm = nw * 2, nh * 4, int(rng.integers(0, 2))
+        else:
+            sw, sh, nw, nh, bm = nw, nh, nw * 2, nh * 2, 1
+        ti, to = types[int(rng.integers(0, 3))], types[int(rng.integers(0, 3))]
+        rb = int(rng.integers(5, 9)) if to == u8 else (int(rng.integers(9, 17)) if to == u16 else int(rng.choice([8, 16])))
+        kw = {"buildmode": bm}
+        if rng.random() < 0.4:
+            kw["gamma"] = True
+        if rng.random() < 0.5:
+            kw["alpha"] = int(rng.choice([0, 3]))
+        case = (fp, sw, sh, nw, nh, 4, ti, to, rb, kw)
+        src = cs.make_input(case, seed=77 + it)
+        rs, v = cs.resizer_and_vars(case)
+        h, dp, modes = rs.descriptor(src.shape, src.dtype, nw, nh, to, 0.0, v)
+        try:
+            if emul.stream_emul_applicable(dp) != 1:
+                continue
+            got = np.zeros((nh, nw, 4), to)
+            wh, wv = int(rng.integers(1, 9)), int(rng.integers(1, 9))
+            bands, var = int(rng.integers(1, 5)), int(rng.integers(0, 4))
+            assert emul.stream_emul_resize(dp, src.ctypes.data, sw * 4, got.ctypes.data, nw * 4, wh, wv, bands,
+                                           var, lut.ctypes.data) == 0
+        finally:
+            rs.free_descriptor(h)
+        want, _ = cs.port_output(case, src)
+        assert cs.count_mismatch(want, got) == 0, (cs.case_id(case), wh, wv, bands, var)
+        ran += 1
+    assert ran >= 30
