@@ -395,3 +395,27 @@ def test_fuzz_product_matches_oracle(seed):
         src = cs.make_input(case, seed=1000 * seed + it)
         got = cs.gpu_output(case, src)
         assert cs.count_mismatch(expected(case, src), got) == 0, cs.case_id(case)
+
+
+@needs_ref
+def test_lancir_fuzz_product_matches_oracle():
+    """Seeded random sweep of CLancIR on the GPU: 1..4 channels, la = 2 .. 5, both scaling
+    directions, offsets, explicit steps, every u8 / u16 / float type pair, against upstream."""
+    rng = np.random.default_rng(17)
+    types = [np.uint8, np.uint16, np.float32]
+    for it in range(60):
+        ch = int(rng.integers(1, 5))
+        sw, sh = int(rng.integers(2, 120)), int(rng.integers(2, 120))
+        nw, nh = int(rng.integers(1, 200)), int(rng.integers(1, 200))
+        ti, to = types[int(rng.integers(0, 3))], types[int(rng.integers(0, 3))]
+        kw = {"la": float(rng.choice([2.0, 2.5, 3.0, 4.0, 5.0]))}
+        if rng.random() < 0.3:
+            kw["kx"], kw["ky"] = float(rng.choice([0.5, 0.8, 1.7, -1.3])), float(rng.choice([0.6, 1.0, 2.2, -0.9]))
+        if rng.random() < 0.3:
+            kw["ox"], kw["oy"] = float(rng.uniform(-1, 1)), float(rng.uniform(-1, 1))
+        src = o.lcg_image(sh, sw, ch, ti, seed=900 + it)
+        r, ref = o.lancir_ref(src, nw, nh, to, **kw)
+        assert r == nh
+        r, got = ab.CLancIR().resizeImage(src, nw, nh, ab.CLancIRParams(**kw), out_dtype=to)
+        assert r == nh
+        assert cs.count_mismatch(ref, got) == 0, (sw, sh, nw, nh, ch, ti, to, kw)
