@@ -760,6 +760,10 @@ int avirb200_plan_create(const avirb200_plan_desc* desc, avirb200_plan** out) {
         // the column pass delivers the gamma-corrected float rows; errd_kernel rounds them in row order
         pl->errd = true;
         pl->desc.out_type = AVIRB200_F32;
+        // errd_kernel's blocks (one warp per 32 rows) wait for their predecessor: keep all of them
+        // resident at once (148 SMs x 32 blocks) instead of relying on in-order block dispatch
+        if ((desc->dst_h + 31) / 32 > 4096)
+            return fail(AVIRB200_ERR_UNSUPPORTED, "error diffusion: more than 131072 destination rows");
     }
     int r = copy_axis_host(pl->h, desc->h);
     if (r != 0) return r;
