@@ -9,5 +9,6 @@ fallback -- every call goes to the CUDA library and raises if that fails.
 """
 from .api import (  # noqa: F401
     FP_DEF, FP_FLOAT4, FP_FLOAT8_DIL, FP_DEF_ERRD, FP_FLOAT4_ERRD, FP_FLOAT8_DIL_ERRD, CImageResizer, CImageResizerVars, CLancIR,
-    CLancIRParams, AvirB200Error, lib, host_lib, device_count,
+    CLancIRParams, AvirB200Error, lib, host_lib, device_count, set_option,
+    OPT_KERNEL_FAMILY, OPT_STREAM_VARIANT_H, OPT_STREAM_VARIANT_V, OPT_HOST_BANDS, OPT_ALL_STREAM_CHAINS, OPT_OVERLAP_HALO,
 )

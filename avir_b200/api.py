@@ -18,8 +18,15 @@ FP_DEF_ERRD, FP_FLOAT4_ERRD, FP_FLOAT8_DIL_ERRD = 3, 4, 5
 _T = {np.dtype(np.uint8): 0, np.dtype(np.uint16): 1, np.dtype(np.float32): 2, np.dtype(np.float64): 3}
 
 
+# avirb200_plan_set_option() keys (include/avirb200.h, avirb200_option)
+OPT_KERNEL_FAMILY, OPT_STREAM_VARIANT_H, OPT_STREAM_VARIANT_V, OPT_HOST_BANDS, OPT_ALL_STREAM_CHAINS, OPT_OVERLAP_HALO = range(6)
+
+
 class AvirB200Error(RuntimeError):
     pass
+
+
+_LT = (np.dtype(np.uint8), np.dtype(np.uint16), np.dtype(np.float32))  # CLancIR buffer types
 
 
 _lib = None
@@ -50,6 +57,7 @@ def host_lib():
             raise AvirB200Error("libavirb200_host.so is not built: run `python avir_b200/build.py`")
         h = C.CDLL(path)
         h.avirb200_host_last_error.restype = C.c_char_p
+        h.avirb200_host_set_option.argtypes = [C.c_int, C.c_int]
         call = [C.c_int] * 6
         geom = [C.c_int] * 5 + [C.c_double] * 3 + [C.c_int] * 3
         h.avirb200_host_desc_create.restype = C.c_void_p
@@ -82,6 +90,12 @@ def host_lib():
 
 def device_count():
     return lib().avirb200_device_count()
+
+
+def set_option(option, value):
+    """Test / tuning hook of the ctypes driver: plan option applied to every plan the front-end
+    objects behind host_lib() use from now on (value -1: back to the plan's default)."""
+    host_lib().avirb200_host_set_option(option, value)
 
 
 class CImageResizerVars:
@@ -178,6 +192,8 @@ class CLancIR:
         out_dtype = np.dtype(out_dtype or src.dtype)
         p = aParams or CLancIRParams()
         dst = np.empty((NewHeight, NewWidth, ch), out_dtype)
+        if src.dtype not in _LT or out_dtype not in _LT:
+            raise AvirB200Error("CLancIR: uint8 / uint16 / float32 buffers only")
         r = host_lib().lancirb200_host_resize(_T[src.dtype], _T[out_dtype], src.ctypes.data, sw, sh,
                                               dst.ctypes.data, NewWidth, NewHeight, ch, p.SrcSSize,
                                               p.NewSSize, p.kx, p.ky, p.ox, p.oy, p.la)

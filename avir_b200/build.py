@@ -95,8 +95,8 @@ def _build_cuda(force=False, verbose=False):
     linked into libavirb200.so."""
     from concurrent.futures import ThreadPoolExecutor
     target = os.path.join(PKG, "libavirb200.so")
-    # (source, object, extra flags); stream_chain.cu holds the kernels of ONE streaming chain and is
-    # compiled once per chain id (stream_types.h: StreamChainId 1..6), in parallel
+    # (source, object, extra flags); stream_chain.cu holds the kernels of ONE pass of ONE streaming
+    # chain and is compiled once per chain id (stream_types.h: StreamChainId 1..6) and pass, in parallel
     # Chain 5 (the 56-tap cfg5 chain) is left out unless AVIRB200_BUILD_ALL_CHAINS=1: it is not
     # selected at run time (slower than the tile kernel) and takes ~18 minutes to compile.
     all_chains = os.environ.get("AVIRB200_BUILD_ALL_CHAINS") == "1"
@@ -106,8 +106,8 @@ def _build_cuda(force=False, verbose=False):
     jobs.append((os.path.join(CSRC, "stream_pass.cu"),
                  os.path.join(PKG, "stream_pass_all.o" if all_chains else "stream_pass.o"),
                  ["-DAVS_WITH_DIL56"] if all_chains else []))
-    jobs += [(os.path.join(CSRC, "stream_chain.cu"), os.path.join(PKG, "stream_chain_%d.o" % k),
-              ["-DAVS_CHAIN_ID=%d" % k]) for k in chains]
+    jobs += [(os.path.join(CSRC, "stream_chain.cu"), os.path.join(PKG, "stream_chain_%d%s.o" % (k, "hv"[v])),
+              ["-DAVS_CHAIN_ID=%d" % k, "-DAVS_CHAIN_PASS=%d" % v]) for k in chains for v in (0, 1)]
     objs = [j[1] for j in jobs]
     todo = [j for j in jobs if force or _obj_stale(j[1], j[0])]
 

@@ -33,18 +33,6 @@ using namespace avb;
 namespace {
 
 thread_local std::string g_err;
-// debug/test switch: 0 = streaming kernel, else tile kernel, else generic kernel (product
-// order); 1 = generic kernel only; 2 = tile kernel, else generic (no streaming kernel)
-int g_kernel_mode = 0;
-#define g_force_generic (g_kernel_mode == 1)
-
-bool env_stream_enabled() {
-    static const bool on = [] {
-        const char* e = getenv("AVIRB200_DISABLE_STREAM");
-        return !(e && e[0] == '1');
-    }();
-    return on;
-}
 
 int fail(int code, const std::string& msg) {
     g_err = msg;
@@ -107,6 +95,10 @@ struct HostAxis {
 
 } // namespace
 
+namespace {
+struct Halo;
+}
+
 struct avirb200_plan {
     avirb200_plan_desc desc;     // in_type / out_type: what the KERNELS read and write (F64 -> F32)
     int io_in_type = 0, io_out_type = 0; // the caller's element types
@@ -118,17 +110,32 @@ struct avirb200_plan {
     PassConfig cfg_h, cfg_v;
     FastPlan fast;
     avs::StreamAxisPlan stream_h, stream_v; // chain != 0: the pass runs on the streaming kernel
-    // resize_host cache
+    // resize_host: the device's shared staging buffers for the duration of a call
     std::mutex mx;
     void* d_src = nullptr;
     void* d_dst = nullptr;
     void* d_ws = nullptr;
-    size_t d_src_bytes = 0, d_dst_bytes = 0, d_ws_bytes = 0;
     cudaStream_t stream = nullptr;
     // pipelined resize_host: copy-in / copy-out streams and per-band events
     cudaStream_t stream_in = nullptr, stream_out = nullptr;
     std::vector<cudaEvent_t> ev_in, ev_out;
     mutable int last_launches = 0;
+    // options (avirb200_plan_set_option)
+    // 1..3-channel images on the 4-channel kernels (streaming / tile): the source is widened to
+    // 4-channel pixels in a scratch copy, both passes run as for RGBA (channels never mix; the
+    // pad channel's results are dropped), the destination is narrowed back.  mid_ch: channels of
+    // the intermediate (4 then, else the image's).
+    bool pad4 = false;
+    int mid_ch = 0;
+    int opt_family = 0;       // 0 product order, 1 generic kernel only, 2 tile kernel else generic
+    int opt_var_h = -1, opt_var_v = -1; // scheduling variant of the streaming passes (-1: default)
+    int opt_host_bands = -1;  // resize_host band count (-1: by size)
+    int opt_all_chains = 0;
+    int opt_overlap = 1;      // sharded: mailbox exchange overlapped with the interior rows
+    int sm_count = 148;       // of `device`
+    Halo* halo = nullptr; // sharded: peer mailboxes (created by the first sharded call)
+    cudaStream_t stream_x = nullptr; // sharded: exchange stream
+    cudaEvent_t ev_x0 = nullptr, ev_x1 = nullptr;
 };
 
 namespace {
@@ -312,14 +319,36 @@ int launch_generic(const PassParams& p, const PassConfig& c, cudaStream_t st) {
     return 0;
 }
 
+int launch_widen(int type, const void* src, size_t src_pitch, void* dst, int w, int rows, int C, cudaStream_t st);
+int launch_narrow(int type, const void* src, void* dst, size_t dst_pitch, int w, int rows, int C, cudaStream_t st);
+
+// 1..3-channel plans whose passes run on the 4-channel kernels in this call (avirb200_plan::pad4)
+bool use_pad4(const avirb200_plan* pl) { return pl->pad4 && pl->opt_family != 1; }
+size_t pad4_src_bytes(const avirb200_plan* pl, int rows) {
+    return pl->pad4 ? ((size_t)rows * pl->desc.src_w * 4 * dtype_size(pl->desc.in_type) + 255) / 256 * 256 : 0;
+}
+size_t pad4_dst_bytes(const avirb200_plan* pl, int rows) {
+    return pl->pad4 ? ((size_t)rows * pl->desc.dst_w * 4 * dtype_size(pl->desc.out_type) + 255) / 256 * 256 : 0;
+}
+
 // Row pass over `rows` source rows (band starting at d_src) into the intermediate band
 // starting at d_mid; column pass producing dst rows [out0, out1) from an intermediate
 // buffer whose row 0 is global row mid_row_base.
+// scratch4: where the band's widened (4-channel) copy goes when use_pad4(pl).
 int run_row_pass(const avirb200_plan* pl, const void* d_src, size_t src_pitch, float* d_mid,
-                 int rows, cudaStream_t st, int* launches) {
+                 int rows, cudaStream_t st, int* launches, void* scratch4 = nullptr) {
     if (rows <= 0) return 0;
     const avirb200_plan_desc& d = pl->desc;
-    if (g_kernel_mode == 0 && env_stream_enabled() && pl->stream_h.chain != 0 &&
+    const bool p4 = use_pad4(pl);
+    if (p4) {
+        if (scratch4 == nullptr) return fail(AVIRB200_ERR_BAD_ARG, "row pass: no scratch for the widened source");
+        if (launch_widen(d.in_type, d_src, src_pitch, scratch4, d.src_w, rows, d.channels, st) != 0)
+            return fail(AVIRB200_ERR_CUDA, "widening the source failed");
+        ++*launches;
+        d_src = scratch4;
+        src_pitch = (size_t)d.src_w * 4;
+    }
+    if (pl->opt_family == 0 && pl->stream_h.chain != 0 &&
         ((uintptr_t)d_src % (4 * dtype_size(d.in_type))) == 0 && (src_pitch % 4) == 0 &&
         ((uintptr_t)d_mid % 16) == 0) {
         // (every pixel of the source must be aligned to its own size: the copies move whole pixels)
@@ -335,15 +364,16 @@ int run_row_pass(const avirb200_plan* pl, const void* d_src, size_t src_pitch, f
         sp.dst = d_mid;
         sp.dst_pitch = (long long)d.dst_w * 4;
         sp.dst_type = AVIRB200_F32;
-        const int r = avs::stream_launch(pl->stream_h.chain, false, 0, sp, st);
+        const int r = avs::stream_launch(pl->stream_h.chain, false, 0, pl->opt_var_h, sp, pl->sm_count, st);
         if (r == -1) return fail(AVIRB200_ERR_CUDA, "streaming row pass launch failed");
         if (r == 0) { ++*launches; return 0; }
     }
-    if (env_fast_enabled() && !g_force_generic && pl->fast.h_ok) {
+    if (pl->opt_family != 1 && pl->fast.h_ok) {
         const int r = fast_row_pass(pl->fast, d, d_src, src_pitch, d_mid, rows, pl->d_lut, st);
         if (r == -1) return fail(AVIRB200_ERR_CUDA, "fast row pass launch failed");
         if (r == 0) { ++*launches; return 0; }
     }
+    if (p4) return fail(AVIRB200_ERR_UNSUPPORTED, "row pass: the 4-channel kernels could not take this band");
     PassParams p;
     std::memset(&p, 0, sizeof p);
     fill_common(p, pl);
@@ -366,13 +396,29 @@ int run_row_pass(const avirb200_plan* pl, const void* d_src, size_t src_pitch, f
     return launch_generic(p, pl->cfg_h, st);
 }
 
+// scratch4: where the band's 4-channel destination rows go when use_pad4(pl) (then narrowed into d_dst).
 int run_col_pass(const avirb200_plan* pl, const float* d_mid, int mid_row_base, void* d_dst,
-                 size_t dst_pitch, int out0, int out1, cudaStream_t st, int* launches) {
+                 size_t dst_pitch, int out0, int out1, cudaStream_t st, int* launches, void* scratch4 = nullptr) {
     if (out1 <= out0) return 0;
     const avirb200_plan_desc& d = pl->desc;
+    const bool p4 = use_pad4(pl);
+    void* const user_dst = d_dst;
+    const size_t user_pitch = dst_pitch;
+    if (p4) {
+        if (scratch4 == nullptr) return fail(AVIRB200_ERR_BAD_ARG, "column pass: no scratch for the 4-channel destination");
+        d_dst = scratch4;
+        dst_pitch = (size_t)d.dst_w * 4;
+    }
+    auto finish = [&]() -> int {
+        if (!p4) return 0;
+        if (launch_narrow(d.out_type, scratch4, user_dst, user_pitch, d.dst_w, out1 - out0, d.channels, st) != 0)
+            return fail(AVIRB200_ERR_CUDA, "narrowing the destination failed");
+        ++*launches;
+        return 0;
+    };
     {
         const size_t es = fast_elsize(d.out_type);
-        if (g_kernel_mode == 0 && env_stream_enabled() && pl->stream_v.chain != 0 &&
+        if (pl->opt_family == 0 && pl->stream_v.chain != 0 &&
             ((uintptr_t)d_dst % (2 * es)) == 0 && (dst_pitch % 2) == 0 && ((uintptr_t)d_mid % 16) == 0) {
             avs::StreamParams sp;
             avs::stream_fill_params(sp, pl->stream_v, d);
@@ -386,17 +432,19 @@ int run_col_pass(const avirb200_plan* pl, const float* d_mid, int mid_row_base, 
             sp.dst_pitch = (long long)dst_pitch;
             sp.dst_type = d.out_type;
             sp.dst_row_base = out0;
-            const int r = avs::stream_launch(pl->stream_v.chain, true, avs::stream_epilogue_code(d), sp, st);
+            const int r = avs::stream_launch(pl->stream_v.chain, true, avs::stream_epilogue_code(d), pl->opt_var_v, sp,
+                                             pl->sm_count, st);
             if (r == -1) return fail(AVIRB200_ERR_CUDA, "streaming column pass launch failed");
-            if (r == 0) { ++*launches; return 0; }
+            if (r == 0) { ++*launches; return finish(); }
         }
     }
-    if (env_fast_enabled() && !g_force_generic && pl->fast.v_ok) {
+    if (pl->opt_family != 1 && pl->fast.v_ok) {
         const int r = fast_col_pass(pl->fast, d, d_mid, mid_row_base, d_dst, dst_pitch, out0, out1,
                                     pl->d_lut, st);
         if (r == -1) return fail(AVIRB200_ERR_CUDA, "fast column pass launch failed");
-        if (r == 0) { ++*launches; return 0; }
+        if (r == 0) { ++*launches; return finish(); }
     }
+    if (p4) return fail(AVIRB200_ERR_UNSUPPORTED, "column pass: the 4-channel kernels could not take this band");
     PassParams p;
     std::memset(&p, 0, sizeof p);
     fill_common(p, pl);
@@ -436,6 +484,7 @@ struct Nccl {
     int (*Recv)(void*, size_t, int, int, void*, cudaStream_t) = nullptr;
     int (*GroupStart)() = nullptr;
     int (*GroupEnd)() = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
 };
 
@@ -456,6 +505,7 @@ Nccl* nccl() {
         n.Recv = (int (*)(void*, size_t, int, int, void*, cudaStream_t))dlsym(n.lib, "ncclRecv");
         n.GroupStart = (int (*)())dlsym(n.lib, "ncclGroupStart");
         n.GroupEnd = (int (*)())dlsym(n.lib, "ncclGroupEnd");
+        n.AllGather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))dlsym(n.lib, "ncclAllGather");
         n.GetErrorString = (const char* (*)(int))dlsym(n.lib, "ncclGetErrorString");
     });
     if (!n.lib || !n.GetUniqueId || !n.CommInitRank || !n.Send || !n.Recv || !n.GroupStart ||
@@ -648,6 +698,55 @@ __global__ void __launch_bounds__(32) errd_kernel(const __grid_constant__ ErrdPa
     }
 }
 
+// ---- 1..3-channel images on the 4-channel kernels: widen the source, narrow the destination ----
+template <typename T>
+__global__ void __launch_bounds__(256) widen_channels_kernel(const T* __restrict__ src, long long src_pitch,
+                                                             T* __restrict__ dst, int w, int rows, int C) {
+    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (i >= (long long)w * rows) return;
+    const int y = (int)(i / w), x = (int)(i - (long long)y * w);
+    const T* s = src + (long long)y * src_pitch + (long long)x * C;
+    T v[4] = {T(0), T(0), T(0), T(0)};
+    for (int c = 0; c < C; ++c) v[c] = s[c];
+    T* o = dst + i * 4;
+    o[0] = v[0]; o[1] = v[1]; o[2] = v[2]; o[3] = v[3];
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) narrow_channels_kernel(const T* __restrict__ src, T* __restrict__ dst,
+                                                              long long dst_pitch, int w, int rows, int C) {
+    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (i >= (long long)w * rows) return;
+    const int y = (int)(i / w), x = (int)(i - (long long)y * w);
+    const T* s = src + i * 4;
+    T* o = dst + (long long)y * dst_pitch + (long long)x * C;
+    for (int c = 0; c < C; ++c) o[c] = s[c];
+}
+
+int launch_widen(int type, const void* src, size_t src_pitch, void* dst, int w, int rows, int C, cudaStream_t st) {
+    const long long n = (long long)w * rows;
+    const unsigned g = (unsigned)((n + 255) / 256);
+    if (type == AVIRB200_U8)
+        widen_channels_kernel<unsigned char><<<g, 256, 0, st>>>((const unsigned char*)src, (long long)src_pitch, (unsigned char*)dst, w, rows, C);
+    else if (type == AVIRB200_U16)
+        widen_channels_kernel<unsigned short><<<g, 256, 0, st>>>((const unsigned short*)src, (long long)src_pitch, (unsigned short*)dst, w, rows, C);
+    else
+        widen_channels_kernel<float><<<g, 256, 0, st>>>((const float*)src, (long long)src_pitch, (float*)dst, w, rows, C);
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+int launch_narrow(int type, const void* src, void* dst, size_t dst_pitch, int w, int rows, int C, cudaStream_t st) {
+    const long long n = (long long)w * rows;
+    const unsigned g = (unsigned)((n + 255) / 256);
+    if (type == AVIRB200_U8)
+        narrow_channels_kernel<unsigned char><<<g, 256, 0, st>>>((const unsigned char*)src, (unsigned char*)dst, (long long)dst_pitch, w, rows, C);
+    else if (type == AVIRB200_U16)
+        narrow_channels_kernel<unsigned short><<<g, 256, 0, st>>>((const unsigned short*)src, (unsigned short*)dst, (long long)dst_pitch, w, rows, C);
+    else
+        narrow_channels_kernel<float><<<g, 256, 0, st>>>((const float*)src, (float*)dst, (long long)dst_pitch, w, rows, C);
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
 // ---- double image buffers: the casts upstream's pack / unpack perform, as two small kernels ----
 
 __global__ void __launch_bounds__(256) narrow_f64_kernel(const double* __restrict__ src, long long src_pitch,
@@ -686,6 +785,168 @@ size_t errd_bytes(const avirb200_plan* pl) {
     return align_up((size_t)errd_groups(pl) * d.dst_w * d.channels * 4, 256) + align_up((size_t)errd_groups(pl) * 4, 256);
 }
 
+// ---- host-call staging: one set of device buffers per device, shared by every plan ----------------
+// (a front-end object caches up to 16 plans; per-plan staging of 8K frames would hold ~1 GB each)
+struct Staging {
+    std::mutex mx; // held for the whole host call: host calls on one device run one at a time
+    void *d_src = nullptr, *d_dst = nullptr, *d_ws = nullptr;
+    size_t src_b = 0, dst_b = 0, ws_b = 0;
+};
+Staging& staging_of(int device) {
+    static Staging pool[64];
+    return pool[(unsigned)device & 63u];
+}
+int grow(void** p, size_t* have, size_t need) {
+    if (*have >= need) return 0;
+    cudaFree(*p);
+    *p = nullptr; *have = 0;
+    CUDA_TRY(cudaMalloc(p, need));
+    *have = need;
+    return 0;
+}
+// Points the plan's d_src / d_dst / d_ws at the device's staging buffers (grown to the sizes
+// asked for).  The caller holds staging_of(pl->device).mx.
+int plan_staging(avirb200_plan* pl, size_t in_bytes, size_t out_bytes, size_t ws) {
+    Staging& sg = staging_of(pl->device);
+    int r;
+    if ((r = grow(&sg.d_src, &sg.src_b, in_bytes)) != 0 || (r = grow(&sg.d_dst, &sg.dst_b, out_bytes)) != 0 ||
+        (r = grow(&sg.d_ws, &sg.ws_b, ws)) != 0)
+        return r;
+    pl->d_src = sg.d_src; pl->d_dst = sg.d_dst; pl->d_ws = sg.d_ws;
+    return 0;
+}
+
+// ---- sharded calls: peer mailboxes for the halo rows ------------------------------------------------
+// NCCL's send/recv between the two passes costs a kernel launch on every rank and runs on SMs the
+// persistent pass kernels want.  Instead every rank owns a MAILBOX in device memory that its two
+// neighbours map through CUDA IPC (handles all-gathered over the caller's communicator once per
+// plan): a rank filters the rows its neighbours need FIRST, pushes them with the copy engines
+// (peer copy over NVLink, no SM) into the neighbours' mailboxes followed by a sequence number,
+// and filters its interior rows meanwhile; before the column pass a one-warp kernel waits for
+// the neighbours' sequence numbers and the rows move from the mailbox into the workspace.
+// Two slots (call parity): a rank can be at most one call ahead of a neighbour, because its
+// column pass needs that neighbour's rows of the same call.
+//   mailbox of rank q:  [256 B: flag_from_up, flag_from_down]
+//                       slot 0: [rows from q-1: halo_up(q)] [rows from q+1: halo_down(q)]   slot 1: the same
+struct Halo {
+    void* comm = nullptr;
+    int rank = -1, nranks = 0;
+    bool usable = false;
+    char* box = nullptr;       // my mailbox
+    char* box_up = nullptr;    // rank-1's mailbox, mapped
+    char* box_down = nullptr;  // rank+1's mailbox, mapped
+    size_t up_bytes = 0, down_bytes = 0, slot_bytes = 0;             // my own layout
+    size_t nb_up_off = 0, nb_up_slot = 0, nb_up_bytes = 0;           // where my top rows go in rank-1's box
+    size_t nb_down_off = 0, nb_down_slot = 0, nb_down_bytes = 0;     // where my bottom rows go in rank+1's box
+    unsigned seq = 0;
+    unsigned* h_seq = nullptr; // pinned ring of sequence numbers the flag copies read
+};
+
+size_t align256(size_t v) { return (v + 255) / 256 * 256; }
+
+__global__ void halo_wait_kernel(const volatile unsigned* flags, unsigned seq, int need_up, int need_down) {
+    const int t = threadIdx.x;
+    if ((t == 0 && need_up) || (t == 1 && need_down)) {
+        long long spins = 0;
+        while ((int)(flags[t] - seq) < 0) {
+            if (++spins > (1ll << 31)) __trap(); // a neighbour never delivered: fail instead of hanging
+            __nanosleep(200);
+        }
+        __threadfence_system();
+    }
+}
+
+void halo_free(Halo* h) {
+    if (h == nullptr) return;
+    if (h->box_up) cudaIpcCloseMemHandle(h->box_up);
+    if (h->box_down) cudaIpcCloseMemHandle(h->box_down);
+    cudaFree(h->box);
+    cudaFreeHost(h->h_seq);
+    delete h;
+}
+
+int shard_compute(const avirb200_plan* pl, int rank, int nranks, avirb200_shard_info* info);
+
+// Collective over `comm` (every rank of the sharded call makes it): builds and maps the mailboxes.
+// Leaves h->usable false (on EVERY rank) when any rank could not: the NCCL schedule runs then.
+int halo_setup(avirb200_plan* pl, void* comm, int rank, int nranks, cudaStream_t st) {
+    Nccl* nc = nccl();
+    if (!nc) return fail(AVIRB200_ERR_NCCL, "libnccl.so.2 not loadable");
+    halo_free(pl->halo);
+    Halo* h = pl->halo = new Halo();
+    h->comm = comm; h->rank = rank; h->nranks = nranks;
+    const size_t rowb = (size_t)pl->desc.dst_w * pl->mid_ch * sizeof(float);
+    auto layout = [&](int q, size_t& upb, size_t& downb, size_t& slotb) -> int {
+        avirb200_shard_info si;
+        int r = shard_compute(pl, q, nranks, &si);
+        if (r != 0) return r;
+        upb = (size_t)si.halo_up * rowb; downb = (size_t)si.halo_down * rowb;
+        slotb = align256(upb) + align256(downb);
+        return 0;
+    };
+    int r = layout(rank, h->up_bytes, h->down_bytes, h->slot_bytes);
+    if (r != 0) return r;
+    bool ok = nc->AllGather != nullptr;
+    if (rank > 0) {
+        size_t u, d, sl;
+        if ((r = layout(rank - 1, u, d, sl)) != 0) return r;
+        h->nb_up_off = 256 + align256(u); h->nb_up_slot = sl; h->nb_up_bytes = d; // its "from below" area
+    }
+    if (rank + 1 < nranks) {
+        size_t u, d, sl;
+        if ((r = layout(rank + 1, u, d, sl)) != 0) return r;
+        h->nb_down_off = 256; h->nb_down_slot = sl; h->nb_down_bytes = u;          // its "from above" area
+    }
+    cudaIpcMemHandle_t mine;
+    std::memset(&mine, 0, sizeof mine);
+    if (ok) ok = cudaMalloc(&h->box, 256 + 2 * h->slot_bytes + 256) == cudaSuccess;
+    if (ok) ok = cudaMemset(h->box, 0, 256) == cudaSuccess;
+    if (ok) ok = cudaHostAlloc(&h->h_seq, 64 * sizeof(unsigned), cudaHostAllocPortable) == cudaSuccess;
+    if (ok) ok = cudaIpcGetMemHandle(&mine, h->box) == cudaSuccess;
+    // all-gather (handle, ok) records
+    const size_t rec = sizeof(cudaIpcMemHandle_t) + 8;
+    std::vector<char> hostrec((size_t)nranks * rec, 0);
+    char* drec = nullptr;
+    if (cudaMalloc(&drec, (size_t)nranks * rec) != cudaSuccess) { cudaGetLastError(); return fail(AVIRB200_ERR_ALLOC, "halo setup"); }
+    std::memcpy(&hostrec[(size_t)rank * rec], &mine, sizeof mine);
+    hostrec[(size_t)rank * rec + sizeof mine] = ok ? 1 : 0;
+    cudaMemcpyAsync(drec + (size_t)rank * rec, &hostrec[(size_t)rank * rec], rec, cudaMemcpyHostToDevice, st);
+    int nr = nc->AllGather ? nc->AllGather(drec + (size_t)rank * rec, drec, rec, /*ncclChar*/ 0, comm, st) : 1;
+    cudaError_t ce = cudaMemcpyAsync(hostrec.data(), drec, (size_t)nranks * rec, cudaMemcpyDeviceToHost, st);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+    cudaFree(drec);
+    if (nr != 0 || ce != cudaSuccess) { cudaGetLastError(); return fail(AVIRB200_ERR_NCCL, "halo setup: handle exchange failed"); }
+    bool all_ok = true;
+    for (int q = 0; q < nranks; ++q) all_ok = all_ok && hostrec[(size_t)q * rec + sizeof mine] == 1;
+    // second round: can every rank map its neighbours?
+    bool mapped = all_ok;
+    if (all_ok && rank > 0) {
+        cudaIpcMemHandle_t hh;
+        std::memcpy(&hh, &hostrec[(size_t)(rank - 1) * rec], sizeof hh);
+        mapped = mapped && cudaIpcOpenMemHandle((void**)&h->box_up, hh, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+    }
+    if (all_ok && rank + 1 < nranks) {
+        cudaIpcMemHandle_t hh;
+        std::memcpy(&hh, &hostrec[(size_t)(rank + 1) * rec], sizeof hh);
+        mapped = mapped && cudaIpcOpenMemHandle((void**)&h->box_down, hh, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+    }
+    cudaGetLastError();
+    std::vector<char> flags((size_t)nranks, 0);
+    char* dflag = nullptr;
+    if (cudaMalloc(&dflag, (size_t)nranks) != cudaSuccess) { cudaGetLastError(); return fail(AVIRB200_ERR_ALLOC, "halo setup"); }
+    flags[rank] = mapped ? 1 : 0;
+    cudaMemcpyAsync(dflag + rank, &flags[rank], 1, cudaMemcpyHostToDevice, st);
+    nr = nc->AllGather(dflag + rank, dflag, 1, 0, comm, st);
+    ce = cudaMemcpyAsync(flags.data(), dflag, (size_t)nranks, cudaMemcpyDeviceToHost, st);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+    cudaFree(dflag);
+    if (nr != 0 || ce != cudaSuccess) { cudaGetLastError(); return fail(AVIRB200_ERR_NCCL, "halo setup: status exchange failed"); }
+    bool every = true;
+    for (int q = 0; q < nranks; ++q) every = every && flags[q] == 1;
+    h->usable = every;
+    return 0;
+}
+
 bool plan_has_f64(const avirb200_plan* pl) { // plans that only run as a whole image through resize_device / _host
     return pl->io_in_type == AVIRB200_F64 || pl->io_out_type == AVIRB200_F64 || pl->errd;
 }
@@ -694,7 +955,30 @@ bool plan_has_f64(const avirb200_plan* pl) { // plans that only run as a whole i
 
 extern "C" {
 
-void avirb200_debug_force_generic(int mode) { g_kernel_mode = (mode == 1 || mode == 2) ? mode : 0; }
+int avirb200_plan_set_option(avirb200_plan* pl, int option, int value) {
+    if (pl == nullptr) return fail(AVIRB200_ERR_BAD_ARG, "null argument");
+    switch (option) {
+    case AVIRB200_OPT_KERNEL_FAMILY: pl->opt_family = (value == 1 || value == 2) ? value : 0; return 0;
+    case AVIRB200_OPT_STREAM_VARIANT_H: pl->opt_var_h = (value >= 0 && value < 3) ? value : -1; return 0;
+    case AVIRB200_OPT_STREAM_VARIANT_V: pl->opt_var_v = (value >= 0 && value < 3) ? value : -1; return 0;
+    case AVIRB200_OPT_HOST_BANDS: pl->opt_host_bands = value >= 1 ? value : -1; return 0;
+    case AVIRB200_OPT_OVERLAP_HALO: pl->opt_overlap = (value == 0) ? 0 : 1; return 0;
+    case AVIRB200_OPT_ALL_STREAM_CHAINS: {
+        const int on = value > 0 ? 1 : 0;
+        if (on != pl->opt_all_chains) { // re-decide which passes run on the streaming kernel (host arithmetic only)
+            pl->opt_all_chains = on;
+            pl->stream_h.chain = pl->stream_v.chain = 0;
+            const avirb200_plan_desc& d = pl->desc;
+            const int ch = pl->pad4 ? 4 : d.channels;
+            if (avs::stream_row_source_ok(d))
+                avs::stream_plan_axis(pl->h.desc, d.sum_mode, ch, pl->stream_h, on != 0);
+            avs::stream_plan_axis(pl->v.desc, d.sum_mode, ch, pl->stream_v, on != 0);
+        }
+        return 0;
+    }
+    default: return fail(AVIRB200_ERR_BAD_ARG, "unknown option");
+    }
+}
 
 int avirb200_plan_kernel_paths(const avirb200_plan* pl) {
     if (pl == nullptr) return 0;
@@ -762,8 +1046,14 @@ int avirb200_plan_create(const avirb200_plan_desc* desc, avirb200_plan** out) {
         pl->desc.out_type = AVIRB200_F32;
         // errd_kernel's blocks (one warp per 32 rows) wait for their predecessor: keep all of them
         // resident at once (148 SMs x 32 blocks) instead of relying on in-order block dispatch
-        if ((desc->dst_h + 31) / 32 > 4096)
-            return fail(AVIRB200_ERR_UNSUPPORTED, "error diffusion: more than 131072 destination rows");
+        // (32 one-warp blocks per SM; the SM count of the current device, where the plan will live)
+        int cur = 0, sms = 0;
+        if (cudaGetDevice(&cur) != cudaSuccess ||
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cur) != cudaSuccess || sms < 1)
+            sms = 1;
+        if ((desc->dst_h + 31) / 32 > sms * 32)
+            return fail(AVIRB200_ERR_UNSUPPORTED, "error diffusion: more destination rows than the device "
+                                                   "keeps resident as one-warp blocks (32 rows each)");
     }
     int r = copy_axis_host(pl->h, desc->h);
     if (r != 0) return r;
@@ -789,12 +1079,44 @@ int avirb200_plan_create(const avirb200_plan_desc* desc, avirb200_plan** out) {
     pl->cfg_h = choose_generic_config(pl->h.hostdev, desc->channels, 0, desc->dst_w);
     pl->cfg_v = choose_generic_config(pl->v.hostdev, desc->channels, 0, desc->dst_h);
     // (pl->desc, not *desc: the kernels' element types, see io_in_type / io_out_type)
-    fast_plan_init(pl->fast, pl->h.hostdev, pl->v.hostdev, pl->desc);
-    const char* up2e = getenv("AVIRB200_STREAM_ALL"); // tuning switch, see stream_plan_axis()
-    const bool up2 = up2e && up2e[0] == '1';
+    // 1..3 channels: can both passes run on the 4-channel kernels (widened copies)?  Not for plans
+    // with double buffers or error diffusion (they keep the image's own channel count throughout).
+    avirb200_plan_desc d4 = pl->desc;
+    const bool try4 = desc->channels < 4 && !(desc->in_type == AVIRB200_F64 || desc->out_type == AVIRB200_F64 || pl->errd);
+    if (try4) d4.channels = 4;
+    pl->mid_ch = desc->channels;
+    fast_plan_init(pl->fast, pl->h.hostdev, pl->v.hostdev, d4);
+    // (pl->h.desc / pl->v.desc: the copies whose table pointers stay valid for the plan's life)
+    for (int i = 0; i < pl->h.desc.nsteps; ++i) {
+        avirb200_step_desc& sd = pl->h.desc.steps[i];
+        sd.taps = pl->h.taps[i].data(); sd.src_pos = pl->h.src_pos[i].data();
+        sd.phase = pl->h.phase[i].data(); sd.frac = pl->h.frac[i].data();
+        sd.prefix_dc = pl->h.pdc[i].data(); sd.suffix_dc = pl->h.sdc[i].data();
+    }
+    for (int i = 0; i < pl->v.desc.nsteps; ++i) {
+        avirb200_step_desc& sd = pl->v.desc.steps[i];
+        sd.taps = pl->v.taps[i].data(); sd.src_pos = pl->v.src_pos[i].data();
+        sd.phase = pl->v.phase[i].data(); sd.frac = pl->v.frac[i].data();
+        sd.prefix_dc = pl->v.pdc[i].data(); sd.suffix_dc = pl->v.sdc[i].data();
+    }
     if (avs::stream_row_source_ok(pl->desc))
-        avs::stream_plan_axis(desc->h, desc->sum_mode, desc->channels, pl->stream_h, up2);
-    avs::stream_plan_axis(desc->v, desc->sum_mode, desc->channels, pl->stream_v, up2);
+        avs::stream_plan_axis(pl->h.desc, desc->sum_mode, d4.channels, pl->stream_h, false);
+    avs::stream_plan_axis(pl->v.desc, desc->sum_mode, d4.channels, pl->stream_v, false);
+    if (try4) {
+        const bool h4 = pl->stream_h.chain != 0 || pl->fast.h_ok, v4 = pl->stream_v.chain != 0 || pl->fast.v_ok;
+        if (h4 && v4) {
+            pl->pad4 = true;
+            pl->mid_ch = 4;
+        } else { // the image's own channel count on the generic kernel
+            pl->stream_h.chain = pl->stream_v.chain = 0;
+            pl->fast.h_ok = pl->fast.v_ok = false;
+        }
+    }
+    {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, pl->device) == cudaSuccess && n > 0)
+            pl->sm_count = n;
+    }
     *out = pl.release();
     return 0;
 }
@@ -802,10 +1124,11 @@ int avirb200_plan_create(const avirb200_plan_desc* desc, avirb200_plan** out) {
 void avirb200_plan_destroy(avirb200_plan* pl) {
     if (pl == nullptr) return;
     cudaFree(pl->arena);
-    cudaFree(pl->d_src);
-    cudaFree(pl->d_dst);
-    cudaFree(pl->d_ws);
     fast_plan_free(pl->fast);
+    halo_free(pl->halo);
+    if (pl->stream_x) cudaStreamDestroy(pl->stream_x);
+    if (pl->ev_x0) cudaEventDestroy(pl->ev_x0);
+    if (pl->ev_x1) cudaEventDestroy(pl->ev_x1);
     if (pl->stream) cudaStreamDestroy(pl->stream);
     if (pl->stream_in) cudaStreamDestroy(pl->stream_in);
     if (pl->stream_out) cudaStreamDestroy(pl->stream_out);
@@ -817,8 +1140,8 @@ void avirb200_plan_destroy(avirb200_plan* pl) {
 int avirb200_plan_workspace_bytes(const avirb200_plan* pl, size_t* bytes) {
     if (pl == nullptr || bytes == nullptr) return fail(AVIRB200_ERR_BAD_ARG, "null argument");
     const avirb200_plan_desc& d = pl->desc;
-    *bytes = align_up((size_t)d.dst_w * d.src_h * d.channels * sizeof(float), 256) + f64_in_bytes(pl) +
-             f64_out_bytes(pl) + errd_bytes(pl);
+    *bytes = align_up((size_t)d.dst_w * d.src_h * pl->mid_ch * sizeof(float), 256) + f64_in_bytes(pl) +
+             f64_out_bytes(pl) + errd_bytes(pl) + pad4_src_bytes(pl, d.src_h) + pad4_dst_bytes(pl, d.dst_h);
     return 0;
 }
 
@@ -831,11 +1154,20 @@ int avirb200_resize_device(const avirb200_plan* pl, const void* d_src, size_t sr
     const avirb200_plan_desc& d = pl->desc;
     if (src_pitch < (size_t)d.src_w * d.channels || dst_pitch < (size_t)d.dst_w * d.channels)
         return fail(AVIRB200_ERR_BAD_ARG, "pitch smaller than a row");
+    {
+        int cur = -1;
+        if (cudaGetDevice(&cur) != cudaSuccess || cur != pl->device)
+            return fail(AVIRB200_ERR_BAD_ARG, "the current device is not the plan's device");
+    }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     int launches = 0;
     // double buffers: float copies live behind the intermediate in the workspace
     char* wsb = static_cast<char*>(d_ws);
-    float* in32 = reinterpret_cast<float*>(wsb + align_up((size_t)d.dst_w * d.src_h * d.channels * 4, 256));
+    float* in32 = reinterpret_cast<float*>(wsb + align_up((size_t)d.dst_w * d.src_h * pl->mid_ch * 4, 256));
+    // (1..3-channel plans on the 4-channel kernels have no double buffers / error diffusion: their
+    // scratch copies start where in32 would)
+    char* src4 = reinterpret_cast<char*>(in32);
+    char* dst4 = src4 + pad4_src_bytes(pl, d.src_h);
     float* out32 = reinterpret_cast<float*>(reinterpret_cast<char*>(in32) + f64_in_bytes(pl));
     const void* ksrc = d_src;
     size_t ksrc_pitch = src_pitch;
@@ -854,10 +1186,10 @@ int avirb200_resize_device(const avirb200_plan* pl, const void* d_src, size_t sr
         kdst = out32;
         kdst_pitch = (size_t)d.dst_w * d.channels;
     }
-    int r = run_row_pass(pl, ksrc, ksrc_pitch, static_cast<float*>(d_ws), d.src_h, st, &launches);
+    int r = run_row_pass(pl, ksrc, ksrc_pitch, static_cast<float*>(d_ws), d.src_h, st, &launches, src4);
     if (r != 0) return r;
     r = run_col_pass(pl, static_cast<const float*>(d_ws), 0, kdst, kdst_pitch, 0, d.dst_h, st,
-                     &launches);
+                     &launches, dst4);
     if (r == 0 && pl->io_out_type == AVIRB200_F64) {
         const int re = d.dst_w * d.channels;
         const long long n = (long long)re * d.dst_h;
@@ -899,8 +1231,10 @@ int avirb200_row_pass_device(const avirb200_plan* pl, const void* d_src, size_t 
         return fail(AVIRB200_ERR_BAD_ARG, "null argument");
     if (plan_has_f64(pl)) return fail(AVIRB200_ERR_UNSUPPORTED, "per-pass entry points: no double buffers, no error diffusion");
     int launches = 0;
+    const avirb200_plan_desc& d = pl->desc;
+    char* src4 = static_cast<char*>(d_ws) + align_up((size_t)d.dst_w * d.src_h * pl->mid_ch * 4, 256);
     return run_row_pass(pl, d_src, src_pitch, static_cast<float*>(d_ws), pl->desc.src_h,
-                        static_cast<cudaStream_t>(stream), &launches);
+                        static_cast<cudaStream_t>(stream), &launches, src4);
 }
 
 int avirb200_col_pass_device(const avirb200_plan* pl, const void* d_ws, void* d_dst,
@@ -909,8 +1243,26 @@ int avirb200_col_pass_device(const avirb200_plan* pl, const void* d_ws, void* d_
         return fail(AVIRB200_ERR_BAD_ARG, "null argument");
     if (plan_has_f64(pl)) return fail(AVIRB200_ERR_UNSUPPORTED, "per-pass entry points: no double buffers, no error diffusion");
     int launches = 0;
+    const avirb200_plan_desc& d = pl->desc;
+    char* dst4 = static_cast<char*>(const_cast<void*>(d_ws)) + align_up((size_t)d.dst_w * d.src_h * pl->mid_ch * 4, 256) +
+                 pad4_src_bytes(pl, d.src_h);
     return run_col_pass(pl, static_cast<const float*>(d_ws), 0, d_dst, dst_pitch, 0,
-                        pl->desc.dst_h, static_cast<cudaStream_t>(stream), &launches);
+                        pl->desc.dst_h, static_cast<cudaStream_t>(stream), &launches, dst4);
+}
+
+int avirb200_resize_device_batch(const avirb200_plan* pl, int n, const void* const* d_srcs, size_t src_pitch,
+                                 void* const* d_dsts, size_t dst_pitch, void* d_ws, void* stream) {
+    if (pl == nullptr || d_srcs == nullptr || d_dsts == nullptr || d_ws == nullptr || n < 0)
+        return fail(AVIRB200_ERR_BAD_ARG, "bad argument");
+    int total = 0;
+    for (int i = 0; i < n; ++i) {
+        // frames share the workspace: the stream keeps frame i's column pass ahead of frame i+1's row pass
+        const int r = avirb200_resize_device(pl, d_srcs[i], src_pitch, d_dsts[i], dst_pitch, d_ws, stream);
+        if (r != 0) return r;
+        total += pl->last_launches;
+    }
+    pl->last_launches = total;
+    return 0;
 }
 
 int avirb200_resize_host(avirb200_plan* pl, const void* h_src, size_t src_pitch, void* h_dst,
@@ -919,27 +1271,29 @@ int avirb200_resize_host(avirb200_plan* pl, const void* h_src, size_t src_pitch,
         return fail(AVIRB200_ERR_BAD_ARG, "null argument");
     const avirb200_plan_desc& d = pl->desc;
     std::lock_guard<std::mutex> lk(pl->mx);
-    CUDA_TRY(cudaSetDevice(pl->device));
+    // the call runs on the plan's device; the caller's current device is restored on every exit
+    struct DeviceGuard {
+        int prev = -1;
+        ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+    } guard;
+    {
+        int cur = -1;
+        CUDA_TRY(cudaGetDevice(&cur));
+        if (cur != pl->device) {
+            CUDA_TRY(cudaSetDevice(pl->device));
+            guard.prev = cur;
+        }
+    }
+    std::lock_guard<std::mutex> sl(staging_of(pl->device).mx);
     const size_t in_row = (size_t)d.src_w * d.channels * dtype_size(pl->io_in_type);
     const size_t out_row = (size_t)d.dst_w * d.channels * dtype_size(pl->io_out_type);
     const size_t in_bytes = in_row * d.src_h, out_bytes = out_row * d.dst_h;
     size_t ws = 0;
     avirb200_plan_workspace_bytes(pl, &ws);
     if (pl->stream == nullptr) CUDA_TRY(cudaStreamCreateWithFlags(&pl->stream, cudaStreamNonBlocking));
-    if (pl->d_src_bytes < in_bytes) {
-        cudaFree(pl->d_src); pl->d_src = nullptr; pl->d_src_bytes = 0;
-        CUDA_TRY(cudaMalloc(&pl->d_src, in_bytes));
-        pl->d_src_bytes = in_bytes;
-    }
-    if (pl->d_dst_bytes < out_bytes) {
-        cudaFree(pl->d_dst); pl->d_dst = nullptr; pl->d_dst_bytes = 0;
-        CUDA_TRY(cudaMalloc(&pl->d_dst, out_bytes));
-        pl->d_dst_bytes = out_bytes;
-    }
-    if (pl->d_ws_bytes < ws) {
-        cudaFree(pl->d_ws); pl->d_ws = nullptr; pl->d_ws_bytes = 0;
-        CUDA_TRY(cudaMalloc(&pl->d_ws, ws));
-        pl->d_ws_bytes = ws;
+    {
+        const int r0 = plan_staging(pl, in_bytes, out_bytes, ws);
+        if (r0 != 0) return r0;
     }
     const size_t in_el = dtype_size(pl->io_in_type), out_el = dtype_size(pl->io_out_type);
     // Pipelined form for large images: the image is cut into row bands (the multi-GPU band
@@ -950,7 +1304,7 @@ int avirb200_resize_host(avirb200_plan* pl, const void* h_src, size_t src_pitch,
     // The arithmetic does not depend on the banding (tests: 8-band schedule == unsharded bits).
     int nb = (int)(in_bytes >> 25); // bands of >= 32 MiB of source
     if (nb > 16) nb = 16;
-    if (const char* e = getenv("AVIRB200_HOST_BANDS")) nb = atoi(e); // test / tuning switch
+    if (pl->opt_host_bands >= 1) nb = pl->opt_host_bands; // test / tuning option
     {   // an aliased or overlapping destination (upstream allows NewBuf == SrcBuf) must not be
         // written before the whole source has been read
         const char* s0 = static_cast<const char*>(h_src);
@@ -978,20 +1332,28 @@ int avirb200_resize_host(avirb200_plan* pl, const void* h_src, size_t src_pitch,
             CUDA_TRY(cudaEventCreateWithFlags(&e1, cudaEventDisableTiming));
             pl->ev_out.push_back(e1);
         }
-        const size_t rowf = (size_t)d.dst_w * d.channels;
-        const size_t dsrc_pitch = (size_t)d.src_w * d.channels, ddst_pitch = rowf;
+        const size_t rowf = (size_t)d.dst_w * pl->mid_ch;
+        const size_t dsrc_pitch = (size_t)d.src_w * d.channels, ddst_pitch = (size_t)d.dst_w * d.channels;
+        char* src4 = static_cast<char*>(pl->d_ws) + align_up((size_t)d.dst_w * d.src_h * pl->mid_ch * 4, 256);
+        char* dst4 = src4 + pad4_src_bytes(pl, d.src_h);
+        const size_t src4_row = (size_t)d.src_w * 4 * in_el, dst4_row = (size_t)d.dst_w * 4 * out_el;
         int launches = 0;
-        for (int b = 0; b < nb; ++b) {
+        // (copies are issued band by band BETWEEN the kernel launches: with pageable host memory a
+        // copy call returns only when its data has moved, and the GPU should be busy meanwhile)
+        auto copy_in = [&](int b) -> int {
             CUDA_TRY(cudaMemcpy2DAsync(static_cast<char*>(pl->d_src) + (size_t)si[b].src_row0 * in_row, in_row,
                                        static_cast<const char*>(h_src) + (size_t)si[b].src_row0 * src_pitch * in_el,
                                        src_pitch * in_el, in_row, si[b].src_rows, cudaMemcpyHostToDevice,
                                        pl->stream_in));
             CUDA_TRY(cudaEventRecord(pl->ev_in[b], pl->stream_in));
-        }
+            return 0;
+        };
+        { const int r0 = copy_in(0); if (r0 != 0) return r0; }
         auto col_band = [&](int b) -> int {
             char* dd = static_cast<char*>(pl->d_dst) + (size_t)si[b].dst_row0 * out_row;
             int r = run_col_pass(pl, static_cast<const float*>(pl->d_ws), 0, dd, ddst_pitch, si[b].dst_row0,
-                                 si[b].dst_row0 + si[b].dst_rows, pl->stream, &launches);
+                                 si[b].dst_row0 + si[b].dst_rows, pl->stream, &launches,
+                                 dst4 + (size_t)si[b].dst_row0 * dst4_row);
             if (r != 0) return r;
             CUDA_TRY(cudaEventRecord(pl->ev_out[b], pl->stream));
             CUDA_TRY(cudaStreamWaitEvent(pl->stream_out, pl->ev_out[b], 0));
@@ -1001,10 +1363,11 @@ int avirb200_resize_host(avirb200_plan* pl, const void* h_src, size_t src_pitch,
             return 0;
         };
         for (int b = 0; b < nb; ++b) {
+            if (b + 1 < nb) { const int r0 = copy_in(b + 1); if (r0 != 0) return r0; }
             CUDA_TRY(cudaStreamWaitEvent(pl->stream, pl->ev_in[b], 0));
             int r = run_row_pass(pl, static_cast<const char*>(pl->d_src) + (size_t)si[b].src_row0 * in_row,
                                  dsrc_pitch, static_cast<float*>(pl->d_ws) + (size_t)si[b].src_row0 * rowf,
-                                 si[b].src_rows, pl->stream, &launches);
+                                 si[b].src_rows, pl->stream, &launches, src4 + (size_t)si[b].src_row0 * src4_row);
             if (r != 0) return r;
             if (b > 0 && (r = col_band(b - 1)) != 0) return r; // needs rows of bands b-2 .. b only
         }
@@ -1030,7 +1393,10 @@ int avirb200_resize_host(avirb200_plan* pl, const void* h_src, size_t src_pitch,
 
 int avirb200_shard_query(const avirb200_plan* pl, int rank, int nranks, avirb200_shard_info* info) {
     if (pl == nullptr || info == nullptr) return fail(AVIRB200_ERR_BAD_ARG, "null argument");
-    return shard_compute(pl, rank, nranks, info);
+    const int r = shard_compute(pl, rank, nranks, info);
+    // (the tile kernel's table of this destination range: built now, not inside the first launch)
+    if (r == 0) fast_prepare_range(pl->fast, info->dst_row0, info->dst_row0 + info->dst_rows);
+    return r;
 }
 
 int avirb200_shard_workspace_bytes(const avirb200_plan* pl, int rank, int nranks, size_t* bytes) {
@@ -1038,7 +1404,9 @@ int avirb200_shard_workspace_bytes(const avirb200_plan* pl, int rank, int nranks
     avirb200_shard_info si;
     int r = shard_compute(pl, rank, nranks, &si);
     if (r != 0) return r;
-    *bytes = (size_t)si.need_rows * pl->desc.dst_w * pl->desc.channels * sizeof(float);
+    fast_prepare_range(pl->fast, si.dst_row0, si.dst_row0 + si.dst_rows);
+    *bytes = align_up((size_t)si.need_rows * pl->desc.dst_w * pl->mid_ch * sizeof(float), 256) +
+             pad4_src_bytes(pl, si.src_rows) + pad4_dst_bytes(pl, si.dst_rows);
     return 0;
 }
 
@@ -1063,52 +1431,160 @@ void avirb200_comm_destroy(void* comm) {
     if (nc && nc->CommDestroy && comm) nc->CommDestroy(comm);
 }
 
-int avirb200_resize_sharded(const avirb200_plan* pl, void* comm, int rank, int nranks,
+int avirb200_resize_sharded(const avirb200_plan* cpl, void* comm, int rank, int nranks,
                             const void* d_src, size_t src_pitch, void* d_dst, size_t dst_pitch,
                             void* d_ws, void* stream) {
-    if (pl == nullptr || d_src == nullptr || d_dst == nullptr || d_ws == nullptr)
+    if (cpl == nullptr || d_src == nullptr || d_dst == nullptr || d_ws == nullptr)
         return fail(AVIRB200_ERR_BAD_ARG, "null argument");
+    avirb200_plan* pl = const_cast<avirb200_plan*>(cpl); // (exchange state is created on first use)
     if (plan_has_f64(pl)) return fail(AVIRB200_ERR_UNSUPPORTED, "sharded calls: no double buffers, no error diffusion");
+    { int cur = -1; if (cudaGetDevice(&cur) != cudaSuccess || cur != pl->device) return fail(AVIRB200_ERR_BAD_ARG, "the current device is not the plan's device"); }
     avirb200_shard_info si;
     int r = shard_compute(pl, rank, nranks, &si);
     if (r != 0) return r;
     const avirb200_plan_desc& d = pl->desc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const size_t rowf = (size_t)d.dst_w * d.channels; // floats per intermediate row
+    const size_t rowf = (size_t)d.dst_w * pl->mid_ch; // floats per intermediate row
+    const size_t in_el = dtype_size(d.in_type);
     float* mid = static_cast<float*>(d_ws);
     float* own = mid + (size_t)si.halo_up * rowf;
+    char* src4 = static_cast<char*>(d_ws) + align_up((size_t)si.need_rows * rowf * sizeof(float), 256);
+    char* dst4 = src4 + pad4_src_bytes(pl, si.src_rows);
+    const size_t src4_row = (size_t)d.src_w * 4 * in_el;
     int launches = 0;
-    r = run_row_pass(pl, d_src, src_pitch, own, si.src_rows, st, &launches);
-    if (r != 0) return r;
-    if (nranks > 1) {
-        if (comm == nullptr) return fail(AVIRB200_ERR_BAD_ARG, "sharded resize needs a communicator");
-        Nccl* nc = nccl();
-        if (!nc) return fail(AVIRB200_ERR_NCCL, "libnccl.so.2 not loadable");
-        // What the neighbours need from this rank is symmetric information: compute theirs.
-        avirb200_shard_info up, down;
-        if (rank > 0) { r = shard_compute(pl, rank - 1, nranks, &up); if (r != 0) return r; }
-        if (rank + 1 < nranks) { r = shard_compute(pl, rank + 1, nranks, &down); if (r != 0) return r; }
-        NCCL_TRY(nc->GroupStart());
-        if (rank > 0) {
-            if (up.halo_down > 0) // my first rows go up
-                NCCL_TRY(nc->Send(own, (size_t)up.halo_down * rowf, 7, rank - 1, comm, st));
-            if (si.halo_up > 0)
-                NCCL_TRY(nc->Recv(mid, (size_t)si.halo_up * rowf, 7, rank - 1, comm, st));
-        }
-        if (rank + 1 < nranks) {
-            if (down.halo_up > 0) // my last rows go down
-                NCCL_TRY(nc->Send(own + (size_t)(si.src_rows - down.halo_up) * rowf,
-                                  (size_t)down.halo_up * rowf, 7, rank + 1, comm, st));
-            if (si.halo_down > 0)
-                NCCL_TRY(nc->Recv(own + (size_t)si.src_rows * rowf, (size_t)si.halo_down * rowf, 7,
-                                  rank + 1, comm, st));
-        }
-        NCCL_TRY(nc->GroupEnd());
+    if (nranks <= 1) {
+        r = run_row_pass(pl, d_src, src_pitch, own, si.src_rows, st, &launches, src4);
+        if (r != 0) return r;
+        r = run_col_pass(pl, mid, si.need_row0, d_dst, dst_pitch, si.dst_row0, si.dst_row0 + si.dst_rows, st, &launches, dst4);
+        pl->last_launches = launches;
+        return r;
     }
-    r = run_col_pass(pl, mid, si.need_row0, d_dst, dst_pitch, si.dst_row0,
-                     si.dst_row0 + si.dst_rows, st, &launches);
+    if (comm == nullptr) return fail(AVIRB200_ERR_BAD_ARG, "sharded resize needs a communicator");
+    Nccl* nc = nccl();
+    if (!nc) return fail(AVIRB200_ERR_NCCL, "libnccl.so.2 not loadable");
+    // What the neighbours need from this rank is symmetric information: compute theirs.
+    avirb200_shard_info up, down;
+    std::memset(&up, 0, sizeof up); std::memset(&down, 0, sizeof down);
+    if (rank > 0) { r = shard_compute(pl, rank - 1, nranks, &up); if (r != 0) return r; }
+    if (rank + 1 < nranks) { r = shard_compute(pl, rank + 1, nranks, &down); if (r != 0) return r; }
+    const int top_rows = (rank > 0) ? up.halo_down : 0;              // my first rows go up
+    const int bot_rows = (rank + 1 < nranks) ? down.halo_up : 0;     // my last rows go down
+
+    std::lock_guard<std::mutex> lk(pl->mx);
+    if (pl->opt_overlap) {
+        if (pl->halo == nullptr || pl->halo->comm != comm || pl->halo->rank != rank || pl->halo->nranks != nranks) {
+            r = halo_setup(pl, comm, rank, nranks, st); // collective, once per plan
+            if (r != 0) return r;
+        }
+    }
+    Halo* h = (pl->opt_overlap && pl->halo && pl->halo->usable) ? pl->halo : nullptr;
+    if (h != nullptr) {
+        if (pl->stream_x == nullptr) CUDA_TRY(cudaStreamCreateWithFlags(&pl->stream_x, cudaStreamNonBlocking));
+        if (pl->ev_x0 == nullptr) CUDA_TRY(cudaEventCreateWithFlags(&pl->ev_x0, cudaEventDisableTiming));
+        if (pl->ev_x1 == nullptr) CUDA_TRY(cudaEventCreateWithFlags(&pl->ev_x1, cudaEventDisableTiming));
+        const unsigned seq = ++h->seq;
+        const int slot = (int)(seq & 1u);
+        unsigned* hs = &h->h_seq[seq & 63u];
+        *hs = seq;
+        const char* srcb = static_cast<const char*>(d_src);
+        auto rows_pass = [&](int row0, int nrows) -> int {
+            if (nrows <= 0) return 0;
+            return run_row_pass(pl, srcb + (size_t)row0 * src_pitch * in_el, src_pitch, own + (size_t)row0 * rowf,
+                                nrows, st, &launches, src4 + (size_t)row0 * src4_row);
+        };
+        // 1. the rows the neighbours need, 2. their push on the exchange stream, 3. the interior rows
+        const bool split = top_rows + bot_rows < si.src_rows;
+        if (split) {
+            if ((r = rows_pass(0, top_rows)) != 0) return r;
+            if ((r = rows_pass(si.src_rows - bot_rows, bot_rows)) != 0) return r;
+        } else if ((r = rows_pass(0, si.src_rows)) != 0) {
+            return r;
+        }
+        CUDA_TRY(cudaEventRecord(pl->ev_x0, st));
+        CUDA_TRY(cudaStreamWaitEvent(pl->stream_x, pl->ev_x0, 0));
+        if (top_rows > 0) {
+            char* dst = h->box_up + h->nb_up_off + (size_t)slot * h->nb_up_slot;
+            CUDA_TRY(cudaMemcpyAsync(dst, own, (size_t)top_rows * rowf * 4, cudaMemcpyDefault, pl->stream_x));
+            CUDA_TRY(cudaMemcpyAsync(h->box_up + 4, hs, 4, cudaMemcpyDefault, pl->stream_x)); // its flag_from_down
+        }
+        if (bot_rows > 0) {
+            char* dst = h->box_down + h->nb_down_off + (size_t)slot * h->nb_down_slot;
+            CUDA_TRY(cudaMemcpyAsync(dst, own + (size_t)(si.src_rows - bot_rows) * rowf, (size_t)bot_rows * rowf * 4,
+                                     cudaMemcpyDefault, pl->stream_x));
+            CUDA_TRY(cudaMemcpyAsync(h->box_down, hs, 4, cudaMemcpyDefault, pl->stream_x));    // its flag_from_up
+        }
+        CUDA_TRY(cudaEventRecord(pl->ev_x1, pl->stream_x));
+        if (split && (r = rows_pass(top_rows, si.src_rows - top_rows - bot_rows)) != 0) return r;
+        // 4. the neighbours' rows: wait for their sequence numbers, mailbox -> workspace
+        const int need_up = (rank > 0 && si.halo_up > 0) ? 1 : 0;
+        const int need_down = (rank + 1 < nranks && si.halo_down > 0) ? 1 : 0;
+        if (need_up || need_down) {
+            halo_wait_kernel<<<1, 32, 0, st>>>(reinterpret_cast<const volatile unsigned*>(h->box), seq, need_up, need_down);
+            ++launches;
+            CUDA_TRY(cudaGetLastError());
+            const char* sl = h->box + 256 + (size_t)slot * h->slot_bytes;
+            if (need_up) CUDA_TRY(cudaMemcpyAsync(mid, sl, h->up_bytes, cudaMemcpyDeviceToDevice, st));
+            if (need_down)
+                CUDA_TRY(cudaMemcpyAsync(own + (size_t)si.src_rows * rowf, sl + align256(h->up_bytes), h->down_bytes,
+                                         cudaMemcpyDeviceToDevice, st));
+        }
+        r = run_col_pass(pl, mid, si.need_row0, d_dst, dst_pitch, si.dst_row0, si.dst_row0 + si.dst_rows, st, &launches, dst4);
+        // the pushes read this call's workspace: the caller's stream does not end before them
+        CUDA_TRY(cudaStreamWaitEvent(st, pl->ev_x1, 0));
+        pl->last_launches = launches;
+        return r;
+    }
+    // NCCL schedule: whole row pass, send/recv group, column pass, one stream
+    r = run_row_pass(pl, d_src, src_pitch, own, si.src_rows, st, &launches, src4);
+    if (r != 0) return r;
+    NCCL_TRY(nc->GroupStart());
+    if (rank > 0) {
+        if (top_rows > 0) NCCL_TRY(nc->Send(own, (size_t)top_rows * rowf, 7, rank - 1, comm, st));
+        if (si.halo_up > 0) NCCL_TRY(nc->Recv(mid, (size_t)si.halo_up * rowf, 7, rank - 1, comm, st));
+    }
+    if (rank + 1 < nranks) {
+        if (bot_rows > 0)
+            NCCL_TRY(nc->Send(own + (size_t)(si.src_rows - bot_rows) * rowf, (size_t)bot_rows * rowf, 7, rank + 1, comm, st));
+        if (si.halo_down > 0)
+            NCCL_TRY(nc->Recv(own + (size_t)si.src_rows * rowf, (size_t)si.halo_down * rowf, 7, rank + 1, comm, st));
+    }
+    NCCL_TRY(nc->GroupEnd());
+    r = run_col_pass(pl, mid, si.need_row0, d_dst, dst_pitch, si.dst_row0, si.dst_row0 + si.dst_rows, st, &launches, dst4);
     pl->last_launches = launches;
     return r;
+}
+
+int avirb200_resize_sharded_host(avirb200_plan* pl, void* comm, int rank, int nranks, const void* h_src,
+                                 size_t src_pitch, void* h_dst, size_t dst_pitch) {
+    if (pl == nullptr || h_src == nullptr || h_dst == nullptr) return fail(AVIRB200_ERR_BAD_ARG, "null argument");
+    if (plan_has_f64(pl)) return fail(AVIRB200_ERR_UNSUPPORTED, "sharded calls: no double buffers, no error diffusion");
+    const avirb200_plan_desc& d = pl->desc;
+    avirb200_shard_info si;
+    int r = shard_compute(pl, rank, nranks, &si);
+    if (r != 0) return r;
+    size_t ws = 0;
+    if ((r = avirb200_shard_workspace_bytes(pl, rank, nranks, &ws)) != 0) return r;
+    const size_t in_row = (size_t)d.src_w * d.channels * dtype_size(d.in_type);
+    const size_t out_row = (size_t)d.dst_w * d.channels * dtype_size(d.out_type);
+    {
+        std::lock_guard<std::mutex> lk(pl->mx);
+        int cur = -1;
+        if (cudaGetDevice(&cur) != cudaSuccess || cur != pl->device)
+            return fail(AVIRB200_ERR_BAD_ARG, "the current device is not the plan's device");
+        if (pl->stream == nullptr) CUDA_TRY(cudaStreamCreateWithFlags(&pl->stream, cudaStreamNonBlocking));
+    }
+    std::lock_guard<std::mutex> sl(staging_of(pl->device).mx);
+    r = plan_staging(pl, in_row * si.src_rows, out_row * si.dst_rows, ws);
+    if (r != 0) return r;
+    CUDA_TRY(cudaMemcpy2DAsync(pl->d_src, in_row, h_src, src_pitch * dtype_size(d.in_type), in_row, si.src_rows,
+                               cudaMemcpyHostToDevice, pl->stream));
+    r = avirb200_resize_sharded(pl, comm, rank, nranks, pl->d_src, (size_t)d.src_w * d.channels, pl->d_dst,
+                                (size_t)d.dst_w * d.channels, pl->d_ws, pl->stream);
+    if (r != 0) return r;
+    CUDA_TRY(cudaMemcpy2DAsync(h_dst, dst_pitch * dtype_size(d.out_type), pl->d_dst, out_row, out_row, si.dst_rows,
+                               cudaMemcpyDeviceToHost, pl->stream));
+    CUDA_TRY(cudaStreamSynchronize(pl->stream));
+    return 0;
 }
 
 int avirb200_resize_sharded_local(const avirb200_plan* pl, int nranks, const void* d_src,
@@ -1119,22 +1595,25 @@ int avirb200_resize_sharded_local(const avirb200_plan* pl, int nranks, const voi
     if (plan_has_f64(pl)) return fail(AVIRB200_ERR_UNSUPPORTED, "sharded calls: no double buffers, no error diffusion");
     const avirb200_plan_desc& d = pl->desc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const size_t rowf = (size_t)d.dst_w * d.channels;
+    const size_t rowf = (size_t)d.dst_w * pl->mid_ch;
     std::vector<avirb200_shard_info> si(nranks);
     std::vector<float*> mid(nranks);
-    float* base = static_cast<float*>(d_ws);
-    for (int r = 0; r < nranks; ++r) {
+    std::vector<char*> src4(nranks), dst4(nranks);
+    char* base = static_cast<char*>(d_ws);
+    for (int r = 0; r < nranks; ++r) { // every band's segment: as avirb200_shard_workspace_bytes lays it out
         int e = shard_compute(pl, r, nranks, &si[r]);
         if (e != 0) return e;
-        mid[r] = base;
-        base += (size_t)si[r].need_rows * rowf;
+        mid[r] = reinterpret_cast<float*>(base);
+        src4[r] = base + align_up((size_t)si[r].need_rows * rowf * sizeof(float), 256);
+        dst4[r] = src4[r] + pad4_src_bytes(pl, si[r].src_rows);
+        base = dst4[r] + pad4_dst_bytes(pl, si[r].dst_rows);
     }
     int launches = 0;
     const size_t in_el = dtype_size(d.in_type), out_el = dtype_size(d.out_type);
     for (int r = 0; r < nranks; ++r) { // every band's row pass
         float* own = mid[r] + (size_t)si[r].halo_up * rowf;
         const char* src = static_cast<const char*>(d_src) + (size_t)si[r].src_row0 * src_pitch * in_el;
-        int e = run_row_pass(pl, src, src_pitch, own, si[r].src_rows, st, &launches);
+        int e = run_row_pass(pl, src, src_pitch, own, si[r].src_rows, st, &launches, src4[r]);
         if (e != 0) return e;
     }
     for (int r = 0; r < nranks; ++r) { // the "exchange"
@@ -1153,7 +1632,7 @@ int avirb200_resize_sharded_local(const avirb200_plan* pl, int nranks, const voi
     for (int r = 0; r < nranks; ++r) {
         char* dst = static_cast<char*>(d_dst) + (size_t)si[r].dst_row0 * dst_pitch * out_el;
         int e = run_col_pass(pl, mid[r], si[r].need_row0, dst, dst_pitch, si[r].dst_row0,
-                             si[r].dst_row0 + si[r].dst_rows, st, &launches);
+                             si[r].dst_row0 + si[r].dst_rows, st, &launches, dst4[r]);
         if (e != 0) return e;
     }
     pl->last_launches = launches;

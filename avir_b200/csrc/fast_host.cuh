@@ -29,14 +29,6 @@ struct FastPlan {
     FastPass h, v;
 };
 
-inline bool env_fast_enabled() {
-    static const bool on = [] {
-        const char* e = getenv("AVIRB200_DISABLE_FAST");
-        return !(e && e[0] == '1');
-    }();
-    return on;
-}
-
 const size_t kFastSmemBudget = (227 * 1024) / kFastBlocksPerSM - 2048; // per block
 
 // A resize step all of whose outputs use effective phase 0 (the only one): integer ratios.
@@ -230,6 +222,14 @@ inline int fast_upload(FastPass& fp) {
     return 0;
 }
 
+inline const int* fast_tile_table(const FastPass& fp, int out0, int out1);
+
+// Builds the tile table of a destination-row range ahead of its first launch (sharded calls,
+// banded host calls): called from the host-side queries every such caller makes first.
+inline void fast_prepare_range(const FastPlan& f, int out0, int out1) {
+    if (f.v_ok && out1 > out0) fast_tile_table(f.v, out0, out1);
+}
+
 inline void fast_plan_init(FastPlan& f, const DevAxis& h_host, const DevAxis& v_host,
                            const avirb200_plan_desc& d) {
     if (d.channels != 4) return;
@@ -248,10 +248,9 @@ inline void fast_plan_init(FastPlan& f, const DevAxis& h_host, const DevAxis& v_
         if (fast_upload(fp) != 0) continue;
         fp.raw = (a == 0 && d.in_type != AVIRB200_F32);
         fast_choose_tile(fp, 0, hs[a]->dst_len);
-        fp.ok = true;
-        if (getenv("AVIRB200_VERBOSE"))
-            fprintf(stderr, "[avirb200] fast %s pass: tile_out %d, span_a %d, span_b %d, taps %d floats, smem %zu B\n",
-                    a ? "column" : "row", fp.tile_out, fp.fpnt.span_a, fp.fpnt.span_b, fp.fpnt.taps_floats, fp.fpnt.smem);
+        // the whole-image tile table is built and uploaded here, not at the first launch (launches
+        // stay asynchronous and allocation-free; shard ranges: fast_prepare_range())
+        fp.ok = (fast_tile_table(fp, 0, hs[a]->dst_len) != nullptr);
     }
     f.h_ok = f.h.ok;
     f.v_ok = f.v.ok;
@@ -315,7 +314,7 @@ inline int fast_launch(const FastParams& p, size_t smem, int sum_mode, cudaStrea
     const int v0 = a.s[0].variant, v1 = a.nsteps > 1 ? a.s[1].variant : -1,
               v2 = a.nsteps > 2 ? a.s[2].variant : -1;
     const int cs = p.rtaps_step;
-    const bool generic_only = [] { const char* g = getenv("AVIRB200_NO_CHAIN_KERNELS"); return g && g[0] == '1'; }();
+    const bool generic_only = false;
 #define AVB_TRY(SUMM, NSS, A0, A1, A2, CSS)                                                         \
     if (!launched && !generic_only && sum_mode == SUMM && a.nsteps == NSS && v0 == A0 &&           \
         (NSS < 2 || v1 == A1) && (NSS < 3 || v2 == A2) && cs == CSS) {                             \

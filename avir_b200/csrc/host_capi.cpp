@@ -165,6 +165,51 @@ extern "C" {
 
 const char* avirb200_host_last_error() { return g_err.c_str(); }
 
+// Test / tuning hook: default plan option of every front-end object in this process
+// (avirb200_option ids; value < 0: the plan's own default).
+void avirb200_host_set_option(int option, int value) {
+    if (option >= 0 && option < 6) avir::b200_detail::default_tuning().opt[option] = value;
+}
+
+// Plans the same call twice on one front-end object (no GPU needed: the workspace query only
+// plans on a cache miss) and reports the informational Vars outputs of both calls:
+// out[0..3] = ElCountIO, k, ... of the first, out[4..7] of the second (cache hit).
+int avirb200_host_vars_probe(int sw, int sh, int nw, int nh, double* out) {
+    try {
+        avir::CImageResizer<avir::fpclass_float4> rs(8);
+        for (int i = 0; i < 2; ++i) {
+            avir::CImageResizerVars v;
+            try {
+                rs.workspaceBytes<uint8_t, uint8_t>(sw, sh, nw, nh, 4, 0.0, &v);
+            } catch (const std::exception&) {
+                // no device: plan_create fails after the descriptor (and Vars) were filled on the
+                // first call; the second call then misses the cache as well
+            }
+            out[4 * i + 0] = v.ElCountIO; out[4 * i + 1] = v.ElCount; out[4 * i + 2] = v.k; out[4 * i + 3] = v.BuildModeH;
+        }
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return -1;
+    }
+    return 0;
+}
+
+// Synthetic input generator of the parity tests and the benchmark: xorshift32
+// from `seed`, one draw per element in memory order, element = (T)((draw & 0xFFFF) * scale) with
+// scale 1/257 (u8), 1 (u16), 1/65535 (float), evaluated in double.  dtype: avirb200_dtype.
+// Returns the generator's state after the last draw.
+uint32_t avirb200_host_fill_xorshift32(void* dst, size_t n, uint32_t seed, int dtype) {
+    uint32_t x = seed;
+    for (size_t i = 0; i < n; ++i) {
+        x ^= x << 13; x ^= x >> 17; x ^= x << 5;
+        const double lo = (double)(x & 0xFFFFu);
+        if (dtype == AVIRB200_U8) static_cast<uint8_t*>(dst)[i] = (uint8_t)(lo * (1.0 / 257));
+        else if (dtype == AVIRB200_U16) static_cast<uint16_t*>(dst)[i] = (uint16_t)lo;
+        else static_cast<float*>(dst)[i] = (float)(lo * (1.0 / 65535));
+    }
+    return x;
+}
+
 // Serialises the plan the host would build for one resizeImage() call.
 // mirror: 0 def, 1 float4, 2 float8_dil (+3: the same class with the error-diffusion ditherer).  Returns doubles needed (size with cap = 0).
 long avirb200_host_plan_dump(int mirror, int res_bits, int src_bits, int params_id, int src_w,
@@ -242,6 +287,10 @@ int lancirb200_host_resize(int tin, int tout, const void* src, int sw, int sh, v
     thread_local avir::CLancIR obj;
     avir::CLancIRParams p(srcssize, newssize, kx, ky, ox, oy);
     p.la = la;
+    if (tin < 0 || tin > 2 || tout < 0 || tout > 2) { // u8 / u16 / float buffers only (no double)
+        g_err = "lancirb200_host_resize: element type code outside 0..2";
+        return -1;
+    }
 #define LR(TI, TO) return obj.resizeImage((const TI*)src, sw, sh, (TO*)dst, nw, nh, ch, &p)
     switch (tin * 3 + tout) {
     case 0: LR(uint8_t, uint8_t);
@@ -266,6 +315,7 @@ struct LancirDescHandle {
 // Host-only LANCIR descriptor (u8 or float I/O selects the output-stage constants).
 void* lancirb200_host_desc_create(int tin, int tout, int sw, int sh, int nw, int nh, int ch,
                                   double kx, double ky, double ox, double oy, double la) {
+    if (tin < 0 || tin > 2 || tout < 0 || tout > 2) return nullptr;
     LancirDescHandle* h = new LancirDescHandle();
     avir::CLancIRParams p(0, 0, kx, ky, ox, oy);
     p.la = la;

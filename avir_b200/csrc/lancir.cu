@@ -12,12 +12,14 @@
 // (lancir.h:1772-2056): optional multiply, clamp, round-to-nearest-even; the last
 // `(NewWidth*C) & 3` elements of a row round as (int)(v + 0.5f) instead.
 //
-// Both passes run one thread per output element: the column pass with threads along x
-// (coalesced reads of every tap's row), the row pass reading its taps' pixels from the fp32
-// intermediate through the caches (neighbouring threads share them).
+// 4-channel images with aligned pixels run one thread per PIXEL with vector loads and stores
+// (lancir_col4_kernel / lancir_row4_kernel); other channel counts one thread per output element:
+// the column pass with threads along x (coalesced reads of every tap's row), the row pass
+// reading its taps' pixels from the fp32 intermediate through the caches.
 
 #include <cuda_runtime.h>
 
+#include <cstdint>
 #include <cstring>
 #include <memory>
 #include <mutex>
@@ -163,6 +165,103 @@ __global__ void __launch_bounds__(256) lancir_row_kernel(const __grid_constant__
     else ((unsigned short*)p.dst)[g] = (unsigned short)iv;
 }
 
+// ---- 4-channel images: one thread per PIXEL, vector loads and stores ----------------------------
+// Same sums as ltapsum's C == 4 branch (resize4: even taps into one chain, odd taps into the
+// other, per channel), on float4 values.  The column pass walks a run of output rows per block so
+// that the kl source rows an output row reads stay in L1 for the next rows (each source byte
+// leaves L2 once per block); the row pass reads its taps' pixels as 16-byte loads.
+template <typename T> struct LPix;
+template <> struct LPix<unsigned char> {
+    static __device__ __forceinline__ float4 load(const void* p, long long i) {
+        const uchar4 v = *reinterpret_cast<const uchar4*>(static_cast<const unsigned char*>(p) + i);
+        return make_float4((float)v.x, (float)v.y, (float)v.z, (float)v.w);
+    }
+};
+template <> struct LPix<unsigned short> {
+    static __device__ __forceinline__ float4 load(const void* p, long long i) {
+        const ushort4 v = *reinterpret_cast<const ushort4*>(static_cast<const unsigned short*>(p) + i);
+        return make_float4((float)v.x, (float)v.y, (float)v.z, (float)v.w);
+    }
+};
+template <> struct LPix<float> {
+    static __device__ __forceinline__ float4 load(const void* p, long long i) {
+        return *reinterpret_cast<const float4*>(static_cast<const float*>(p) + i);
+    }
+};
+
+__device__ __forceinline__ float4 lmul4(float f, float4 v) {
+    return make_float4(__fmul_rn(f, v.x), __fmul_rn(f, v.y), __fmul_rn(f, v.z), __fmul_rn(f, v.w));
+}
+__device__ __forceinline__ float4 ladd4(float4 a, float4 b) {
+    return make_float4(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y), __fadd_rn(a.z, b.z), __fadd_rn(a.w, b.w));
+}
+
+constexpr int kLColRows = 32; // output rows a block of the column pass walks
+
+template <typename TIN>
+__global__ void __launch_bounds__(256) lancir_col4_kernel(const __grid_constant__ LParams p) {
+    const int px = blockIdx.x * 256 + threadIdx.x;
+    if (px >= p.src_w) return;
+    const int y0 = blockIdx.y * kLColRows;
+    const int y1 = (y0 + kLColRows < p.dst_h) ? y0 + kLColRows : p.dst_h;
+    const int kl = p.v.kl, src_h = p.src_h;
+    const long long pitch = p.src_pitch;
+    for (int y = y0; y < y1; ++y) {
+        const float* f = p.v.taps + (size_t)__ldg(p.v.phase + y) * kl;
+        const int s0 = __ldg(p.v.src_pos + y);
+        auto S = [&](int t) {
+            int sy = s0 + t;
+            sy = sy < 0 ? 0 : (sy >= src_h ? src_h - 1 : sy);
+            return LPix<TIN>::load(p.src, (long long)sy * pitch + (long long)px * 4);
+        };
+        float4 ev = lmul4(__ldg(f), S(0)), od = lmul4(__ldg(f + 1), S(1));
+        for (int t = 2; t < kl; t += 2) {
+            ev = ladd4(ev, lmul4(__ldg(f + t), S(t)));
+            od = ladd4(od, lmul4(__ldg(f + t + 1), S(t + 1)));
+        }
+        reinterpret_cast<float4*>(p.mid + (size_t)y * p.src_w * 4)[px] = ladd4(ev, od);
+    }
+}
+
+// OUT: 0 float, 1 u8, 2 u16
+template <int OUT>
+__global__ void __launch_bounds__(256) lancir_row4_kernel(const __grid_constant__ LParams p) {
+    const int x = blockIdx.x * 256 + threadIdx.x;
+    const int y = blockIdx.y;
+    if (x >= p.dst_w) return;
+    const int kl = p.h.kl, src_w = p.src_w;
+    const float* f = p.h.taps + (size_t)__ldg(p.h.phase + x) * kl;
+    const int s0 = __ldg(p.h.src_pos + x);
+    const float4* row = reinterpret_cast<const float4*>(p.mid + (size_t)y * src_w * 4);
+    auto M = [&](int t) {
+        int sx = s0 + t;
+        sx = sx < 0 ? 0 : (sx >= src_w ? src_w - 1 : sx);
+        return row[sx];
+    };
+    float4 ev = lmul4(__ldg(f), M(0)), od = lmul4(__ldg(f + 1), M(1));
+    for (int t = 2; t < kl; t += 2) {
+        ev = ladd4(ev, lmul4(__ldg(f + t), M(t)));
+        od = ladd4(od, lmul4(__ldg(f + t + 1), M(t + 1)));
+    }
+    float4 v = ladd4(ev, od);
+    if (!p.unity) v = lmul4(p.out_mul, v);
+    const long long g = (long long)y * p.dst_pitch + (long long)x * 4;
+    if (OUT == 0) {
+        *reinterpret_cast<float4*>(static_cast<float*>(p.dst) + g) = v;
+        return;
+    }
+    // (a row of 4-channel pixels has no (NewWidth*C) & 3 tail: every element rounds nearest-even)
+    const float cm = p.clamp_max;
+    const int a = __float2int_rn(fmaxf(fminf(v.x, cm), 0.0f)), b = __float2int_rn(fmaxf(fminf(v.y, cm), 0.0f));
+    const int c = __float2int_rn(fmaxf(fminf(v.z, cm), 0.0f)), d = __float2int_rn(fmaxf(fminf(v.w, cm), 0.0f));
+    if (OUT == 1)
+        *reinterpret_cast<uchar4*>(static_cast<unsigned char*>(p.dst) + g) =
+            make_uchar4((unsigned char)a, (unsigned char)b, (unsigned char)c, (unsigned char)d);
+    else
+        *reinterpret_cast<ushort4*>(static_cast<unsigned short*>(p.dst) + g) =
+            make_ushort4((unsigned short)a, (unsigned short)b, (unsigned short)c, (unsigned short)d);
+}
+
 size_t lsize(int t) { return t == AVIRB200_U8 ? 1 : (t == AVIRB200_U16 ? 2 : 4); }
 
 } // namespace
@@ -262,10 +361,29 @@ int lancirb200_resize_device(const lancirb200_plan* pl, const void* d_src, size_
     p.dst = d_dst; p.dst_pitch = (long long)dst_pitch;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (d.dst_h > 65535) return lfail(AVIRB200_ERR_UNSUPPORTED, "image too tall");
-    dim3 g1((d.src_w * d.channels + 255) / 256, d.dst_h);
-    lancir_col_kernel<<<g1, 256, 0, st>>>(p);
-    dim3 g2((d.dst_w * d.channels + 255) / 256, d.dst_h);
-    lancir_row_kernel<<<g2, 256, 0, st>>>(p);
+    // 4-channel images whose pixels are aligned to their own size: the vector kernels
+    const bool vec_in = d.channels == 4 && (src_pitch % 4) == 0 && ((uintptr_t)d_src % (4 * lsize(d.in_type))) == 0 &&
+                        ((uintptr_t)d_ws % 16) == 0;
+    const bool vec_out = d.channels == 4 && (dst_pitch % 4) == 0 && ((uintptr_t)d_dst % (4 * lsize(d.out_type))) == 0 &&
+                         ((uintptr_t)d_ws % 16) == 0;
+    if (vec_in) {
+        dim3 g1((d.src_w + 255) / 256, (d.dst_h + kLColRows - 1) / kLColRows);
+        if (d.in_type == AVIRB200_U8) lancir_col4_kernel<unsigned char><<<g1, 256, 0, st>>>(p);
+        else if (d.in_type == AVIRB200_U16) lancir_col4_kernel<unsigned short><<<g1, 256, 0, st>>>(p);
+        else lancir_col4_kernel<float><<<g1, 256, 0, st>>>(p);
+    } else {
+        dim3 g1((d.src_w * d.channels + 255) / 256, d.dst_h);
+        lancir_col_kernel<<<g1, 256, 0, st>>>(p);
+    }
+    if (vec_out) {
+        dim3 g2((d.dst_w + 255) / 256, d.dst_h);
+        if (d.out_type == AVIRB200_U8) lancir_row4_kernel<1><<<g2, 256, 0, st>>>(p);
+        else if (d.out_type == AVIRB200_U16) lancir_row4_kernel<2><<<g2, 256, 0, st>>>(p);
+        else lancir_row4_kernel<0><<<g2, 256, 0, st>>>(p);
+    } else {
+        dim3 g2((d.dst_w * d.channels + 255) / 256, d.dst_h);
+        lancir_row_kernel<<<g2, 256, 0, st>>>(p);
+    }
     LCUDA_TRY(cudaGetLastError());
     return 0;
 }

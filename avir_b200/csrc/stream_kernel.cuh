@@ -55,6 +55,7 @@ namespace avs {
 
 using avb::lin2srgb;
 using avb::round_out;
+using avb::round_out_int;
 
 constexpr int kLines = 16;      // lines per warp (2 lanes per line)
 constexpr int kPitchL = 32;     // float2 units: [position][lane] rows of 256 bytes
@@ -91,7 +92,13 @@ constexpr int cdiv(int a, int b) { return (a + b - 1) / b; }
 //   SRCT     element type of the row pass's source image (AVIRB200_F32 / _U8 / _U16): integer
 //            pixels stream into the source ring as they are (4 / 8 bytes per pixel) and are
 //            converted -- upstream's packScanline cast, avir.h:2777-2971 -- in the lanes' reads
-template <class S0, class S1, class S2, int REPS_LAST, int LA, int STEADY_ = 1, int PRE_ = 0, int SRCT_ = AVIRB200_F32>
+//   MODE     scheduling of the interior ("steady") rounds of a run, same arithmetic:
+//            0 ring windows (every batch reads its whole window from the shared-memory rings),
+//            1 register windows (run_regwin(): every input is read from shared memory once and
+//              slides through a register window; later steps never touch shared memory),
+//            2 = 1 + mbarrier-tracked source ring filled by one-lane tensor copies (TMA; column pass),
+//            3 = 0 without the separate straight-line loop (every round takes the checked path)
+template <class S0, class S1, class S2, int REPS_LAST, int LA, int MODE_ = 0, int SRCT_ = AVIRB200_F32, int RWU_ = 1>
 struct ChainC {
     using T0 = S0;
     using T1 = S1;
@@ -100,7 +107,16 @@ struct ChainC {
     static constexpr int PIXB = (SRCT == AVIRB200_F32) ? 16 : (SRCT == AVIRB200_U16 ? 8 : 4); // bytes per source pixel (u8, u8 sRGB: 4)
     static constexpr int NS = (S2::KIND == K_NONE) ? 2 : 3;
     static constexpr int LOOKAHEAD = LA;
-    static constexpr bool STEADY_LOOP = (STEADY_ != 0); // straight-line code for the interior rounds of a run
+    static constexpr int MODE = MODE_;
+    static constexpr bool STEADY_LOOP = (MODE_ != 3); // straight-line code for the interior rounds of a run
+    static constexpr bool REGWIN = (MODE_ == 1 || MODE_ == 2) && S0::KIND != K_RESIZE2 && S1::KIND != K_RESIZE2 &&
+                                   S2::KIND != K_RESIZE2;
+    // source ring filled by one-lane tensor copies (TMA) and tracked by mbarriers instead of
+    // per-lane cp.async groups: column pass only (ChainV maps the row pass's mode 2 to mode 1 --
+    // its ring is [line][position] with padded lines, which no dense TMA box lands as)
+    static constexpr bool MBAR = (MODE_ == 2) && REGWIN;
+    // register-window rounds per trip of the unrolled loop (run_regwin())
+    static constexpr int RW_UNROLL = RWU_;
     static constexpr int reps2 = (NS == 3) ? REPS_LAST : 0;
     static constexpr int reps1 = (NS == 3) ? (S2::CH * reps2) / S1::M : REPS_LAST;
     static constexpr int reps0 = (S1::CH * reps1) / S0::M;
@@ -110,13 +126,8 @@ struct ChainC {
     static constexpr int SRC_N = S0::CH * reps0;                        // source positions per round
     static_assert(SRC_N % 16 == 0, "source positions per round must be whole 16-position loads");
     // consumer i+1 needs its producer d rounds ahead
-    // PRE: in the straight-line rounds a later step's window is read from shared memory at the
-    // top of the round, before step 0's arithmetic (its latency hides behind that); the
-    // window must then be complete one round earlier: one more round of delay and ring.
-    static constexpr bool PRE1 = PRE_ && (S1::KIND == K_FIR || S1::KIND == K_RESIZE) && reps1 == 1;
-    static constexpr bool PRE2 = PRE_ && (NS == 3) && (S2::KIND == K_FIR || S2::KIND == K_RESIZE) && reps2 == 1;
-    static constexpr int d0 = cdiv(cdiv(S1::W, S1::CH) - 1, reps1) + (PRE1 ? 1 : 0);
-    static constexpr int d1 = (NS == 3) ? cdiv(cdiv(S2::W, S2::CH) - 1, reps2) + (PRE2 ? 1 : 0) : 0;
+    static constexpr int d0 = cdiv(cdiv(S1::W, S1::CH) - 1, reps1);
+    static constexpr int d1 = (NS == 3) ? cdiv(cdiv(S2::W, S2::CH) - 1, reps2) : 0;
     static constexpr int delay0 = 0, delay1 = d0, delay2 = d0 + d1;
     static constexpr int DELAY_LAST = (NS == 3) ? delay2 : delay1;
     static constexpr int rsp1 = S1::CH * reps1 * (d0 + 1);
@@ -131,8 +142,9 @@ struct ChainC {
     static constexpr int LINE_B = (rsp0 + 1) * PIXB; // row pass: bytes per line of the source ring (one pixel of padding)
     static constexpr int SRC_RING_F2 = (kLines * LINE_B + 15) / 16 * 2;
     static constexpr int STAGE_LINE = MLAST * 2 + 2;
-    static constexpr int WARP_F2_H = SRC_RING_F2 + (rsp1 + rsp2) * kPitchL + kLines * STAGE_LINE;
-    static constexpr int WARP_F2_V = rsp0 * kPitchL + (rsp1 + rsp2) * kPitchL;
+    static constexpr int MBAR_F2 = MBAR ? NG : 0; // one 8-byte mbarrier per source-ring group
+    static constexpr int WARP_F2_H = SRC_RING_F2 + (rsp1 + rsp2) * kPitchL + kLines * STAGE_LINE + MBAR_F2;
+    static constexpr int WARP_F2_V = rsp0 * kPitchL + (rsp1 + rsp2) * kPitchL + MBAR_F2;
     // warps per block (one block per SM): 8 (two per scheduler; the register windows leave room
     // for no more), fewer where the rings of 8 warps exceed the shared memory of an SM
     static constexpr int kSmemF2 = 227 * 1024 / 8;
@@ -205,7 +217,49 @@ AVS_FN void cp_async_px(void* smem, const void* gmem) {
 AVS_FN void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 AVS_FN void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+// ---- mbarrier-tracked staging (C::MBAR): one barrier per source-ring group, 32 arrivals per phase
+AVS_FN unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+AVS_FN void mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+AVS_FN void mbar_init_fence() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+AVS_FN void mbar_arrive(unsigned bar) {
+    asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.shared::cta.b64 st, [%0];\n}" ::"r"(bar) : "memory");
+}
+AVS_FN void mbar_arrive_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}" ::"r"(bar), "r"(bytes) : "memory");
+}
+// the lane's arrival fires when all cp.async copies it has issued so far have landed
+AVS_FN void mbar_arrive_cp_async(unsigned bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+// Bounded wait: a protocol error traps instead of hanging the device.
+AVS_FN void mbar_wait(unsigned bar, unsigned parity) {
+    unsigned done = 0;
+#pragma unroll 1
+    for (int spin = 0; spin < (1 << 24); ++spin) {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (done) return;
+    }
+    __trap();
+}
+// one 2-D tile (TMA): box of the tensor map at element coordinates (c0, c1) -> shared memory,
+// completion counted in bytes on `bar`
+AVS_FN void tma_tile_2d(void* dst, const void* tmap, int c0, int c1, unsigned bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(smem_u32(dst)), "l"(tmap), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
 #else
+// host emulation: copies are immediate, barriers have nothing to wait for
+AVS_FN unsigned smem_u32(const void*) { return 0; }
+AVS_FN void mbar_arrive(unsigned) {}
+AVS_FN void mbar_arrive_expect_tx(unsigned, unsigned) {}
+AVS_FN void mbar_arrive_cp_async(unsigned) {}
+AVS_FN void mbar_wait(unsigned, unsigned) {}
 AVS_FN void cp_async16(void* smem, const void* gmem) { memcpy(smem, gmem, 16); }
 template <int N>
 AVS_FN void cp_async_px(void* smem, const void* gmem) { memcpy(smem, gmem, N); }
@@ -325,13 +379,13 @@ struct WarpRun {
     // (they point one sweep behind and are advanced BEFORE use: the copies read them in place
     // and the next write to them is a whole round away -- no write-after-read wait on the
     // copy queue)
-    const unsigned char* gp[8];
+    const unsigned char* gp[C::MBAR ? 1 : 8];
     // row pass: the previous final batch, read back from the staging rows, waiting to be stored
     float4 pend[C::MLAST / 2];
     int pend_j0;
-    // windows of later steps read ahead at the top of a straight-line round
-    float2 xp1[C::PRE1 ? C::T1::W : 1];
-    float2 xp2[C::PRE2 ? C::T2::W : 1];
+    // source ring tracked by mbarriers (C::MBAR): shared address of slot 0's barrier, the phase
+    // parity each slot's next completion will have (bit s = slot s)
+    unsigned mbar0, mpar;
 };
 
 template <class C, bool IS_V, int I>
@@ -386,6 +440,7 @@ AVS_FN void loader_init(const StreamParams& p, WarpRun<C, IS_V>& w) {
     const unsigned char* src = static_cast<const unsigned char*>(p.src);
     const size_t rowb = (size_t)p.src_pitch * (PIXB / 4); // bytes between rows (pitch is in elements)
     const int lane = w.lane;
+    if constexpr (C::MBAR) return; // the checked rounds compute every address afresh, the tensor copies take coordinates
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
         if (IS_V) {
@@ -419,9 +474,11 @@ AVS_FN void load_group(const StreamParams& p, WarpRun<C, IS_V>& w, int g, int gs
             // a position is an intermediate row; the warp's 16 pixel columns are 256 contiguous bytes
             const int piece = lane & 15, rsub = lane >> 4;
             unsigned char* d = ring + rsub * PITCH_B + piece * 16;
+            if constexpr (!C::MBAR) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) w.gp[k] += 16 * rowb;
-            if (STEADY || (issue && interior)) {
+                for (int k = 0; k < 8; ++k) w.gp[k] += 16 * rowb;
+            }
+            if (!C::MBAR && (STEADY || (issue && interior))) {
 #pragma unroll
                 for (int k = 0; k < 8; ++k) cp_async16(d + 2 * k * PITCH_B, w.gp[k]);
             } else if (issue) {
@@ -436,9 +493,11 @@ AVS_FN void load_group(const StreamParams& p, WarpRun<C, IS_V>& w, int g, int gs
             // a position is a pixel of a row: 16 consecutive pixels of one row per half warp
             const int pos = lane & 15, lsub = lane >> 4;
             unsigned char* d = ring + pos * PIXB + lsub * C::LINE_B; // line lsub + 2k: + 2k * LINE_B
+            if constexpr (!C::MBAR) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) w.gp[k] += 16 * PIXB;
-            if (STEADY || (issue && interior)) {
+                for (int k = 0; k < 8; ++k) w.gp[k] += 16 * PIXB;
+            }
+            if (!C::MBAR && (STEADY || (issue && interior))) {
 #pragma unroll
                 for (int k = 0; k < 8; ++k) cp_async_px<PIXB>(d + 2 * k * C::LINE_B, w.gp[k]);
             } else if (issue) {
@@ -484,6 +543,16 @@ AVS_FN void store_v(const StreamParams& p, unsigned char* g, float2 v, int c0) {
         return;
     }
     if (EPI == 2) { // integer destination, no output gamma (no double-precision code in the kernel)
+        if (p.tr_mul == 1.0f) {
+            // no bit-depth truncation (the common case): one float->int conversion per sample,
+            // clamp and narrow in integers -- same values as round, clamp, (Tout) in floats
+            const int pk = (int)p.pk_out;
+            const int a = imin_(imax_(round_out_int(v.x, p.round_mode), 0), pk);
+            const int b = imin_(imax_(round_out_int(v.y, p.round_mode), 0), pk);
+            if (p.dst_type == AVIRB200_U8) *reinterpret_cast<unsigned short*>(g) = (unsigned short)(a | (b << 8));
+            else *reinterpret_cast<unsigned*>(g) = (unsigned)a | ((unsigned)b << 16);
+            return;
+        }
         v.x = epilogue_round(p, v.x);
         v.y = epilogue_round(p, v.y);
         if (p.dst_type == AVIRB200_U8)
@@ -581,35 +650,13 @@ AVS_FN void window_bases(const unsigned char* ring, int rd, const unsigned char*
     }
 }
 
-// Reads the window of step I's next batch into registers (straight-line rounds, PRE chains).
 template <class C, bool IS_V, int I, class S>
-AVS_FN void preload_window(WarpRun<C, IS_V>& w) {
-    using R = RingOf<C, IS_V, I>;
-    const unsigned char* ring = reinterpret_cast<const unsigned char*>((I == 1) ? w.ring1 : w.ring2) + R::lane_off_b(w.lane);
-    const unsigned char* base[(S::W + S::CH - 1) / S::CH + 1];
-    window_bases<C, IS_V, I, S>(ring, w.rd[I], base);
-    float2* xp = (I == 1) ? w.xp1 : w.xp2;
-#pragma unroll
-    for (int i = 0; i < S::W; ++i) xp[i] = R::load(base[i / S::CH] + (i % S::CH) * R::PITCH_B, w.cv);
-}
-
-// PRELOADED: the window is already in w.xp1 / w.xp2 (preload_window).
-template <class C, bool IS_V, int I, class S, bool PRELOADED = false>
 AVS_FN void fast_batch(const StreamParams& p, WarpRun<C, IS_V>& w, const unsigned char* ring, int rd, int kbcur,
                        int j0, float2* o) {
     using R = RingOf<C, IS_V, I>;
     constexpr int PITCH_B = R::PITCH_B;
     constexpr int M = S::M;
     const StreamStep& sp = p.s[I];
-    if constexpr (PRELOADED) {
-        const float2* x = (I == 1) ? w.xp1 : w.xp2;
-#pragma unroll
-        for (int m = 0; m < M; ++m) {
-            if (S::KIND == K_FIR) o[m] = fir_one<S>(x, m * S::ADV, sp.taps);
-            else o[m] = resize_one<S>(x, m * S::ADV, sp.taps, sp.zero_start);
-        }
-        return;
-    }
     const unsigned char* base[(S::W + S::CH - 1) / S::CH + 1];
     window_bases<C, IS_V, I, S>(ring, rd, base);
     if constexpr (S::KIND == K_RESIZE2) {
@@ -686,13 +733,11 @@ AVS_FN void run_batch(const StreamParams& p, WarpRun<C, IS_V>& w) {
     w.kb[I] += 1;
     w.rd[I] = (rd + S::CH == RSP) ? 0 : rd + S::CH;
 
-    constexpr bool PRE = STEADY && ((I == 1 && C::PRE1) || (I == 2 && C::PRE2));
-    // (PRE chains read the row sink's staged batch back at the top of the round as well)
-    if constexpr (LAST && !IS_V && !(STEADY && C::PRE1)) sink_h_readback<C, M>(w);
+    if constexpr (LAST && !IS_V) sink_h_readback<C, M>(w);
     float2 o[M];
     bool have = true;
     if constexpr (STEADY) {
-        fast_batch<C, IS_V, I, S, PRE>(p, w, ring, rd, kbcur, j0, o);
+        fast_batch<C, IS_V, I, S>(p, w, ring, rd, kbcur, j0, o);
     } else {
         const int pin = in_first<S>(sp, j0);
         const bool in_dom = (j0 >= 0) && (j0 + M <= sp.out_len);
@@ -757,6 +802,247 @@ AVS_FN void steady_bounds(const StreamParams& p, const WarpRun<C, IS_V>& w, int 
     hi = imin_(hi, delay + fdiv_(kb_hi - reps + 1, reps));
 }
 
+// ---- register-window rounds (C::REGWIN) -----------------------------------------------------------------
+// The ring rounds above read every batch's whole window from shared memory (38 reads per 8
+// outputs of the 24-tap resize, the later steps through their own rings) and wait for it
+// before the arithmetic starts; with two warps per scheduler those waits show (stall `wait` +
+// `long scoreboard`, FP32 pipe 74 % busy, profiles/r01_final_ncu_summary.txt).  In the interior
+// of a run the windows slide through REGISTERS instead: every round reads only the SRC_N source
+// positions it has not seen yet -- they are first needed by the round's last outputs, so the
+// shared-memory latency hides behind the arithmetic of the first ones -- and a later step's window
+// is the previous step's outputs, which never leave the register file.  Shared memory then
+// carries the source ring only (one read per input) plus the row pass's output staging.
+//
+// win0[q]: source position (first position of the round's step-0 window) + q; win1 / win2: the
+// same for steps 1 / 2, whose producers append this round's outputs at d * A (the consumer lags
+// d rounds).  After its arithmetic a window shifts down by the positions the step consumed: in
+// the unrolled loop that is register renaming.  Entering, the windows are filled from the
+// rings the checked rounds wrote; leaving, the later steps' windows are written back so that
+// the checked rounds can go on.
+template <class C>
+struct RegWinGeom {
+    using S0 = typename C::T0;
+    using S1 = typename C::T1;
+    using S2 = typename C::T2;
+    static constexpr int A0 = C::SRC_N;                           // positions a round consumes
+    static constexpr int WR0 = S0::W + (C::reps0 - 1) * S0::CH;   // positions a round reads
+    static constexpr int Q0 = WR0 - A0;                           // first position a round has not seen before
+    static constexpr int A1 = S1::CH * C::reps1;
+    static constexpr int WR1 = S1::W + (C::reps1 - 1) * S1::CH;
+    static constexpr int K1 = C::d0 * A1;                         // positions kept from earlier rounds
+    static constexpr int A2 = (C::NS == 3) ? S2::CH * C::reps2 : 1;
+    static constexpr int WR2 = (C::NS == 3) ? S2::W + (C::reps2 - 1) * S2::CH : 1;
+    static constexpr int K2 = (C::NS == 3) ? C::d1 * A2 : 0;
+    static_assert(S0::M * C::reps0 == A1, "step 0 outputs per round");
+    static_assert(C::NS == 2 || S1::M * C::reps1 == A2, "step 1 outputs per round");
+    static_assert(WR1 <= K1 + A1 && WR2 <= K2 + A2, "window inside the kept positions");
+    static_assert(Q0 < C::rsp0 && Q0 >= 0, "source window");
+};
+
+template <class C>
+struct RegWin {
+    using G = RegWinGeom<C>;
+    float2 w0[G::WR0];
+    float2 w1[G::K1 + G::A1];
+    float2 w2[G::K2 + G::A2];
+};
+
+template <class S, class X>
+AVS_FN float2 step_one(const X& x, const int off, const StreamStep& sp) {
+    if (S::KIND == K_FIR) return fir_one<S>(x, off, sp.taps);
+    return resize_one<S>(x, off, sp.taps, sp.zero_start);
+}
+
+template <class C, bool IS_V>
+AVS_FN void regwin_enter(const WarpRun<C, IS_V>& w, RegWin<C>& R) {
+    using G = RegWinGeom<C>;
+    using R0 = RingOf<C, IS_V, 0>;
+    const unsigned char* ring0 = reinterpret_cast<const unsigned char*>(w.ring0) + R0::lane_off_b(w.lane);
+#pragma unroll
+    for (int q = 0; q < G::Q0; ++q) {
+        int s = w.rd[0] + q;
+        if (s >= C::rsp0) s -= C::rsp0;
+        R.w0[q] = R0::load(ring0 + (size_t)s * R0::PITCH_B, w.cv);
+    }
+#pragma unroll
+    for (int q = 0; q < G::K1; ++q) {
+        int s = w.rd[1] + q;
+        if (s >= C::rsp1) s -= C::rsp1;
+        R.w1[q] = w.ring1[(size_t)s * kPitchL + w.lane];
+    }
+    if constexpr (C::NS == 3) {
+#pragma unroll
+        for (int q = 0; q < G::K2; ++q) {
+            int s = w.rd[2] + q;
+            if (s >= C::rsp2) s -= C::rsp2;
+            R.w2[q] = w.ring2[(size_t)s * kPitchL + w.lane];
+        }
+    }
+}
+
+// n rounds were run in registers: advance the ring cursors as the ring rounds would have and
+// write the kept part of the later steps' windows where the next checked round reads it.
+template <class C, bool IS_V>
+AVS_FN void regwin_leave(WarpRun<C, IS_V>& w, const RegWin<C>& R, int n) {
+    using G = RegWinGeom<C>;
+    w.rd[0] = (int)(((unsigned)w.rd[0] + (unsigned)n * G::A0) % (unsigned)C::rsp0);
+    w.kb[0] += n * C::reps0;
+    w.wr[0] = (int)(((unsigned)w.wr[0] + (unsigned)n * G::A1) % (unsigned)C::rsp1);
+    w.rd[1] = (int)(((unsigned)w.rd[1] + (unsigned)n * G::A1) % (unsigned)C::rsp1);
+    w.kb[1] += n * C::reps1;
+#pragma unroll
+    for (int q = 0; q < G::K1; ++q) {
+        int s = w.rd[1] + q;
+        if (s >= C::rsp1) s -= C::rsp1;
+        w.ring1[(size_t)s * kPitchL + w.lane] = R.w1[q];
+    }
+    if constexpr (C::NS == 3) {
+        w.wr[1] = (int)(((unsigned)w.wr[1] + (unsigned)n * G::A2) % (unsigned)C::rsp2);
+        w.rd[2] = (int)(((unsigned)w.rd[2] + (unsigned)n * G::A2) % (unsigned)C::rsp2);
+        w.kb[2] += n * C::reps2;
+#pragma unroll
+        for (int q = 0; q < G::K2; ++q) {
+            int s = w.rd[2] + q;
+            if (s >= C::rsp2) s -= C::rsp2;
+            w.ring2[(size_t)s * kPitchL + w.lane] = R.w2[q];
+        }
+    }
+}
+
+// Stages source group g of the column pass (interior: no clamping) with ONE tensor copy issued
+// by one lane: the box SRC_N intermediate rows x 256 bytes (the strip's 16 pixel columns) lands
+// as the ring's [position][lane] rows.  Columns past the image's right edge (ragged strip) are
+// outside the tensor: the TMA unit fills them with zeros, their lanes never store.
+template <class C, bool IS_V>
+AVS_FN void bulk_group(const StreamParams& p, WarpRun<C, IS_V>& w, int row, int gslot, unsigned bar) {
+    static_assert(IS_V, "tensor staging: column pass");
+    unsigned char* d = reinterpret_cast<unsigned char*>(w.ring0) + (size_t)gslot * (kPitchL * 8);
+#if defined(__CUDACC__)
+    if (w.lane == 0) {
+        mbar_arrive_expect_tx(bar, C::SRC_N * kPitchL * 8);
+        tma_tile_2d(d, &p.tmap, w.line0 * 4, row, bar);
+    } else {
+        mbar_arrive(bar);
+    }
+#else
+    if (w.lane == 0) {
+        const unsigned char* src = static_cast<const unsigned char*>(p.src);
+        const size_t rowb = (size_t)p.src_pitch * 4;
+        for (int k = 0; k < C::SRC_N; ++k)
+            memcpy(d + k * (kPitchL * 8), src + (size_t)(row + k) * rowb + (size_t)w.line0 * 16, (size_t)w.nlines * 16);
+    }
+    (void)bar;
+#endif
+}
+
+// One round in registers.  s1 / s2: ring slots (positions) of the two source groups the round's
+// new positions lie in; jout: first final output of the round.
+template <class C, bool IS_V, int EPI>
+AVS_FN void regwin_round(const StreamParams& p, WarpRun<C, IS_V>& w, RegWin<C>& R, int s1, int s2, int jout) {
+    using G = RegWinGeom<C>;
+    using S0 = typename C::T0;
+    using S1 = typename C::T1;
+    using S2 = typename C::T2;
+    using R0 = RingOf<C, IS_V, 0>;
+    constexpr int OQ = G::Q0 % G::A0; // offset of the first new position inside its group
+    const unsigned char* ring0 = reinterpret_cast<const unsigned char*>(w.ring0) + R0::lane_off_b(w.lane);
+    const unsigned char* b1 = ring0 + (size_t)s1 * R0::PITCH_B;
+    const unsigned char* b2 = ring0 + (size_t)s2 * R0::PITCH_B;
+#pragma unroll
+    for (int i = 0; i < G::A0; ++i) {
+        R.w0[G::Q0 + i] = (i < G::A0 - OQ) ? R0::load(b1 + (OQ + i) * R0::PITCH_B, w.cv)
+                                           : R0::load(b2 + (i - (G::A0 - OQ)) * R0::PITCH_B, w.cv);
+    }
+    float2 o[C::B];
+    // step 0
+#pragma unroll
+    for (int q = 0; q < C::reps0; ++q) {
+#pragma unroll
+        for (int m = 0; m < S0::M; ++m)
+            R.w1[G::K1 + q * S0::M + m] = step_one<S0>(R.w0, q * S0::CH + m * S0::ADV, p.s[0]);
+    }
+#pragma unroll
+    for (int k = 0; k < G::Q0; ++k) R.w0[k] = R.w0[k + G::A0];
+    // step 1
+#pragma unroll
+    for (int q = 0; q < C::reps1; ++q) {
+#pragma unroll
+        for (int m = 0; m < S1::M; ++m) {
+            const float2 v = step_one<S1>(R.w1, q * S1::CH + m * S1::ADV, p.s[1]);
+            if constexpr (C::NS == 3) R.w2[G::K2 + q * S1::M + m] = v;
+            else o[q * S1::M + m] = v;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < G::K1; ++k) R.w1[k] = R.w1[k + G::A1];
+    if constexpr (C::NS == 3) {
+#pragma unroll
+        for (int q = 0; q < C::reps2; ++q) {
+#pragma unroll
+            for (int m = 0; m < S2::M; ++m) o[q * S2::M + m] = step_one<S2>(R.w2, q * S2::CH + m * S2::ADV, p.s[2]);
+        }
+#pragma unroll
+        for (int k = 0; k < G::K2; ++k) R.w2[k] = R.w2[k + G::A2];
+    }
+    // final outputs (every batch inside [out0, out1): steady_bounds)
+    constexpr int ML = C::MLAST;
+#pragma unroll
+    for (int q = 0; q < C::B / ML; ++q) {
+        if constexpr (IS_V) {
+            sink_v<C, EPI, ML, true>(p, w, jout + q * ML, o + q * ML);
+        } else {
+            if (q > 0) sink_h_readback<C, ML>(w);
+            sink_h_store<C, ML>(p, w);
+            sink_h_stage<C, ML>(w, jout + q * ML, o + q * ML);
+        }
+    }
+}
+
+// Rounds [r, r + n) of a run in registers (n a multiple of C::RW_UNROLL, every round "steady").
+// gslot / gi: ring slot (positions / group index) the loader fills next; wi: group index the
+// next round waits for (C::MBAR).
+template <class C, bool IS_V, int EPI>
+AVS_FN void run_regwin(const StreamParams& p, WarpRun<C, IS_V>& w, int r, int n, int& gslot, int& gi, int& wi) {
+    using G = RegWinGeom<C>;
+    constexpr int PRO = C::H + C::LOOKAHEAD;
+    RegWin<C> R;
+    regwin_enter<C, IS_V>(w, R);
+    int s1 = w.rd[0] + (G::Q0 / G::A0) * G::A0;
+    if (s1 >= C::rsp0) s1 -= C::rsp0;
+    int s2 = (s1 + G::A0 == C::rsp0) ? 0 : s1 + G::A0;
+    int jout = w.a[C::NS - 1] + C::MLAST * w.kb[C::NS - 1];
+    int grow = w.o0 + (r + PRO) * C::SRC_N - p.src_row_base; // C::MBAR: first buffer row of the group staged next
+    for (int it = n / C::RW_UNROLL; it > 0; --it) {
+#pragma unroll
+        for (int u = 0; u < C::RW_UNROLL; ++u) {
+            if constexpr (C::MBAR) {
+                mbar_wait(w.mbar0 + wi * 8, (w.mpar >> wi) & 1u);
+                w.mpar ^= 1u << wi;
+                wi = (wi + 1 == C::NG) ? 0 : wi + 1;
+            } else {
+                cp_async_wait<C::LOOKAHEAD - 1>();
+            }
+            AVS_SYNCWARP(); // all lanes' copies have landed; the previous round is done with its slots
+            if constexpr (!IS_V) sink_h_readback<C, C::MLAST>(w);
+            if constexpr (C::MBAR) {
+                bulk_group<C, IS_V>(p, w, grow, gslot, w.mbar0 + gi * 8);
+                grow += C::SRC_N;
+                gi = (gi + 1 == C::NG) ? 0 : gi + 1;
+            } else {
+                load_group<C, IS_V, true>(p, w, r + PRO, gslot, true);
+                cp_async_commit();
+            }
+            gslot = (gslot + C::SRC_N == C::rsp0) ? 0 : gslot + C::SRC_N;
+            regwin_round<C, IS_V, EPI>(p, w, R, s1, s2, jout);
+            s1 = s2;
+            s2 = (s2 + G::A0 == C::rsp0) ? 0 : s2 + G::A0;
+            jout += C::B;
+            ++r;
+        }
+    }
+    regwin_leave<C, IS_V>(w, R, n);
+}
+
 // ---- one run: `rounds` rounds of B final outputs of one 16-line strip -----------------------------
 
 template <class C, bool IS_V, int EPI>
@@ -780,13 +1066,34 @@ AVS_FN void run_warp(const StreamParams& p, WarpRun<C, IS_V>& w, int strip, int 
     const int total = rounds + C::DELAY_LAST;  // wall rounds; step 0 runs all of them
     const int groups = total + C::H;           // source groups step 0 reads
     int gslot = 0;
+    int gi = 0, wi = 0; // C::MBAR: group index (ring slot / SRC_N) the loader fills / a round waits for next
     constexpr int PRO = C::H + C::LOOKAHEAD;
     loader_init<C, IS_V>(p, w);
     if constexpr (!IS_V) w.pend_j0 = kNoPend;
-    for (int g = 0; g < PRO; ++g) {
-        load_group<C, IS_V, false>(p, w, g, gslot, g < groups);
-        cp_async_commit();
-        gslot = (gslot + C::SRC_N == C::rsp0) ? 0 : gslot + C::SRC_N;
+    // one checked group: per-lane copies (clamped at the line's ends), completion through the
+    // lane's cp.async group or, C::MBAR, the group's mbarrier
+#define AVS_ISSUE_CHECKED(G)                                                                          \
+    {                                                                                                 \
+        const bool issue_ = (G) < groups;                                                             \
+        load_group<C, IS_V, false>(p, w, (G), gslot, issue_);                                         \
+        if constexpr (C::MBAR) {                                                                      \
+            if (issue_) mbar_arrive_cp_async(w.mbar0 + gi * 8);                                       \
+            gi = (gi + 1 == C::NG) ? 0 : gi + 1;                                                      \
+        } else {                                                                                      \
+            cp_async_commit();                                                                        \
+        }                                                                                             \
+        gslot = (gslot + C::SRC_N == C::rsp0) ? 0 : gslot + C::SRC_N;                                 \
+    }
+#define AVS_WAIT_GROUP()                                                                              \
+    {                                                                                                 \
+        mbar_wait(w.mbar0 + wi * 8, (w.mpar >> wi) & 1u);                                             \
+        w.mpar ^= 1u << wi;                                                                           \
+        wi = (wi + 1 == C::NG) ? 0 : wi + 1;                                                          \
+    }
+    for (int g = 0; g < PRO; ++g) AVS_ISSUE_CHECKED(g)
+    if constexpr (C::MBAR) {
+        // round r waits for group r + H; groups 0 .. H-1 have no round of their own
+        for (int g = 0; g < C::H; ++g) AVS_WAIT_GROUP()
     }
     // rounds [slo, shi]: every batch of every step and the source group issued are "steady"
     int slo = C::DELAY_LAST, shi = total - 1;
@@ -798,16 +1105,16 @@ AVS_FN void run_warp(const StreamParams& p, WarpRun<C, IS_V>& w, int strip, int 
 
 #define AVS_ROUND(STEADY)                                                                             \
     {                                                                                                 \
-        cp_async_wait<C::LOOKAHEAD - 1>(); /* groups <= r + H have landed (this lane's copies) */     \
+        if constexpr (C::MBAR) AVS_WAIT_GROUP()                                                       \
+        else cp_async_wait<C::LOOKAHEAD - 1>(); /* groups <= r + H have landed (this lane's copies) */ \
         AVS_SYNCWARP();                    /* ... all lanes'; round r-1 is done with its slots */     \
-        if constexpr (STEADY && C::PRE1) {                                                            \
-            preload_window<C, IS_V, 1, S1>(w);                                                        \
-            if constexpr (C::PRE2) preload_window<C, IS_V, 2, S2>(w);                                 \
-            if constexpr (!IS_V) sink_h_readback<C, C::MLAST>(w);                                     \
+        if constexpr (STEADY) {                                                                       \
+            load_group<C, IS_V, true>(p, w, r + PRO, gslot, true);                                    \
+            cp_async_commit();                                                                        \
+            gslot = (gslot + C::SRC_N == C::rsp0) ? 0 : gslot + C::SRC_N;                             \
+        } else {                                                                                      \
+            AVS_ISSUE_CHECKED(r + PRO)                                                                \
         }                                                                                             \
-        load_group<C, IS_V, STEADY>(p, w, r + PRO, gslot, r + PRO < groups);                          \
-        cp_async_commit();                                                                            \
-        gslot = (gslot + C::SRC_N == C::rsp0) ? 0 : gslot + C::SRC_N;                                 \
         _Pragma("unroll") for (int q = 0; q < C::reps0; ++q) run_batch<C, IS_V, EPI, 0, S0, STEADY>(p, w); \
         if (STEADY || r >= C::delay1) {                                                               \
             _Pragma("unroll") for (int q = 0; q < C::reps1; ++q) run_batch<C, IS_V, EPI, 1, S1, STEADY>(p, w); \
@@ -820,24 +1127,39 @@ AVS_FN void run_warp(const StreamParams& p, WarpRun<C, IS_V>& w, int strip, int 
     }
     int r = 0;
     while (r < total) {
-        if (C::STEADY_LOOP && r >= slo && r <= shi) {
-            // the hot loop: straight-line rounds
-            do {
-                AVS_ROUND(true)
-                ++r;
-            } while (r <= shi);
-        } else {
+        if constexpr (C::REGWIN) {
+            // the interior of the run in registers; what is left of it (fewer rounds than one
+            // trip of the unrolled loop) takes the checked path
+            const int n = (shi - r + 1) / C::RW_UNROLL * C::RW_UNROLL;
+            if (r == slo && n > 0) {
+                run_regwin<C, IS_V, EPI>(p, w, r, n, gslot, gi, wi);
+                r += n;
+                continue;
+            }
             AVS_ROUND(false)
             ++r;
+        } else {
+            if (C::STEADY_LOOP && r >= slo && r <= shi) {
+                // the hot loop: straight-line rounds
+                do {
+                    AVS_ROUND(true)
+                    ++r;
+                } while (r <= shi);
+            } else {
+                AVS_ROUND(false)
+                ++r;
+            }
         }
     }
 #undef AVS_ROUND
+#undef AVS_ISSUE_CHECKED
+#undef AVS_WAIT_GROUP
     if constexpr (!IS_V) {
         // the last batch is still in the staging rows
         sink_h_readback<C, C::MLAST>(w);
         sink_h_store<C, C::MLAST>(p, w);
     }
-    cp_async_wait<0>();
+    if constexpr (!C::MBAR) cp_async_wait<0>(); // (C::MBAR: every issued group has been waited for)
     AVS_SYNCWARP(); // the next run refills the rings
 }
 
@@ -857,6 +1179,21 @@ AVS_FN void stream_warp_main(const StreamParams& p, long long gw, long long nwar
     w.ring1 = w.ring0 + (IS_V ? (size_t)C::rsp0 * kPitchL : (size_t)C::SRC_RING_F2);
     w.ring2 = w.ring1 + (size_t)C::rsp1 * kPitchL;
     w.stage = w.ring2 + (size_t)C::rsp2 * kPitchL;
+    w.mbar0 = 0;
+    w.mpar = 0;
+    if constexpr (C::MBAR) {
+        // the warp's own barriers (behind its rings): every lane arrives once per group, either
+        // with its cp.async copies (checked rounds) or plainly beside lane 0's bulk copies
+        float2* bars = sm + (IS_V ? C::WARP_F2_V : C::WARP_F2_H) - C::MBAR_F2;
+        w.mbar0 = smem_u32(bars);
+#if defined(__CUDACC__)
+        if (lane == 0) {
+            for (int i = 0; i < C::NG; ++i) mbar_init(w.mbar0 + i * 8, 32);
+            mbar_init_fence();
+        }
+        __syncwarp();
+#endif
+    }
     const int rho_first = p.out0 / C::B, rho_last = (p.out1 - 1) / C::B;
     const int rps = rho_last - rho_first + 1;
     const int nstrips = (p.n_lines + kLines - 1) / kLines;
@@ -898,36 +1235,40 @@ stream_pass_kernel(const __grid_constant__ StreamParams p) {
 
 // Source look-ahead in rounds (LAH row pass, LAV column pass) is what shared memory affords at
 // 8 warps per SM: the row pass carries the staging rows, three-step chains a second
-// intermediate ring.  PRE_OK: the chain has room for the read-ahead variant (one more chunk
-// of every intermediate ring, paid for with one round of source look-ahead).
-template <class S0, class S1, class S2, int REPS_LAST, int LAH, int LAV, bool PRE_OK, int VAR, bool IS_V, int SRCT>
-using ChainV = ChainC<S0, S1, S2, REPS_LAST, (IS_V ? LAV : LAH) - ((PRE_OK && (VAR & 1)) ? 1 : 0), !((VAR >> 1) & 1),
-                      (PRE_OK && (VAR & 1)) ? 1 : 0, IS_V ? AVIRB200_F32 : SRCT>;
+// intermediate ring.  RWU: rounds per trip of the register-window loop (the source window of a
+// chain closes on itself -- no register moves at the loop's back edge -- after WR0 / SRC_N rounds,
+// rounded up; more rounds per trip cost instruction-cache reach).  VAR = ChainC MODE.
+#ifndef AVS_RWU_OVERRIDE
+#define AVS_RWU_OVERRIDE 0
+#endif
+template <class S0, class S1, class S2, int REPS_LAST, int LAH, int LAV, int RWU, int VAR, bool IS_V, int SRCT>
+using ChainV = ChainC<S0, S1, S2, REPS_LAST, (IS_V ? LAV : LAH), (VAR == 2 && !IS_V) ? 1 : VAR, IS_V ? AVIRB200_F32 : SRCT,
+                      AVS_RWU_OVERRIDE ? AVS_RWU_OVERRIDE : RWU>;
 
 // cfg3, float8_dil mirror (k = 2): RESIZE(24 taps, source step 2) -> 8-tap correction FIR
 template <int VAR, bool IS_V, int SRCT = AVIRB200_F32>
 using ChainDil24 = ChainV<StepC<K_RESIZE, AVIRB200_SUM_DIL8, 24, 2>, StepC<K_FIR, AVIRB200_SUM_DIL8, 8, 1>, NoStep,
-                          1, 2, 3, true, VAR, IS_V, SRCT>;
+                          1, 2, 3, 3, VAR, IS_V, SRCT>;
 // k = 2 in build mode 1, interleaved classes (fpclass_def<float>, fpclass_float4): RESIZE(24) -> FIR(7)
 template <int VAR, bool IS_V, int SRCT = AVIRB200_F32>
 using ChainInl24 = ChainV<StepC<K_RESIZE, AVIRB200_SUM_INL, 24, 2>, StepC<K_FIR, AVIRB200_SUM_INL, 7, 1>, NoStep,
-                          1, 2, 3, true, VAR, IS_V, SRCT>;
+                          1, 2, 3, 3, VAR, IS_V, SRCT>;
 // cfg3, float4 mirror (k = 2, build mode 0): FIR(7) -> RESIZE(18, source step 2) -> FIR(7)
 template <int VAR, bool IS_V, int SRCT = AVIRB200_F32>
 using ChainInl3 = ChainV<StepC<K_FIR, AVIRB200_SUM_INL, 7, 1>, StepC<K_RESIZE, AVIRB200_SUM_INL, 18, 2>,
-                         StepC<K_FIR, AVIRB200_SUM_INL, 7, 1>, 1, 1, 2, false, VAR, IS_V, SRCT>;
+                         StepC<K_FIR, AVIRB200_SUM_INL, 7, 1>, 1, 1, 2, 2, VAR, IS_V, SRCT>;
 // cfg4 (k = 4, build mode 0): FIR(15, decimation 2) -> RESIZE(18, source step 2) -> FIR(7)
 template <int VAR, bool IS_V, int SRCT = AVIRB200_F32>
 using ChainInl3D = ChainV<StepC<K_FIR, AVIRB200_SUM_INL, 15, 2>, StepC<K_RESIZE, AVIRB200_SUM_INL, 18, 2>,
-                          StepC<K_FIR, AVIRB200_SUM_INL, 7, 1>, 1, 1, 1, false, VAR, IS_V, SRCT>;
+                          StepC<K_FIR, AVIRB200_SUM_INL, 7, 1>, 1, 1, 1, 2, VAR, IS_V, SRCT>;
 // cfg5, float8_dil mirror (k = 4, build mode 1): RESIZE(56 taps, source step 4; 4-output batches) -> FIR(8)
 template <int VAR, bool IS_V, int SRCT = AVIRB200_F32>
 using ChainDil56 = ChainV<StepC<K_RESIZE, AVIRB200_SUM_DIL8, 56, 4, 4>, StepC<K_FIR, AVIRB200_SUM_DIL8, 8, 1>, NoStep,
-                          1, 1, 1, false, VAR, IS_V, SRCT>;
+                          1, 1, 1, 2, VAR, IS_V, SRCT>;
 // cfg2 (k = 0.5): FIR(7) -> RESIZE(24) over the virtual 2X line; 32 final outputs per round
 template <int VAR, bool IS_V, int SRCT = AVIRB200_F32>
 using ChainUp2 = ChainV<StepC<K_FIR, AVIRB200_SUM_INL, 7, 1>, StepC<K_RESIZE2, AVIRB200_SUM_INL, 24, 1>, NoStep,
-                        2, 1, 3, false, VAR, IS_V, SRCT>;
+                        2, 1, 3, 1, VAR, IS_V, SRCT>;
 
 template <class C>
 struct ChainTag {
@@ -941,7 +1282,7 @@ struct PassTag {
 
 // Calls f(ChainTag<Chain>(), PassTag<is_v>()) with the description of chain ID in scheduling
 // variant `variant` for the row pass (is_v false) or the column pass.  Integer sources (row
-// pass only) run the default row-pass variant whatever `variant` says: one instantiation each.
+// pass only) have two instantiations each: ring windows (variants 0, 3) and register windows.
 // One chain per call so that every chain's kernels can live in their own translation unit
 // (stream_chain.cu is compiled once per chain, in parallel).
 template <int ID, class F>
@@ -951,21 +1292,25 @@ inline bool stream_dispatch_chain(bool is_v, int variant, int src_type, F&& f) {
         if (is_v) f(ChainTag<NAME<N, true> >(), PassTag<true>());                         \
         else f(ChainTag<NAME<N, false> >(), PassTag<false>());                            \
         return true;
+// (variant 3, every round on the checked path, exists in the host emulation only: it is the
+// cross-check of the other variants' index logic, not something to launch)
+#if defined(__CUDACC__)
+#define AVS_V3(NAME)
+#else
+#define AVS_V3(NAME) AVS_V(NAME, 3)
+#endif
+#define AVS_INT_SRC(NAME, T)                                                              \
+    if (!is_v && src_type == T) {                                                         \
+        if (variant == 0 || variant == 3) f(ChainTag<NAME<0, false, T> >(), PassTag<false>()); \
+        else f(ChainTag<NAME<1, false, T> >(), PassTag<false>());                         \
+        return true;                                                                      \
+    }
 #define AVS_VARIANTS(NAME)                                                                \
-    if (!is_v && src_type == AVIRB200_U8) {                                               \
-        f(ChainTag<NAME<kStreamDefaultVariantH, false, AVIRB200_U8> >(), PassTag<false>()); \
-        return true;                                                                      \
-    }                                                                                     \
-    if (!is_v && src_type == AVIRB200_U16) {                                              \
-        f(ChainTag<NAME<kStreamDefaultVariantH, false, AVIRB200_U16> >(), PassTag<false>()); \
-        return true;                                                                      \
-    }                                                                                     \
-    if (!is_v && src_type == kSrcU8Srgb) {                                                \
-        f(ChainTag<NAME<kStreamDefaultVariantH, false, kSrcU8Srgb> >(), PassTag<false>()); \
-        return true;                                                                      \
-    }                                                                                     \
+    AVS_INT_SRC(NAME, AVIRB200_U8)                                                        \
+    AVS_INT_SRC(NAME, AVIRB200_U16)                                                       \
+    AVS_INT_SRC(NAME, kSrcU8Srgb)                                                         \
     switch (variant) {                                                                    \
-        AVS_V(NAME, 0) AVS_V(NAME, 1) AVS_V(NAME, 2) AVS_V(NAME, 3)                       \
+        AVS_V(NAME, 0) AVS_V(NAME, 1) AVS_V(NAME, 2) AVS_V3(NAME)                         \
     default: return false;                                                                \
     }
     if (variant < 0 || variant >= kStreamVariants) return false;
@@ -977,6 +1322,8 @@ inline bool stream_dispatch_chain(bool is_v, int variant, int src_type, F&& f) {
     else if constexpr (ID == kChainUp2) { AVS_VARIANTS(ChainUp2) }
     else return false;
 #undef AVS_VARIANTS
+#undef AVS_INT_SRC
+#undef AVS_V3
 #undef AVS_V
 }
 

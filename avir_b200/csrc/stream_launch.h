@@ -8,16 +8,23 @@ namespace avs {
 // Launches the chain kernel `chain` (StreamChainId) for one pass on `stream` (cudaStream_t).
 // epi: column pass output stage, stream_epilogue_code() (ignored for the row pass).
 // Returns 0 = launched, -2 = unknown chain, -1 = launch error.
-int stream_launch(int chain, bool is_v, int epi, const StreamParams& p, void* stream);
+// variant: scheduling variant (stream_types.h), < 0 = the pass's default; sm_count: of the device
+// the launch goes to (one persistent block per SM).
+int stream_launch(int chain, bool is_v, int epi, int variant, const StreamParams& p, int sm_count, void* stream);
 
-// One chain's launcher, specialised in that chain's own translation unit (stream_chain.cu).
-template <int ID>
-int stream_launch_chain(bool is_v, int variant, int epi, const StreamParams& p, void* stream);
-template <> int stream_launch_chain<kChainDil24>(bool, int, int, const StreamParams&, void*);
-template <> int stream_launch_chain<kChainInl24>(bool, int, int, const StreamParams&, void*);
-template <> int stream_launch_chain<kChainInl3>(bool, int, int, const StreamParams&, void*);
-template <> int stream_launch_chain<kChainInl3D>(bool, int, int, const StreamParams&, void*);
-template <> int stream_launch_chain<kChainDil56>(bool, int, int, const StreamParams&, void*);
-template <> int stream_launch_chain<kChainUp2>(bool, int, int, const StreamParams&, void*);
+// One pass of one chain, specialised in its own translation unit (stream_chain.cu is compiled
+// once per chain and pass: the kernels of a unit take minutes to compile, the units build in parallel).
+template <int ID, bool IS_V>
+int stream_launch_chain(int variant, int epi, const StreamParams& p, int sm_count, void* stream);
+#define AVS_DECL_CHAIN(ID)                                                                  \
+    template <> int stream_launch_chain<ID, false>(int, int, const StreamParams&, int, void*); \
+    template <> int stream_launch_chain<ID, true>(int, int, const StreamParams&, int, void*);
+AVS_DECL_CHAIN(kChainDil24)
+AVS_DECL_CHAIN(kChainInl24)
+AVS_DECL_CHAIN(kChainInl3)
+AVS_DECL_CHAIN(kChainInl3D)
+AVS_DECL_CHAIN(kChainDil56)
+AVS_DECL_CHAIN(kChainUp2)
+#undef AVS_DECL_CHAIN
 
 } // namespace avs

@@ -1,47 +1,33 @@
-// stream_pass.cu -- launch entry of the warp-streaming pass kernel: picks the scheduling variant
-// and routes to the chain's own translation unit (stream_chain.cu, compiled once per chain).
-#include <stdlib.h>
-
+// stream_pass.cu -- launch entry of the warp-streaming pass kernel: routes to the chain's and
+// pass's own translation unit (stream_chain.cu, compiled once per chain and pass).
 #include "stream_launch.h"
 
 namespace avs {
 
-// Scheduling variant of a pass: AVIRB200_STREAM_VARIANT_H / _V (or AVIRB200_STREAM_VARIANT for
-// both) override the defaults; tuning and test switch, every variant computes the same bits.
-int stream_variant(bool is_v) {
-    static const int v[2] = {
-        [] {
-            const char* e = getenv("AVIRB200_STREAM_VARIANT_H");
-            if (!e) e = getenv("AVIRB200_STREAM_VARIANT");
-            const int x = e ? atoi(e) : kStreamDefaultVariantH;
-            return (x >= 0 && x < kStreamVariants) ? x : kStreamDefaultVariantH;
-        }(),
-        [] {
-            const char* e = getenv("AVIRB200_STREAM_VARIANT_V");
-            if (!e) e = getenv("AVIRB200_STREAM_VARIANT");
-            const int x = e ? atoi(e) : kStreamDefaultVariantV;
-            return (x >= 0 && x < kStreamVariants) ? x : kStreamDefaultVariantV;
-        }()};
-    return v[is_v ? 1 : 0];
-}
-
-int stream_launch(int chain, bool is_v, int epi, const StreamParams& p, void* stream) {
-    const int var = stream_variant(is_v);
+int stream_launch(int chain, bool is_v, int epi, int variant, const StreamParams& p, int sm_count, void* stream) {
+    // scheduling variant (a per-plan option, AVIRB200_OPT_STREAM_VARIANT_H / _V); every variant
+    // computes the same bits (variant 3, all rounds on the checked path, is host-emulation only)
+    const int var = (variant >= 0 && variant < 3) ? variant : (is_v ? kStreamDefaultVariantV : kStreamDefaultVariantH);
+#define AVS_ROUTE(ID)                                                                              \
+    case ID:                                                                                       \
+        return is_v ? stream_launch_chain<ID, true>(var, epi, p, sm_count, stream)                 \
+                    : stream_launch_chain<ID, false>(var, epi, p, sm_count, stream);
     switch (chain) {
-    case kChainDil24: return stream_launch_chain<kChainDil24>(is_v, var, epi, p, stream);
-    case kChainInl24: return stream_launch_chain<kChainInl24>(is_v, var, epi, p, stream);
-    case kChainInl3: return stream_launch_chain<kChainInl3>(is_v, var, epi, p, stream);
-    case kChainInl3D: return stream_launch_chain<kChainInl3D>(is_v, var, epi, p, stream);
+        AVS_ROUTE(kChainDil24)
+        AVS_ROUTE(kChainInl24)
+        AVS_ROUTE(kChainInl3)
+        AVS_ROUTE(kChainInl3D)
 #ifdef AVS_WITH_DIL56
-    // Not in the default build: the chain loses to the tile kernel on B200 (stream_types.h) and its
-    // kernels take ~18 minutes to compile; AVIRB200_BUILD_ALL_CHAINS=1 python avir_b200/build.py
-    // builds them (then selectable with AVIRB200_STREAM_ALL=1).  Without them the engine falls
-    // back to the tile kernel (return -2 = no such instantiation).
-    case kChainDil56: return stream_launch_chain<kChainDil56>(is_v, var, epi, p, stream);
+        // Not in the default build: the chain loses to the tile kernel on B200 (stream_types.h) and
+        // its kernels take long to compile; AVIRB200_BUILD_ALL_CHAINS=1 python avir_b200/build.py
+        // builds them (then selectable with AVIRB200_OPT_ALL_STREAM_CHAINS).  Without them the engine
+        // falls back to the tile kernel (return -2 = no such instantiation).
+        AVS_ROUTE(kChainDil56)
 #endif
-    case kChainUp2: return stream_launch_chain<kChainUp2>(is_v, var, epi, p, stream);
+        AVS_ROUTE(kChainUp2)
     default: return -2;
     }
+#undef AVS_ROUTE
 }
 
 } // namespace avs

@@ -52,6 +52,10 @@ struct StreamParams {
     float out_gamma_mult;
     int round_mode;
     float tr_mul, tr_mul_inv, pk_out;
+    // column pass, scheduling variant 2: CUtensorMap over the intermediate buffer (2-D, fp32:
+    // n_lines * 4 elements per row, rows from p.src on; box 64 elements x SRC_N rows), encoded by
+    // the launcher (stream_chain.cu)
+    alignas(64) unsigned char tmap[128];
 };
 
 enum StreamChainId {
@@ -65,12 +69,15 @@ enum StreamChainId {
     kChainCount
 };
 
-// Scheduling variants (same arithmetic): bit 0 = later steps' windows read ahead at the top of
-// a round (one more round of delay and ring; the source look-ahead shrinks by a round to stay
-// within shared memory), bit 1 = no separate straight-line loop for the interior rounds.
-// Measured on cfg3 with the packed arithmetic (profiles/r01_variant_sweeps_packed.jsonl): both
-// passes are fastest with the straight-line loop and without read-ahead (variant 0); with the
-// scalar arithmetic the column pass preferred variant 3 (profiles/r01_variant_sweeps.jsonl).
+// Scheduling variants (same arithmetic; ChainC MODE in stream_kernel.cuh):
+//   0  ring windows: every batch reads its whole window from the per-warp shared-memory rings
+//   1  register windows: in the interior of a run the windows slide through registers, shared
+//      memory carries the source ring only (each input read once)
+//   2  = 1 with the column pass's source ring filled by one lane's tensor copies (TMA,
+//      cp.async.bulk.tensor.2d) and tracked by mbarriers instead of per-lane cp.async groups
+//      (the row pass runs 1)
+//   3  = 0 without the straight-line loop for the interior rounds (every round takes the
+//      checked path: the cross-check of the other three)
 constexpr int kStreamVariants = 4;
 constexpr int kStreamDefaultVariantH = 0, kStreamDefaultVariantV = 0;
 

@@ -106,6 +106,12 @@ public:
     void* Stream = nullptr; // B200 extension: cudaStream_t for resizeImageDevice()
 };
 
+// B200 extension: tuning / test options applied to every plan a call uses (avirb200_option in
+// avirb200.h, indexed by option id; -1 = the plan's default).  None changes a result bit.
+struct CImageResizerTuning {
+    int opt[6] = {-1, -1, -1, -1, -1, -1};
+};
+
 // ---- fpclass tags -------------------------------------------------------------------------
 // Tag types naming the upstream processing class to mirror (upstream avir.h:4569-4592,
 // avir_float4_sse.h:331, avir_float8_avx.h:370).
@@ -195,8 +201,24 @@ struct PlanHolder {
     avirb200::plan::ImagePlan ip;
     avirb200_plan_desc desc;
     avirb200_plan* dev = nullptr;
+    int el_count_io = 0;
     ~PlanHolder() { if (dev != nullptr) avirb200_plan_destroy(dev); }
+    // the informational outputs of a call (upstream fills them on every call, avir.h:2473-2547)
+    void fillVars(CImageResizerVarsBase& v) const {
+        v.ElCount = ip.el_count;
+        v.ElCountIO = el_count_io;
+        v.k = ip.kx; v.o = ip.ox;
+        v.InGammaMult = ip.in_gamma_mult;
+        v.OutGammaMult = ip.out_gamma_mult;
+        v.BuildModeH = ip.h.mode; v.BuildModeV = ip.v.mode;
+    }
 };
+
+// Process-wide default of the tuning options (what tests and sweeps set through the C driver).
+inline CImageResizerTuning& default_tuning() {
+    static CImageResizerTuning t;
+    return t;
+}
 
 inline bool fill_axis(avirb200_axis_desc& ad, const avirb200::plan::AxisPlan& ap, bool dil,
                       bool is_h, int channels) {
@@ -359,14 +381,35 @@ public:
             !b200_detail::fill_axis(d.v, ph->ip.v, dil, false, ElCountIO))
             throw std::runtime_error("avir_b200: this filtering chain is not available on the "
                                      "GPU path (upsampling factor other than 2)");
-        Vars.ElCount = ph->ip.el_count;
-        Vars.ElCountIO = ElCountIO;
-        Vars.k = ph->ip.kx; Vars.o = ph->ip.ox;
-        Vars.InGammaMult = ph->ip.in_gamma_mult;
-        Vars.OutGammaMult = ph->ip.out_gamma_mult;
-        Vars.BuildModeH = ph->ip.h.mode; Vars.BuildModeV = ph->ip.v.mode;
+        ph->el_count_io = ElCountIO;
+        ph->fillVars(Vars);
         return ph;
     }
+
+    // B200 extension: a batch of equally shaped frames on the device (video): one plan, one
+    // launch pair per frame, all on Vars.Stream; the frames share `Workspace`.
+    template <typename Tin, typename Tout>
+    void resizeImageDeviceBatch(const int FrameCount, const Tin* const* const dSrcBufs, const int SrcWidth,
+                                const int SrcHeight, int SrcScanlineSize, Tout* const* const dNewBufs,
+                                const int NewWidth, const int NewHeight, const int ElCountIO, const double k,
+                                void* const Workspace, CImageResizerVars* const aVars = nullptr) const {
+        if (SrcWidth == 0 || SrcHeight == 0 || NewWidth == 0 || NewHeight == 0)
+            throw std::runtime_error("avir_b200: resizeImageDeviceBatch needs non-empty images");
+        CImageResizerVars DefVars;
+        CImageResizerVars& Vars = (aVars == nullptr ? DefVars : *aVars);
+        if (SrcScanlineSize < 1) SrcScanlineSize = SrcWidth * ElCountIO;
+        std::shared_ptr<b200_detail::PlanHolder> ph =
+            getPlan<Tin, Tout>(SrcWidth, SrcHeight, NewWidth, NewHeight, ElCountIO, k, Vars);
+        b200_detail::check(avirb200_resize_device_batch(ph->dev, FrameCount,
+                                                        reinterpret_cast<const void* const*>(dSrcBufs),
+                                                        (size_t)SrcScanlineSize,
+                                                        reinterpret_cast<void* const*>(dNewBufs),
+                                                        (size_t)NewWidth * ElCountIO, Workspace, Vars.Stream),
+                           "resizeImageDeviceBatch");
+    }
+
+    // B200 extension: per-object tuning options (see CImageResizerTuning).
+    mutable CImageResizerTuning Tuning;
 
     // Drops cached plans (device tables and staging buffers).
     void clearPlanCache() const {
@@ -392,17 +435,27 @@ private:
         const Key key(b200_detail::dtype_of<Tin>::value, b200_detail::dtype_of<Tout>::value,
                       SrcWidth, SrcHeight, NewWidth, NewHeight, ElCountIO, k, Vars.ox, Vars.oy,
                       Vars.UseSRGBGamma, Vars.AlphaIndex, Vars.BuildMode);
+        std::shared_ptr<b200_detail::PlanHolder> ph;
         {
             std::lock_guard<std::mutex> lk(Mx);
             auto it = Cache.find(key);
-            if (it != Cache.end()) return it->second;
+            if (it != Cache.end()) ph = it->second;
         }
-        std::shared_ptr<b200_detail::PlanHolder> ph = buildDescriptor<Tin, Tout>(
-            SrcWidth, SrcHeight, NewWidth, NewHeight, ElCountIO, k, Vars);
-        b200_detail::check(avirb200_plan_create(&ph->desc, &ph->dev), "plan_create");
-        std::lock_guard<std::mutex> lk(Mx);
-        if (Cache.size() >= 16) Cache.clear(); // bound device memory held by cached plans
-        Cache[key] = ph;
+        if (ph) {
+            // A cached plan is the plan of the FIRST call with this key.  Upstream re-plans every
+            // call, and its build-mode choice reads the filter bank's lazily built phases (avir.h:
+            // 4813-4847, 6206-6270), so a repeated identical call may pick another mode there; here a
+            // repeated call repeats the first call's bits.  Vars' outputs are refreshed either way.
+            ph->fillVars(Vars);
+        } else {
+            ph = buildDescriptor<Tin, Tout>(SrcWidth, SrcHeight, NewWidth, NewHeight, ElCountIO, k, Vars);
+            b200_detail::check(avirb200_plan_create(&ph->desc, &ph->dev), "plan_create");
+            std::lock_guard<std::mutex> lk(Mx);
+            if (Cache.size() >= 16) Cache.clear(); // bound the device tables held by cached plans
+            Cache[key] = ph;
+        }
+        const CImageResizerTuning& t = b200_detail::default_tuning();
+        for (int i = 0; i < 6; ++i) avirb200_plan_set_option(ph->dev, i, Tuning.opt[i] >= 0 ? Tuning.opt[i] : t.opt[i]);
         return ph;
     }
 };

@@ -158,6 +158,36 @@ int avirb200_resize_host(avirb200_plan* plan, const void* h_src, size_t src_pitc
 /* Number of kernel launches the last avirb200_resize_device on this plan issued. */
 int avirb200_plan_last_launches(const avirb200_plan* plan);
 
+/* Video / batch entry: `n` frames of the plan's geometry, one launch pair per frame, all on
+ * `stream` in order (the frames share `d_workspace`: stream order keeps them apart).  d_srcs /
+ * d_dsts are HOST arrays of n device pointers; pitches as in avirb200_resize_device.  The
+ * plan-building cost (host filter design, table upload) is paid once for the whole batch --
+ * upstream's equivalent is re-using one CImageResizer object and its Vars across frames. */
+int avirb200_resize_device_batch(const avirb200_plan* plan, int n, const void* const* d_srcs,
+                                 size_t src_pitch, void* const* d_dsts, size_t dst_pitch,
+                                 void* d_workspace, void* stream);
+
+/* Per-plan options (tuning and test switches; none changes a result bit).  Options are plan
+ * state: set them while no call on the plan is in flight.  value < 0 restores the default. */
+typedef enum avirb200_option {
+    /* kernel family order: 0 = streaming kernel where the chain is regular, else the tile kernel,
+     * else the generic kernel (default); 1 = generic kernel only; 2 = tile kernel, else generic */
+    AVIRB200_OPT_KERNEL_FAMILY = 0,
+    /* scheduling variant of the streaming row / column pass: 0 ring windows, 1 register windows,
+     * 2 register windows + TMA-staged source ring (column pass) */
+    AVIRB200_OPT_STREAM_VARIANT_H = 1,
+    AVIRB200_OPT_STREAM_VARIANT_V = 2,
+    /* avirb200_resize_host: number of row bands of the pipelined form (1 = unbanded; default by size) */
+    AVIRB200_OPT_HOST_BANDS = 3,
+    /* 1: also select the streaming chains that measured slower than the tile kernel (upsizing, 56-tap) */
+    AVIRB200_OPT_ALL_STREAM_CHAINS = 4,
+    /* avirb200_resize_sharded: 1 (default) = boundary rows first, halo rows pushed into the
+     * neighbours' mailboxes over NVLink while the interior rows are filtered; 0 = NCCL send/recv
+     * between the two passes */
+    AVIRB200_OPT_OVERLAP_HALO = 5
+} avirb200_option;
+int avirb200_plan_set_option(avirb200_plan* plan, int option, int value);
+
 /* ---- row-sharded multi-GPU path (one process per GPU) -------------------------------- */
 
 /* Source/destination row ranges rank `rank` of `nranks` owns, and the intermediate rows it
@@ -186,10 +216,21 @@ void avirb200_comm_destroy(void* comm);
 /* d_src holds this rank's source band (src_rows rows), d_dst receives its destination band
  * (dst_rows rows).  Row pass -> NCCL halo send/recv with rank-1/rank+1 -> column pass, all
  * enqueued on `stream`.  `comm` is an ncclComm_t (from avirb200_comm_create or the
- * caller's own).  Output is bit-identical to the single-GPU path. */
+ * caller's own).  Output is bit-identical to the single-GPU path.
+ * Default schedule (AVIRB200_OPT_OVERLAP_HALO): the rows the neighbours need are filtered first
+ * and pushed (copy engine, NVLink peer memory mapped through CUDA IPC; the handles travel over
+ * `comm` once per plan) into the neighbours' mailboxes while the interior rows are filtered; the
+ * column pass waits for the neighbours' flags.  The first call on a plan is collective (every
+ * rank must make it).  Where peer mapping is unavailable the NCCL send/recv schedule runs. */
 int avirb200_resize_sharded(const avirb200_plan* plan, void* comm, int rank, int nranks,
                             const void* d_src, size_t src_pitch, void* d_dst, size_t dst_pitch,
                             void* d_workspace, void* stream);
+
+/* The same with HOST buffers (this rank's source band in, its destination band out): copies
+ * in, avirb200_resize_sharded on the plan's own stream, copies out, synchronises.  Staging
+ * buffers are cached in the plan.  The multi-GPU form of avirb200_resize_host. */
+int avirb200_resize_sharded_host(avirb200_plan* plan, void* comm, int rank, int nranks,
+                                 const void* h_src, size_t src_pitch, void* h_dst, size_t dst_pitch);
 
 /* Validation aid: runs the `nranks` bands of the sharded schedule one after another on the
  * CURRENT device (halo rows moved with device copies instead of NCCL).  Full-image device
@@ -197,11 +238,6 @@ int avirb200_resize_sharded(const avirb200_plan* plan, void* comm, int rank, int
 int avirb200_resize_sharded_local(const avirb200_plan* plan, int nranks, const void* d_src,
                                   size_t src_pitch, void* d_dst, size_t dst_pitch,
                                   void* d_workspace, void* stream);
-
-/* Test switch selecting the kernel family: 0 = product order (streaming kernel where the
- * chain is regular, else the tile kernel, else the generic kernel); 1 = generic kernel only;
- * 2 = tile kernel, else generic (no streaming kernel). */
-void avirb200_debug_force_generic(int mode);
 
 /* Which specialised kernels the plan's passes qualify for: bit 0 / 1 = row / column pass on
  * the warp-streaming kernel, bit 2 / 3 = row / column pass on the tile kernel. */

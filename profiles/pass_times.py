@@ -2,7 +2,7 @@
 """Device-resident timing of the two passes of one config (CUDA events, 3 warm-ups, median of
 N), with a checksum of the output so that scheduling variants can be compared bit for bit.
 
-    AVIRB200_STREAM_VARIANT=3 python profiles/pass_times.py [--mirror dil] [--n 20]
+    python profiles/pass_times.py --cfg cfg3 --var-h 1 --var-v 2 [--n 20]
 """
 import argparse
 import ctypes as C
@@ -26,7 +26,9 @@ CFG = {  # name: (fpclass, sw, sh, nw, nh, tin, tout, resbits, kwargs)
     "cfg5": (2, 7680, 4320, 1920, 1080, np.uint8, np.uint8, 8, {"gamma": True, "alpha": 3}),
     "u8k": (1, 7680, 4320, 3840, 2160, np.uint8, np.uint8, 8, {}),
     "u8kdil": (2, 7680, 4320, 3840, 2160, np.uint8, np.uint8, 8, {}),
+    "rgb": (0, 5184, 3456, 1920, 1280, np.uint8, np.uint8, 8, {}),   # upstream README case (3 channels)
 }
+CH = {"rgb": 3}
 TT = {np.uint8: torch.uint8, np.uint16: torch.uint16, np.float32: torch.float32}
 
 
@@ -35,22 +37,32 @@ def main():
     ap.add_argument("--cfg", default="cfg3")
     ap.add_argument("--n", type=int, default=20)
     ap.add_argument("--only", default="both", choices=["both", "row", "col"])
+    ap.add_argument("--var-h", type=int, default=-1, help="scheduling variant of the streaming row pass")
+    ap.add_argument("--var-v", type=int, default=-1, help="scheduling variant of the streaming column pass")
+    ap.add_argument("--family", type=int, default=-1, help="kernel family: 0 product order, 1 generic, 2 tile")
+    ap.add_argument("--all-chains", type=int, default=-1)
     a = ap.parse_args()
     fp, sw, sh, nw, nh, ti, to, rb, kw = CFG[a.cfg]
+    ch = CH.get(a.cfg, 4)
     lib = ab.lib()
     rs = ab.CImageResizer(rb, 0, 0, fp)
     v = ab.CImageResizerVars(UseSRGBGamma=kw.get("gamma", False), AlphaIndex=kw.get("alpha", -1))
-    h, dp, modes = rs.descriptor((sh, sw, 4), ti, nw, nh, to, 0.0, v)
+    h, dp, modes = rs.descriptor((sh, sw, ch), ti, nw, nh, to, 0.0, v)
     plan = C.c_void_p()
     assert lib.avirb200_plan_create(C.c_void_p(dp), C.byref(plan)) == 0, lib.avirb200_last_error()
+    lib.avirb200_plan_set_option.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    for opt, val in ((ab.OPT_STREAM_VARIANT_H, a.var_h), (ab.OPT_STREAM_VARIANT_V, a.var_v),
+                     (ab.OPT_KERNEL_FAMILY, a.family), (ab.OPT_ALL_STREAM_CHAINS, a.all_chains)):
+        if val >= 0:
+            assert lib.avirb200_plan_set_option(plan, opt, val) == 0
     g = torch.Generator(device="cuda")
     g.manual_seed(1)
     if ti == np.float32:
-        d_src = torch.rand((sh, sw, 4), generator=g, device="cuda", dtype=torch.float32)
+        d_src = torch.rand((sh, sw, ch), generator=g, device="cuda", dtype=torch.float32)
     else:
         hi = 256 if ti == np.uint8 else 65536
-        d_src = torch.randint(0, hi, (sh, sw, 4), generator=g, device="cuda", dtype=torch.int32).to(TT[ti])
-    d_dst = torch.zeros((nh, nw, 4), device="cuda", dtype=TT[to])
+        d_src = torch.randint(0, hi, (sh, sw, ch), generator=g, device="cuda", dtype=torch.int32).to(TT[ti])
+    d_dst = torch.zeros((nh, nw, ch), device="cuda", dtype=TT[to])
     wsb = C.c_size_t()
     assert lib.avirb200_plan_workspace_bytes(plan, C.byref(wsb)) == 0
     d_ws = torch.empty(wsb.value, dtype=torch.uint8, device="cuda")
@@ -60,10 +72,10 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
     def row():
-        assert lib.avirb200_row_pass_device(plan, d_src.data_ptr(), sw * 4, d_ws.data_ptr(), st) == 0
+        assert lib.avirb200_row_pass_device(plan, d_src.data_ptr(), sw * ch, d_ws.data_ptr(), st) == 0
 
     def col():
-        assert lib.avirb200_col_pass_device(plan, d_ws.data_ptr(), d_dst.data_ptr(), nw * 4, st) == 0
+        assert lib.avirb200_col_pass_device(plan, d_ws.data_ptr(), d_dst.data_ptr(), nw * ch, st) == 0
 
     def med(fn):
         for _ in range(3):
@@ -84,9 +96,8 @@ def main():
     cms = med(col) if a.only != "row" else None
     digest = hashlib.sha1(d_dst.cpu().numpy().tobytes()).hexdigest()[:16]
     paths = lib.avirb200_plan_kernel_paths(plan)
-    print(json.dumps({"cfg": a.cfg, "variant_h": os.environ.get("AVIRB200_STREAM_VARIANT_H", "default"),
-                      "variant_v": os.environ.get("AVIRB200_STREAM_VARIANT_V", "default"),
-                      "stream_disabled": os.environ.get("AVIRB200_DISABLE_STREAM", "0"),
+    print(json.dumps({"cfg": a.cfg, "variant_h": a.var_h, "variant_v": a.var_v, "family": a.family,
+                      "all_chains": a.all_chains,
                       "kernel_paths": paths, "row_ms": rms, "col_ms": cms,
                       "out_sha1": digest, "build_modes": list(modes)}))
     lib.avirb200_plan_destroy(plan)

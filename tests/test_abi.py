@@ -69,3 +69,43 @@ def test_lancir_argument_errors_follow_upstream():
     # lancir.h:392-408: bad sizes / la < 2 -> 0
     r, _ = ab.CLancIR().resizeImage(np.zeros((8, 8, 4), np.uint8), 4, 4, ab.CLancIRParams(la=1.5))
     assert r == 0
+
+
+def test_plan_options_reject_bad_arguments():
+    lib = ab.lib()
+    lib.avirb200_plan_set_option.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    assert lib.avirb200_plan_set_option(None, 0, 0) == -1
+    assert lib.avirb200_resize_device_batch(None, 0, None, 0, None, 0, None, None) == -1
+    assert lib.avirb200_resize_sharded_host(None, None, 0, 1, None, 0, None, 0) == -1
+
+
+def test_host_generator_is_the_survey_generator():
+    """bench.py's synthetic input (C loop in the host driver library) == the SURVEY 8(d) xorshift32
+    generator as the tests spell it in Python."""
+    import oracle_ref as o
+    hl = ab.host_lib()
+    hl.avirb200_host_fill_xorshift32.argtypes = [C.c_void_p, C.c_size_t, C.c_uint32, C.c_int]
+    hl.avirb200_host_fill_xorshift32.restype = C.c_uint32
+    for dt, code in ((np.uint8, 0), (np.uint16, 1), (np.float32, 2)):
+        want = o.xorshift32_image(7, 11, 3, dt, seed=12345)
+        got = np.empty((7, 11, 3), dt)
+        hl.avirb200_host_fill_xorshift32(got.ctypes.data, got.size, 12345, code)
+        assert np.array_equal(want.view(np.uint8), got.view(np.uint8)), dt
+
+
+def test_lancir_rejects_double_buffers():
+    with pytest.raises(ab.AvirB200Error):
+        ab.CLancIR().resizeImage(np.zeros((8, 8, 4), np.float64), 4, 4)
+    with pytest.raises(ab.AvirB200Error):
+        ab.CLancIR().resizeImage(np.zeros((8, 8, 4), np.uint8), 4, 4, out_dtype=np.float64)
+
+
+def test_vars_outputs_are_filled_on_plan_cache_hits():
+    """A second identical call (served from the front-end's plan cache) reports the same
+    informational Vars outputs as the first."""
+    hl = ab.host_lib()
+    hl.avirb200_host_vars_probe.argtypes = [C.c_int] * 4 + [C.c_void_p]
+    out = (C.c_double * 8)()
+    assert hl.avirb200_host_vars_probe(64, 48, 100, 75, out) == 0
+    first, second = list(out)[:4], list(out)[4:]
+    assert first == second and first[0] == 4 and first[2] > 0.0 and first[3] >= 0

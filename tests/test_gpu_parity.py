@@ -40,9 +40,9 @@ def kernel_path(request):
     """Every parity case runs in the product's kernel order (warp-streaming kernel where the
     chain is regular, else the tile kernel, else the generic kernel), with the streaming
     kernel switched off (tile kernel where it applies), and through the fully generic kernel."""
-    ab.lib().avirb200_debug_force_generic(request.param)
+    ab.set_option(ab.OPT_KERNEL_FAMILY, request.param)
     yield request.param
-    ab.lib().avirb200_debug_force_generic(0)
+    ab.set_option(ab.OPT_KERNEL_FAMILY, -1)
 
 
 def test_native_library_is_what_runs():
@@ -115,11 +115,11 @@ def test_generic_and_fast_kernels_agree_on_medium():
     case = MEDIUM[0]
     src = cs.make_input(case, seed=5)
     a = cs.gpu_output(case, src)
-    ab.lib().avirb200_debug_force_generic(1)
+    ab.set_option(ab.OPT_KERNEL_FAMILY, 1)
     try:
         b = cs.gpu_output(case, src)
     finally:
-        ab.lib().avirb200_debug_force_generic(0)
+        ab.set_option(ab.OPT_KERNEL_FAMILY, -1)
     assert cs.count_mismatch(a, b) == 0
 
 
@@ -134,13 +134,14 @@ def test_generic_and_fast_kernels_agree_on_medium():
 ], ids=cs.case_id)
 def test_deselected_streaming_chains_bit_exact(case):
     """The upsizing and the 56-tap chain run on the tile kernel by default (it measured faster);
-    AVIRB200_STREAM_ALL=1 selects their streaming instantiations, which must give the same bits."""
+    the ALL_STREAM_CHAINS plan option selects their streaming instantiations, which must give
+    the same bits."""
     src = cs.make_input(case, seed=31)
-    os.environ["AVIRB200_STREAM_ALL"] = "1"
+    ab.set_option(ab.OPT_ALL_STREAM_CHAINS, 1)
     try:
-        got = cs.gpu_output(case, src)  # (geometries no other test plans: plans are cached per call shape)
+        got = cs.gpu_output(case, src)
     finally:
-        del os.environ["AVIRB200_STREAM_ALL"]
+        ab.set_option(ab.OPT_ALL_STREAM_CHAINS, -1)
     assert cs.count_mismatch(expected(case, src), got) == 0
 
 
@@ -151,15 +152,15 @@ def test_deselected_streaming_chains_bit_exact(case):
                                   (0, 300, 200, 431, 287, 3, np.uint8, np.uint8, 8, {})], ids=cs.case_id)
 def test_banded_host_call_matches_single_band(case, bands):
     """avirb200_resize_host cuts large images into row bands so that PCIe transfers overlap the
-    kernels; the band count must not change a bit (AVIRB200_HOST_BANDS forces it)."""
+    kernels; the band count must not change a bit (the HOST_BANDS plan option forces it)."""
     src = cs.make_input(case, seed=23)
-    os.environ["AVIRB200_HOST_BANDS"] = "1"
+    ab.set_option(ab.OPT_HOST_BANDS, 1)
     try:
         one = cs.gpu_output(case, src)
-        os.environ["AVIRB200_HOST_BANDS"] = str(bands)
+        ab.set_option(ab.OPT_HOST_BANDS, bands)
         many = cs.gpu_output(case, src)
     finally:
-        del os.environ["AVIRB200_HOST_BANDS"]
+        ab.set_option(ab.OPT_HOST_BANDS, -1)
     assert cs.count_mismatch(one, many) == 0
     if o.have_ref():
         assert cs.count_mismatch(expected(case, src), many) == 0
@@ -170,14 +171,14 @@ def test_banded_host_call_in_place():
     case = (1, 512, 512, 256, 256, 4, np.uint8, np.uint8, 8, {})
     src = cs.make_input(case, seed=29)
     want = cs.gpu_output(case, src)
-    os.environ["AVIRB200_HOST_BANDS"] = "4"  # the overlap check must win over the forced banding
+    ab.set_option(ab.OPT_HOST_BANDS, 4)  # the overlap check must win over the forced banding
     try:
         buf = src.copy()
         rs = ab.CImageResizer(8, 0, 0, ab.FP_FLOAT4)
         dst = buf.reshape(-1)[:256 * 256 * 4].reshape(256, 256, 4)
         out = rs.resizeImage(buf, 256, 256, NewBuf=dst)
     finally:
-        del os.environ["AVIRB200_HOST_BANDS"]
+        ab.set_option(ab.OPT_HOST_BANDS, -1)
     assert cs.count_mismatch(want, out) == 0
 
 
@@ -218,6 +219,69 @@ def test_full_size_baseline_configs_bit_exact(name, case):
                        **cs.ref_kwargs(kw))
     got = _device_run(case, src)
     assert cs.count_mismatch(ref, got) == 0
+
+
+@needs_ref
+def test_full_size_cfg4_bit_exact():
+    """BASELINE configs[3] at full size, 16384^2 -> 4096^2 RGBA u16, against multi-threaded
+    upstream (a few seconds per thread-second of a 1.07 GB intermediate)."""
+    case = (1, 16384, 16384, 4096, 4096, 4, np.uint16, np.uint16, 16, {})
+    fp, sw, sh, nw, nh, ch, ti, to, rb, kw = case
+    src = o.lcg_image(sh, sw, ch, ti, seed=4)
+    ref = o.ref_resize(src, nw, nh, to, fpclass=fp, resbits=rb, nthreads=_oracle_threads())
+    got = _device_run(case, src)
+    assert cs.count_mismatch(ref, got) == 0
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2])
+@pytest.mark.parametrize("case", [
+    (2, 1920, 1080, 960, 540, 4, np.float32, np.float32, 16, {}),          # cfg3 chain
+    (2, 1000, 531, 500, 266, 4, np.float32, np.uint8, 8, {}),              # ragged strips, integer output
+    (1, 1920, 1080, 960, 540, 4, np.float32, np.float32, 16, {}),          # float4 mirror: 3-step chain
+    (1, 2048, 1024, 512, 256, 4, np.uint16, np.uint16, 16, {}),            # cfg4 chain, integer source
+    (1, 1920, 1080, 960, 540, 4, np.uint8, np.uint8, 8, {}),               # k = 2 mode 1, u8
+], ids=cs.case_id)
+def test_stream_scheduling_variants_bit_exact(case, variant):
+    """Scheduling variants of the streaming kernel (0 ring windows, 1 register windows, 2 register
+    windows + TMA-staged column pass): same bits as upstream."""
+    src = cs.make_input(case, seed=51)
+    ab.set_option(ab.OPT_STREAM_VARIANT_H, variant)
+    ab.set_option(ab.OPT_STREAM_VARIANT_V, variant)
+    try:
+        got = cs.gpu_output(case, src)
+    finally:
+        ab.set_option(ab.OPT_STREAM_VARIANT_H, -1)
+        ab.set_option(ab.OPT_STREAM_VARIANT_V, -1)
+    assert cs.count_mismatch(expected(case, src), got) == 0
+
+
+def test_batch_entry_matches_single_calls():
+    """avirb200_resize_device_batch: n frames through one plan = n single calls."""
+    import torch
+    case = (2, 640, 360, 320, 180, 4, np.float32, np.float32, 16, {})
+    fp, sw, sh, nw, nh, ch, ti, to, rb, kw = case
+    rs, v = cs.resizer_and_vars(case)
+    h, dp, _ = rs.descriptor((sh, sw, ch), ti, nw, nh, to, 0.0, v)
+    lib = ab.lib()
+    plan = C.c_void_p()
+    assert lib.avirb200_plan_create(C.c_void_p(dp), C.byref(plan)) == 0
+    wsb = C.c_size_t()
+    assert lib.avirb200_plan_workspace_bytes(plan, C.byref(wsb)) == 0
+    n = 5
+    srcs = [torch.from_numpy(cs.make_input(case, seed=60 + i)).cuda() for i in range(n)]
+    dsts = [torch.zeros((nh, nw, ch), device="cuda") for _ in range(n)]
+    d_ws = torch.empty(wsb.value, dtype=torch.uint8, device="cuda")
+    sp = (C.c_void_p * n)(*[t.data_ptr() for t in srcs])
+    dpp = (C.c_void_p * n)(*[t.data_ptr() for t in dsts])
+    lib.avirb200_resize_device_batch.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p,
+                                                 C.c_size_t, C.c_void_p, C.c_void_p]
+    assert lib.avirb200_resize_device_batch(plan, n, sp, sw * ch, dpp, nw * ch, d_ws.data_ptr(), None) == 0
+    torch.cuda.synchronize()
+    lib.avirb200_plan_destroy(plan)
+    rs.free_descriptor(h)
+    for i in range(n):
+        want = expected(case, srcs[i].cpu().numpy())
+        assert cs.count_mismatch(want, dsts[i].cpu().numpy()) == 0, i
 
 
 def test_full_size_properties_cfg4():
