@@ -97,15 +97,10 @@ def _build_cuda(force=False, verbose=False):
     target = os.path.join(PKG, "libavirb200.so")
     # (source, object, extra flags); stream_chain.cu holds the kernels of ONE pass of ONE streaming
     # chain and is compiled once per chain id (stream_types.h: StreamChainId 1..6) and pass, in parallel
-    # Chain 5 (the 56-tap cfg5 chain) is left out unless AVIRB200_BUILD_ALL_CHAINS=1: it is not
-    # selected at run time (slower than the tile kernel) and takes ~18 minutes to compile.
-    all_chains = os.environ.get("AVIRB200_BUILD_ALL_CHAINS") == "1"
-    chains = [k for k in range(1, 7) if all_chains or k != 5]
+    chains = list(range(1, 7))
     jobs = [(os.path.join(CSRC, n + ".cu"), os.path.join(PKG, n + ".o"), [])
             for n in ("engine", "lancir")]
-    jobs.append((os.path.join(CSRC, "stream_pass.cu"),
-                 os.path.join(PKG, "stream_pass_all.o" if all_chains else "stream_pass.o"),
-                 ["-DAVS_WITH_DIL56"] if all_chains else []))
+    jobs.append((os.path.join(CSRC, "stream_pass.cu"), os.path.join(PKG, "stream_pass.o"), []))
     jobs += [(os.path.join(CSRC, "stream_chain.cu"), os.path.join(PKG, "stream_chain_%d%s.o" % (k, "hv"[v])),
               ["-DAVS_CHAIN_ID=%d" % k, "-DAVS_CHAIN_PASS=%d" % v]) for k in chains for v in (0, 1)]
     objs = [j[1] for j in jobs]

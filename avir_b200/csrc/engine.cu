@@ -959,8 +959,8 @@ int avirb200_plan_set_option(avirb200_plan* pl, int option, int value) {
     if (pl == nullptr) return fail(AVIRB200_ERR_BAD_ARG, "null argument");
     switch (option) {
     case AVIRB200_OPT_KERNEL_FAMILY: pl->opt_family = (value == 1 || value == 2) ? value : 0; return 0;
-    case AVIRB200_OPT_STREAM_VARIANT_H: pl->opt_var_h = (value >= 0 && value < 3) ? value : -1; return 0;
-    case AVIRB200_OPT_STREAM_VARIANT_V: pl->opt_var_v = (value >= 0 && value < 3) ? value : -1; return 0;
+    case AVIRB200_OPT_STREAM_VARIANT_H: pl->opt_var_h = (value >= 0 && value < 6 && value != 3) ? value : -1; return 0;
+    case AVIRB200_OPT_STREAM_VARIANT_V: pl->opt_var_v = (value >= 0 && value < 6 && value != 3) ? value : -1; return 0;
     case AVIRB200_OPT_HOST_BANDS: pl->opt_host_bands = value >= 1 ? value : -1; return 0;
     case AVIRB200_OPT_OVERLAP_HALO: pl->opt_overlap = (value == 0) ? 0 : 1; return 0;
     case AVIRB200_OPT_ALL_STREAM_CHAINS: {

@@ -233,6 +233,10 @@ inline void fast_prepare_range(const FastPlan& f, int out0, int out1) {
 inline void fast_plan_init(FastPlan& f, const DevAxis& h_host, const DevAxis& v_host,
                            const avirb200_plan_desc& d) {
     if (d.channels != 4) return;
+    {   // the 1 of the packed adds (fast_kernel.cuh: f2add)
+        const float2 one = make_float2(1.0f, 1.0f);
+        if (cudaMemcpyToSymbol(avb_packed_one, &one, sizeof one) != cudaSuccess) { cudaGetLastError(); return; }
+    }
     FastPass* ps[2] = {&f.h, &f.v};
     const DevAxis* hs[2] = {&h_host, &v_host};
     for (int a = 0; a < 2; ++a) {

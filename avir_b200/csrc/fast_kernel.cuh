@@ -133,11 +133,33 @@ AVB_HD Range clampr(Range r, int lo, int hi) {
 
 // ---- small device helpers ------------------------------------------------------------------------
 
+// The two channels a lane owns travel as one packed pair (sm_100a FMUL2 / FFMA2, as in
+// stream_kernel.cuh): the product is mul.rn.f32x2, the sum fma.rn.f32x2(a, 1, b) == round(a + b)
+// with the 1 read from constant memory the HOST fills (fast_plan_init) -- ptxas contracts a
+// packed multiply feeding a packed add (or an fma by a literal 1) into ONE rounding even under
+// -fmad=false; a value it cannot see it cannot fold.  Same bits as separate FMUL / FADD, half the
+// issue slots.
+__constant__ float2 avb_packed_one;
+typedef unsigned long long avb_u64;
+__device__ __forceinline__ avb_u64 f2pk(float2 v) {
+    avb_u64 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(v.x), "f"(v.y));
+    return r;
+}
+__device__ __forceinline__ float2 f2up(avb_u64 v) {
+    float2 r;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+    return r;
+}
 __device__ __forceinline__ float2 f2mul(float t, float2 x) {
-    return make_float2(__fmul_rn(t, x.x), __fmul_rn(t, x.y));
+    avb_u64 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(f2pk(x)), "l"(f2pk(make_float2(t, t))));
+    return f2up(r);
 }
 __device__ __forceinline__ float2 f2add(float2 a, float2 b) {
-    return make_float2(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y));
+    avb_u64 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(f2pk(a)), "l"(f2pk(avb_packed_one)), "l"(f2pk(b)));
+    return f2up(r);
 }
 __device__ __forceinline__ float2 f2hadd8(const float2* v) {
     return f2add(f2add(f2add(v[0], v[4]), f2add(v[1], v[5])),
@@ -403,10 +425,20 @@ __device__ __forceinline__ void sink_store(const FastParams& p, const Sink& k, i
         return;
     }
     if (EPI == 2) {
-        v.x = epilogue_round_c4(p, v.x);
-        v.y = epilogue_round_c4(p, v.y);
         if (!k.gok) return;
         unsigned char* g2 = k.gp + (size_t)(j - k.grow_base) * k.grow;
+        if (p.tr_mul == 1.0f) {
+            // no bit-depth truncation: one float->int conversion per sample, clamp and narrow in
+            // integers (round_out_int, pixel_ops.cuh) -- the values of round, clamp, (Tout) in floats
+            const int pk = (int)p.pk_out;
+            const int a = imin(imax(round_out_int(v.x, p.round_mode), 0), pk);
+            const int b = imin(imax(round_out_int(v.y, p.round_mode), 0), pk);
+            if (p.dst_type == AVIRB200_U8) *reinterpret_cast<unsigned short*>(g2) = (unsigned short)(a | (b << 8));
+            else *reinterpret_cast<unsigned*>(g2) = (unsigned)a | ((unsigned)b << 16);
+            return;
+        }
+        v.x = epilogue_round_c4(p, v.x);
+        v.y = epilogue_round_c4(p, v.y);
         if (p.dst_type == AVIRB200_U8)
             *reinterpret_cast<uchar2*>(g2) = make_uchar2((unsigned char)v.x, (unsigned char)v.y);
         else

@@ -142,7 +142,10 @@ struct ChainC {
     static constexpr int LINE_B = (rsp0 + 1) * PIXB; // row pass: bytes per line of the source ring (one pixel of padding)
     static constexpr int SRC_RING_F2 = (kLines * LINE_B + 15) / 16 * 2;
     static constexpr int STAGE_LINE = MLAST * 2 + 2;
-    static constexpr int MBAR_F2 = MBAR ? NG : 0; // one 8-byte mbarrier per source-ring group
+    // one 8-byte mbarrier per source-ring group; padded so that every warp's block (and with it
+    // its source ring, the destination of the tensor copies) stays 128-byte aligned
+    static constexpr int MBAR_F2 = MBAR ? 16 * ((NG + 15) / 16) : 0;
+    static_assert(!MBAR || ((rsp0 * kPitchL + (rsp1 + rsp2) * kPitchL) % 16 == 0), "ring rows are 256 bytes");
     static constexpr int WARP_F2_H = SRC_RING_F2 + (rsp1 + rsp2) * kPitchL + kLines * STAGE_LINE + MBAR_F2;
     static constexpr int WARP_F2_V = rsp0 * kPitchL + (rsp1 + rsp2) * kPitchL + MBAR_F2;
     // warps per block (one block per SM): 8 (two per scheduler; the register windows leave room
@@ -1221,7 +1224,7 @@ stream_pass_kernel(const __grid_constant__ StreamParams p) {
         for (int i = threadIdx.x; i < 256; i += NW * 32) slut[i] = __ldg(p.srgb_lut + i);
         __syncthreads();
     }
-    extern __shared__ __align__(16) unsigned char stream_smem[];
+    extern __shared__ __align__(128) unsigned char stream_smem[]; // (tensor copies land 128-byte aligned)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float2* sm = reinterpret_cast<float2*>(stream_smem) + (size_t)warp * (IS_V ? C::WARP_F2_V : C::WARP_F2_H);
     stream_warp_main<C, IS_V, EPI>(p, (long long)blockIdx.x * NW + warp, (long long)gridDim.x * NW, lane, sm, slut);
@@ -1241,9 +1244,12 @@ stream_pass_kernel(const __grid_constant__ StreamParams p) {
 #ifndef AVS_RWU_OVERRIDE
 #define AVS_RWU_OVERRIDE 0
 #endif
+// VAR 4 / 5 (tuning experiment, headline chain only): modes 1 / 2 with ONE round per trip of the
+// register-window loop (a third of the code, register moves at the back edge instead).
 template <class S0, class S1, class S2, int REPS_LAST, int LAH, int LAV, int RWU, int VAR, bool IS_V, int SRCT>
-using ChainV = ChainC<S0, S1, S2, REPS_LAST, (IS_V ? LAV : LAH), (VAR == 2 && !IS_V) ? 1 : VAR, IS_V ? AVIRB200_F32 : SRCT,
-                      AVS_RWU_OVERRIDE ? AVS_RWU_OVERRIDE : RWU>;
+using ChainV = ChainC<S0, S1, S2, REPS_LAST, (IS_V ? LAV : LAH),
+                      ((VAR >= 4 ? VAR - 3 : VAR) == 2 && !IS_V) ? 1 : (VAR >= 4 ? VAR - 3 : VAR),
+                      IS_V ? AVIRB200_F32 : SRCT, AVS_RWU_OVERRIDE ? AVS_RWU_OVERRIDE : (VAR >= 4 ? 1 : RWU)>;
 
 // cfg3, float8_dil mirror (k = 2): RESIZE(24 taps, source step 2) -> 8-tap correction FIR
 template <int VAR, bool IS_V, int SRCT = AVIRB200_F32>
@@ -1263,7 +1269,7 @@ using ChainInl3D = ChainV<StepC<K_FIR, AVIRB200_SUM_INL, 15, 2>, StepC<K_RESIZE,
                           StepC<K_FIR, AVIRB200_SUM_INL, 7, 1>, 1, 1, 1, 2, VAR, IS_V, SRCT>;
 // cfg5, float8_dil mirror (k = 4, build mode 1): RESIZE(56 taps, source step 4; 4-output batches) -> FIR(8)
 template <int VAR, bool IS_V, int SRCT = AVIRB200_F32>
-using ChainDil56 = ChainV<StepC<K_RESIZE, AVIRB200_SUM_DIL8, 56, 4, 4>, StepC<K_FIR, AVIRB200_SUM_DIL8, 8, 1>, NoStep,
+using ChainDil56 = ChainV<StepC<K_RESIZE, AVIRB200_SUM_DIL8, 56, 4, 4>, StepC<K_FIR, AVIRB200_SUM_DIL8, 8, 1, 4>, NoStep,
                           1, 1, 1, 2, VAR, IS_V, SRCT>;
 // cfg2 (k = 0.5): FIR(7) -> RESIZE(24) over the virtual 2X line; 32 final outputs per round
 template <int VAR, bool IS_V, int SRCT = AVIRB200_F32>
@@ -1312,6 +1318,18 @@ inline bool stream_dispatch_chain(bool is_v, int variant, int src_type, F&& f) {
     switch (variant) {                                                                    \
         AVS_V(NAME, 0) AVS_V(NAME, 1) AVS_V(NAME, 2) AVS_V3(NAME)                         \
     default: return false;                                                                \
+    }
+    if constexpr (ID == kChainDil24) {
+        // tuning experiment: the register-window modes with one round per loop trip
+        if (variant == 4 && src_type == AVIRB200_F32) {
+            if (is_v) f(ChainTag<ChainDil24<4, true> >(), PassTag<true>());
+            else f(ChainTag<ChainDil24<4, false> >(), PassTag<false>());
+            return true;
+        }
+        if (variant == 5 && src_type == AVIRB200_F32 && is_v) {
+            f(ChainTag<ChainDil24<5, true> >(), PassTag<true>());
+            return true;
+        }
     }
     if (variant < 0 || variant >= kStreamVariants) return false;
     if constexpr (ID == kChainDil24) { AVS_VARIANTS(ChainDil24) }

@@ -7,7 +7,8 @@ namespace avs {
 int stream_launch(int chain, bool is_v, int epi, int variant, const StreamParams& p, int sm_count, void* stream) {
     // scheduling variant (a per-plan option, AVIRB200_OPT_STREAM_VARIANT_H / _V); every variant
     // computes the same bits (variant 3, all rounds on the checked path, is host-emulation only)
-    const int var = (variant >= 0 && variant < 3) ? variant : (is_v ? kStreamDefaultVariantV : kStreamDefaultVariantH);
+    const int var = ((variant >= 0 && variant < 3) || ((variant == 4 || variant == 5) && chain == kChainDil24))
+                        ? variant : (is_v ? kStreamDefaultVariantV : kStreamDefaultVariantH);
 #define AVS_ROUTE(ID)                                                                              \
     case ID:                                                                                       \
         return is_v ? stream_launch_chain<ID, true>(var, epi, p, sm_count, stream)                 \
@@ -17,13 +18,7 @@ int stream_launch(int chain, bool is_v, int epi, int variant, const StreamParams
         AVS_ROUTE(kChainInl24)
         AVS_ROUTE(kChainInl3)
         AVS_ROUTE(kChainInl3D)
-#ifdef AVS_WITH_DIL56
-        // Not in the default build: the chain loses to the tile kernel on B200 (stream_types.h) and
-        // its kernels take long to compile; AVIRB200_BUILD_ALL_CHAINS=1 python avir_b200/build.py
-        // builds them (then selectable with AVIRB200_OPT_ALL_STREAM_CHAINS).  Without them the engine
-        // falls back to the tile kernel (return -2 = no such instantiation).
         AVS_ROUTE(kChainDil56)
-#endif
         AVS_ROUTE(kChainUp2)
     default: return -2;
     }
