@@ -11,7 +11,11 @@
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 
+#include <atomic>
 #include <charconv>
+#include <condition_variable>
+#include <functional>
+#include <thread>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -118,7 +122,7 @@ struct avirb200_plan {
     cudaStream_t stream = nullptr;
     // pipelined resize_host: copy-in / copy-out streams and per-band events
     cudaStream_t stream_in = nullptr, stream_out = nullptr;
-    std::vector<cudaEvent_t> ev_in, ev_out;
+    std::vector<cudaEvent_t> ev_in, ev_out, ev_d2h, ev_slot; // (+ staged copies of pageable buffers)
     mutable int last_launches = 0;
     // options (avirb200_plan_set_option)
     // 1..3-channel images on the 4-channel kernels (streaming / tile): the source is widened to
@@ -791,11 +795,90 @@ struct Staging {
     std::mutex mx; // held for the whole host call: host calls on one device run one at a time
     void *d_src = nullptr, *d_dst = nullptr, *d_ws = nullptr;
     size_t src_b = 0, dst_b = 0, ws_b = 0;
+    // page-locked bounce buffers for callers' pageable (malloc) images: a ring of source bands
+    // and the whole destination
+    char *h_in = nullptr, *h_out = nullptr;
+    size_t h_in_b = 0, h_out_b = 0;
 };
+
+// A few host threads that move image rows between the caller's pageable memory and the
+// page-locked bounce buffers (one thread's memcpy is slower than PCIe).
+class CopyPool {
+public:
+    static CopyPool& get() {
+        static CopyPool p;
+        return p;
+    }
+    // rows of `row_bytes` from src (pitch sp) to dst (pitch dp), split over the workers and the caller
+    void copy2d(char* dst, size_t dp, const char* src, size_t sp, size_t row_bytes, int rows) {
+        if (rows <= 0) return;
+        const int parts = (int)std::min<size_t>(nthreads_ + 1, std::max<size_t>(1, (size_t)rows * row_bytes >> 20));
+        if (parts <= 1) { rows_copy(dst, dp, src, sp, row_bytes, 0, rows); return; }
+        std::atomic<int> left(parts - 1);
+        std::mutex dm;
+        std::condition_variable dcv;
+        for (int i = 1; i < parts; ++i) {
+            const int a = (int)((long long)rows * i / parts), b = (int)((long long)rows * (i + 1) / parts);
+            submit([=, &left, &dm, &dcv] {
+                rows_copy(dst, dp, src, sp, row_bytes, a, b);
+                if (left.fetch_sub(1) == 1) { std::lock_guard<std::mutex> g(dm); dcv.notify_one(); }
+            });
+        }
+        rows_copy(dst, dp, src, sp, row_bytes, 0, (int)((long long)rows / parts));
+        std::unique_lock<std::mutex> g(dm);
+        dcv.wait(g, [&] { return left.load() == 0; });
+    }
+
+private:
+    CopyPool() {
+        unsigned hw = std::thread::hardware_concurrency();
+        nthreads_ = hw >= 32 ? 7 : (hw >= 8 ? 3 : 1);
+        for (size_t i = 0; i < nthreads_; ++i) std::thread([this] { run(); }).detach();
+    }
+    static void rows_copy(char* dst, size_t dp, const char* src, size_t sp, size_t row_bytes, int a, int b) {
+        if (dp == row_bytes && sp == row_bytes) { std::memcpy(dst + (size_t)a * dp, src + (size_t)a * sp, (size_t)(b - a) * row_bytes); return; }
+        for (int y = a; y < b; ++y) std::memcpy(dst + (size_t)y * dp, src + (size_t)y * sp, row_bytes);
+    }
+    void submit(std::function<void()> f) {
+        { std::lock_guard<std::mutex> g(m_); q_.push_back(std::move(f)); }
+        cv_.notify_one();
+    }
+    void run() {
+        for (;;) {
+            std::function<void()> f;
+            {
+                std::unique_lock<std::mutex> g(m_);
+                cv_.wait(g, [&] { return !q_.empty(); });
+                f = std::move(q_.front());
+                q_.erase(q_.begin());
+            }
+            f();
+        }
+    }
+    size_t nthreads_ = 1;
+    std::mutex m_;
+    std::condition_variable cv_;
+    std::vector<std::function<void()> > q_;
+};
+
+bool is_pageable(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return true; }
+    return a.type == cudaMemoryTypeUnregistered;
+}
+int grow_host(char** p, size_t* have, size_t need) {
+    if (*have >= need) return 0;
+    if (*p) cudaFreeHost(*p);
+    *p = nullptr; *have = 0;
+    CUDA_TRY(cudaHostAlloc(reinterpret_cast<void**>(p), need, cudaHostAllocDefault));
+    *have = need;
+    return 0;
+}
 Staging& staging_of(int device) {
     static Staging pool[64];
     return pool[(unsigned)device & 63u];
 }
+int grow(void** p, size_t* have, size_t need);
 int grow(void** p, size_t* have, size_t need) {
     if (*have >= need) return 0;
     cudaFree(*p);
@@ -971,8 +1054,8 @@ int avirb200_plan_set_option(avirb200_plan* pl, int option, int value) {
             const avirb200_plan_desc& d = pl->desc;
             const int ch = pl->pad4 ? 4 : d.channels;
             if (avs::stream_row_source_ok(d))
-                avs::stream_plan_axis(pl->h.desc, d.sum_mode, ch, pl->stream_h, on != 0);
-            avs::stream_plan_axis(pl->v.desc, d.sum_mode, ch, pl->stream_v, on != 0);
+                avs::stream_plan_axis(pl->h.desc, d.sum_mode, ch, pl->stream_h, on != 0, false);
+            avs::stream_plan_axis(pl->v.desc, d.sum_mode, ch, pl->stream_v, on != 0, true);
         }
         return 0;
     }
@@ -1100,8 +1183,8 @@ int avirb200_plan_create(const avirb200_plan_desc* desc, avirb200_plan** out) {
         sd.prefix_dc = pl->v.pdc[i].data(); sd.suffix_dc = pl->v.sdc[i].data();
     }
     if (avs::stream_row_source_ok(pl->desc))
-        avs::stream_plan_axis(pl->h.desc, desc->sum_mode, d4.channels, pl->stream_h, false);
-    avs::stream_plan_axis(pl->v.desc, desc->sum_mode, d4.channels, pl->stream_v, false);
+        avs::stream_plan_axis(pl->h.desc, desc->sum_mode, d4.channels, pl->stream_h, false, false);
+    avs::stream_plan_axis(pl->v.desc, desc->sum_mode, d4.channels, pl->stream_v, false, true);
     if (try4) {
         const bool h4 = pl->stream_h.chain != 0 || pl->fast.h_ok, v4 = pl->stream_v.chain != 0 || pl->fast.v_ok;
         if (h4 && v4) {
@@ -1134,6 +1217,8 @@ void avirb200_plan_destroy(avirb200_plan* pl) {
     if (pl->stream_out) cudaStreamDestroy(pl->stream_out);
     for (cudaEvent_t e : pl->ev_in) cudaEventDestroy(e);
     for (cudaEvent_t e : pl->ev_out) cudaEventDestroy(e);
+    for (cudaEvent_t e : pl->ev_d2h) cudaEventDestroy(e);
+    for (cudaEvent_t e : pl->ev_slot) cudaEventDestroy(e);
     delete pl;
 }
 
@@ -1338,9 +1423,59 @@ int avirb200_resize_host(avirb200_plan* pl, const void* h_src, size_t src_pitch,
         char* dst4 = src4 + pad4_src_bytes(pl, d.src_h);
         const size_t src4_row = (size_t)d.src_w * 4 * in_el, dst4_row = (size_t)d.dst_w * 4 * out_el;
         int launches = 0;
-        // (copies are issued band by band BETWEEN the kernel launches: with pageable host memory a
-        // copy call returns only when its data has moved, and the GPU should be busy meanwhile)
+        // Pageable (malloc) caller buffers: a copy call straight from / to them returns only when
+        // its data has moved (the driver bounces it through its own staging, one thread), which
+        // serialises the pipeline.  Such buffers go through the library's page-locked bounce
+        // buffers instead, filled / drained by a few host threads: source bands through a ring
+        // (a slot is reused once its host->device copy has finished), the destination through a
+        // whole-image buffer drained band by band by a helper thread.
+        constexpr int kInSlots = 3;
+        const bool stage_in = is_pageable(h_src), stage_out = is_pageable(h_dst);
+        Staging& sg = staging_of(pl->device);
+        size_t slot_bytes = 0;
+        for (int b = 0; b < nb; ++b) slot_bytes = std::max(slot_bytes, align_up((size_t)si[b].src_rows * in_row, 4096));
+        if (stage_in) { const int r0 = grow_host(&sg.h_in, &sg.h_in_b, slot_bytes * kInSlots); if (r0 != 0) return r0; }
+        if (stage_out) { const int r0 = grow_host(&sg.h_out, &sg.h_out_b, out_bytes); if (r0 != 0) return r0; }
+        while ((int)pl->ev_slot.size() < kInSlots || (int)pl->ev_d2h.size() < nb) {
+            cudaEvent_t e0;
+            CUDA_TRY(cudaEventCreateWithFlags(&e0, cudaEventDisableTiming));
+            if ((int)pl->ev_slot.size() < kInSlots) pl->ev_slot.push_back(e0); else pl->ev_d2h.push_back(e0);
+        }
+        // drains destination bands from the bounce buffer into the caller's memory as their copies land
+        std::atomic<int> d2h_issued(0), drain_stop(0);
+        struct Joiner {
+            std::thread t; std::atomic<int>* stop;
+            ~Joiner() { if (t.joinable()) { stop->store(1); t.join(); } }
+        } drainer{std::thread(), &drain_stop};
+        if (stage_out) {
+            const int dev = pl->device;
+            drainer.t = std::thread([&, dev] {
+                cudaSetDevice(dev);
+                for (int b = 0; b < nb; ++b) {
+                    while (d2h_issued.load() <= b) {
+                        if (drain_stop.load()) return;
+                        std::this_thread::yield();
+                    }
+                    if (cudaEventSynchronize(pl->ev_d2h[b]) != cudaSuccess) return;
+                    CopyPool::get().copy2d(static_cast<char*>(h_dst) + (size_t)si[b].dst_row0 * dst_pitch * out_el,
+                                           dst_pitch * out_el, sg.h_out + (size_t)si[b].dst_row0 * out_row, out_row,
+                                           out_row, si[b].dst_rows);
+                }
+            });
+        }
         auto copy_in = [&](int b) -> int {
+            if (stage_in) {
+                const int slot = b % kInSlots;
+                if (b >= kInSlots) CUDA_TRY(cudaEventSynchronize(pl->ev_slot[slot])); // its previous copy has left the slot
+                char* hs = sg.h_in + (size_t)slot * slot_bytes;
+                CopyPool::get().copy2d(hs, in_row, static_cast<const char*>(h_src) + (size_t)si[b].src_row0 * src_pitch * in_el,
+                                       src_pitch * in_el, in_row, si[b].src_rows);
+                CUDA_TRY(cudaMemcpyAsync(static_cast<char*>(pl->d_src) + (size_t)si[b].src_row0 * in_row, hs,
+                                         (size_t)si[b].src_rows * in_row, cudaMemcpyHostToDevice, pl->stream_in));
+                CUDA_TRY(cudaEventRecord(pl->ev_slot[slot], pl->stream_in));
+                CUDA_TRY(cudaEventRecord(pl->ev_in[b], pl->stream_in));
+                return 0;
+            }
             CUDA_TRY(cudaMemcpy2DAsync(static_cast<char*>(pl->d_src) + (size_t)si[b].src_row0 * in_row, in_row,
                                        static_cast<const char*>(h_src) + (size_t)si[b].src_row0 * src_pitch * in_el,
                                        src_pitch * in_el, in_row, si[b].src_rows, cudaMemcpyHostToDevice,
@@ -1357,6 +1492,13 @@ int avirb200_resize_host(avirb200_plan* pl, const void* h_src, size_t src_pitch,
             if (r != 0) return r;
             CUDA_TRY(cudaEventRecord(pl->ev_out[b], pl->stream));
             CUDA_TRY(cudaStreamWaitEvent(pl->stream_out, pl->ev_out[b], 0));
+            if (stage_out) {
+                CUDA_TRY(cudaMemcpyAsync(sg.h_out + (size_t)si[b].dst_row0 * out_row, dd, (size_t)si[b].dst_rows * out_row,
+                                         cudaMemcpyDeviceToHost, pl->stream_out));
+                CUDA_TRY(cudaEventRecord(pl->ev_d2h[b], pl->stream_out));
+                d2h_issued.store(b + 1);
+                return 0;
+            }
             CUDA_TRY(cudaMemcpy2DAsync(static_cast<char*>(h_dst) + (size_t)si[b].dst_row0 * dst_pitch * out_el,
                                        dst_pitch * out_el, dd, out_row, out_row, si[b].dst_rows,
                                        cudaMemcpyDeviceToHost, pl->stream_out));
@@ -1376,6 +1518,7 @@ int avirb200_resize_host(avirb200_plan* pl, const void* h_src, size_t src_pitch,
         pl->last_launches = launches;
         CUDA_TRY(cudaStreamSynchronize(pl->stream_out));
         CUDA_TRY(cudaStreamSynchronize(pl->stream));
+        if (drainer.t.joinable()) drainer.t.join(); // the last bands reach the caller's memory
         return 0;
     }
     CUDA_TRY(cudaMemcpy2DAsync(pl->d_src, in_row, h_src, src_pitch * in_el, in_row,

@@ -162,16 +162,15 @@ inline bool stream_match_step(const avirb200_step_desc& d, const StepSpec& sp, S
 // Decides whether the axis runs on the streaming kernel; on success `out` holds everything
 // the kernel parameters need.
 inline bool stream_plan_axis(const avirb200_axis_desc& ad, int sum_mode, int channels, StreamAxisPlan& out,
-                             bool allow_deselected = false) {
+                             bool allow_deselected = false, bool is_v = false) {
     out.chain = kChainNone;
     if (channels != 4) return false;
-    // allow_deselected: two chains are instantiated and checked (emulation; on the GPU with
-    // AVIRB200_STREAM_ALL=1) but not selected by default, because the tile kernel measured
-    // faster on B200: the upsizing chain (cfg2's column pass 0.40 vs 0.17 ms,
-    // profiles/r01_variant_sweeps_packed.jsonl) and the 56-tap chain (cfg5: row pass 0.92 vs
-    // 0.73 ms, column pass 0.28 vs 0.20 ms, profiles/r01_pass_times.jsonl).
+    // allow_deselected (AVIRB200_OPT_ALL_STREAM_CHAINS): the upsizing chain is instantiated and
+    // checked for both passes but its COLUMN pass is not selected by default -- the tile kernel's
+    // blocked skip-odd resize measured faster on B200 (cfg2: 0.106 vs 0.227 ms; the row pass is the
+    // other way round, 0.044 vs 0.057 ms; profiles/r02a_sweep.jsonl).
     for (int id = 1; id < kChainCount; ++id) {
-        if ((id == kChainUp2 || id == kChainDil56) && !allow_deselected) continue;
+        if (id == kChainUp2 && is_v && !allow_deselected) continue;
         int ns = 0;
         const StepSpec* spec = chain_spec(id, &ns);
         if (ns != ad.nsteps) continue;

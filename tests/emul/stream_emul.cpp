@@ -124,9 +124,9 @@ int stream_emul_variants(void) { return kStreamVariants; }
 // out[3] = column-pass epilogue code.  all_chains: as with AVIRB200_STREAM_ALL=1.
 void stream_emul_selection(const avirb200_plan_desc* d, int all_chains, int* out) {
     StreamAxisPlan h, v;
-    out[0] = (stream_row_source_ok(*d) && stream_plan_axis(d->h, d->sum_mode, d->channels, h, all_chains != 0))
+    out[0] = (stream_row_source_ok(*d) && stream_plan_axis(d->h, d->sum_mode, d->channels, h, all_chains != 0, false))
                  ? h.chain : 0;
-    out[1] = stream_plan_axis(d->v, d->sum_mode, d->channels, v, all_chains != 0) ? v.chain : 0;
+    out[1] = stream_plan_axis(d->v, d->sum_mode, d->channels, v, all_chains != 0, true) ? v.chain : 0;
     out[2] = stream_row_source_code(*d);
     out[3] = stream_epilogue_code(*d);
 }

@@ -138,11 +138,11 @@ def test_chain_selection_of_the_baseline_configs(emul):
     U8, U16, F32, SRGB = 0, 1, 2, 4
     table = [
         # case (full BASELINE sizes; planning only)                                 default      all chains   src   epi
-        ((1, 1920, 1080, 3840, 2160, 4, u8, u8, 8, {}),                             (0, 0),      (UP2, UP2),   U8,   2),   # cfg2
+        ((1, 1920, 1080, 3840, 2160, 4, u8, u8, 8, {}),                             (UP2, 0),    (UP2, UP2),   U8,   2),   # cfg2: streaming row pass, tile column pass
         ((2, 7680, 4320, 3840, 2160, 4, f32, f32, 16, {}),                          (DIL24,) * 2, (DIL24,) * 2, F32, 1),   # cfg3
         ((1, 7680, 4320, 3840, 2160, 4, f32, f32, 16, {}),                          (INL3,) * 2, (INL3,) * 2,  F32,  1),
         ((1, 16384, 16384, 4096, 4096, 4, u16, u16, 16, {}),                        (INL3D,) * 2, (INL3D,) * 2, U16, 2),   # cfg4
-        ((2, 7680, 4320, 1920, 1080, 4, u8, u8, 8, {"gamma": True, "alpha": 3}),    (0, 0),      (DIL56,) * 2, SRGB, 0),   # cfg5
+        ((2, 7680, 4320, 1920, 1080, 4, u8, u8, 8, {"gamma": True, "alpha": 3}),    (DIL56,) * 2, (DIL56,) * 2, SRGB, 0),   # cfg5
         ((1, 7680, 4320, 3840, 2160, 4, u8, u8, 8, {}),                             (INL24,) * 2, (INL24,) * 2, U8,  2),
         ((2, 7680, 4320, 3840, 2160, 4, f32, u16, 16, {"gamma": True}),             (0, DIL24),  (0, DIL24),   SRGB, 0),   # float + gamma source: tile row pass
         ((1, 1500, 1000, 1111, 741, 4, u8, u8, 8, {}),                              (0, 0),      (0, 0),       U8,   2),   # irregular ratio
