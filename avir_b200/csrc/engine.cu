@@ -814,19 +814,26 @@ public:
         if (rows <= 0) return;
         const int parts = (int)std::min<size_t>(nthreads_ + 1, std::max<size_t>(1, (size_t)rows * row_bytes >> 20));
         if (parts <= 1) { rows_copy(dst, dp, src, sp, row_bytes, 0, rows); return; }
-        std::atomic<int> left(parts - 1);
-        std::mutex dm;
-        std::condition_variable dcv;
+        // (completion state outlives this call: a worker may still be leaving its critical section
+        // when the caller has already seen the count reach zero)
+        struct Done {
+            std::mutex m;
+            std::condition_variable cv;
+            int left;
+        };
+        std::shared_ptr<Done> done(new Done());
+        done->left = parts - 1;
         for (int i = 1; i < parts; ++i) {
             const int a = (int)((long long)rows * i / parts), b = (int)((long long)rows * (i + 1) / parts);
-            submit([=, &left, &dm, &dcv] {
+            submit([=] {
                 rows_copy(dst, dp, src, sp, row_bytes, a, b);
-                if (left.fetch_sub(1) == 1) { std::lock_guard<std::mutex> g(dm); dcv.notify_one(); }
+                std::lock_guard<std::mutex> g(done->m);
+                if (--done->left == 0) done->cv.notify_one();
             });
         }
         rows_copy(dst, dp, src, sp, row_bytes, 0, (int)((long long)rows / parts));
-        std::unique_lock<std::mutex> g(dm);
-        dcv.wait(g, [&] { return left.load() == 0; });
+        std::unique_lock<std::mutex> g(done->m);
+        done->cv.wait(g, [&] { return done->left == 0; });
     }
 
 private:
@@ -1042,8 +1049,8 @@ int avirb200_plan_set_option(avirb200_plan* pl, int option, int value) {
     if (pl == nullptr) return fail(AVIRB200_ERR_BAD_ARG, "null argument");
     switch (option) {
     case AVIRB200_OPT_KERNEL_FAMILY: pl->opt_family = (value == 1 || value == 2) ? value : 0; return 0;
-    case AVIRB200_OPT_STREAM_VARIANT_H: pl->opt_var_h = (value >= 0 && value < 6 && value != 3) ? value : -1; return 0;
-    case AVIRB200_OPT_STREAM_VARIANT_V: pl->opt_var_v = (value >= 0 && value < 6 && value != 3) ? value : -1; return 0;
+    case AVIRB200_OPT_STREAM_VARIANT_H: pl->opt_var_h = (value >= 0 && value < 3) ? value : -1; return 0;
+    case AVIRB200_OPT_STREAM_VARIANT_V: pl->opt_var_v = (value >= 0 && value < 3) ? value : -1; return 0;
     case AVIRB200_OPT_HOST_BANDS: pl->opt_host_bands = value >= 1 ? value : -1; return 0;
     case AVIRB200_OPT_OVERLAP_HALO: pl->opt_overlap = (value == 0) ? 0 : 1; return 0;
     case AVIRB200_OPT_ALL_STREAM_CHAINS: {

@@ -330,7 +330,7 @@ inline int fast_launch(const FastParams& p, size_t smem, int sum_mode, cudaStrea
     }
     bool launched = false;
     const bool plain_f32 = (p.dst_type == AVIRB200_F32 && !p.gamma_out);
-    const bool int_plain = (p.dst_type != AVIRB200_F32 && !p.gamma_out); // integer destination, no output gamma
+    const bool int_plain = (p.dst_type != AVIRB200_F32 && !p.gamma_out && p.tr_mul == 1.0f); // integer destination, no output gamma, no truncation
     AVB_TRY(AVIRB200_SUM_DIL8, 2, kVarResizeDil24D2, kVarFirDil8R1, -1, 0)        // cfg3 (float8_dil)
     AVB_TRY(AVIRB200_SUM_DIL8, 2, kVarResizeDil56D4, kVarFirDil8R1, -1, -1)       // cfg5
     AVB_TRY(AVIRB200_SUM_INL, 3, kVarFirInl7R1, kVarResizeInl18D2, kVarFirInl7R1, 1)   // cfg3 (float4)

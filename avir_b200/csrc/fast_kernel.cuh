@@ -427,22 +427,14 @@ __device__ __forceinline__ void sink_store(const FastParams& p, const Sink& k, i
     if (EPI == 2) {
         if (!k.gok) return;
         unsigned char* g2 = k.gp + (size_t)(j - k.grow_base) * k.grow;
-        if (p.tr_mul == 1.0f) {
-            // no bit-depth truncation: one float->int conversion per sample, clamp and narrow in
-            // integers (round_out_int, pixel_ops.cuh) -- the values of round, clamp, (Tout) in floats
-            const int pk = (int)p.pk_out;
-            const int a = imin(imax(round_out_int(v.x, p.round_mode), 0), pk);
-            const int b = imin(imax(round_out_int(v.y, p.round_mode), 0), pk);
-            if (p.dst_type == AVIRB200_U8) *reinterpret_cast<unsigned short*>(g2) = (unsigned short)(a | (b << 8));
-            else *reinterpret_cast<unsigned*>(g2) = (unsigned)a | ((unsigned)b << 16);
-            return;
-        }
-        v.x = epilogue_round_c4(p, v.x);
-        v.y = epilogue_round_c4(p, v.y);
-        if (p.dst_type == AVIRB200_U8)
-            *reinterpret_cast<uchar2*>(g2) = make_uchar2((unsigned char)v.x, (unsigned char)v.y);
-        else
-            *reinterpret_cast<ushort2*>(g2) = make_ushort2((unsigned short)v.x, (unsigned short)v.y);
+        // (no bit-depth truncation, fast_launch(): one rounding conversion per sample, clamp and
+        // narrow in integers, selects and predicated stores instead of branches)
+        const int pk = (int)p.pk_out;
+        const int a = imin(imax(round_out_int(v.x, p.round_mode), 0), pk);
+        const int b = imin(imax(round_out_int(v.y, p.round_mode), 0), pk);
+        const bool narrow = (p.dst_type == AVIRB200_U8);
+        if (narrow) *reinterpret_cast<unsigned short*>(g2) = (unsigned short)(a | (b << 8));
+        if (!narrow) *reinterpret_cast<unsigned*>(g2) = (unsigned)a | ((unsigned)b << 16);
         return;
     }
     v.x = epilogue_value_c4(p, v.x, c0);

@@ -183,7 +183,9 @@ AVS_FN float2 f2up(avs_u64 v) {
 }
 AVS_FN float2 f2mul(const StreamTap& t, float2 x) {
     avs_u64 r;
-    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(f2pk(x)), "l"(f2pk(make_float2(t.lo, t.hi))));
+    // (both halves from ONE register: ptxas emits the scalar-broadcast operand form, FMUL2 R, R, UR.F32,
+    // one uniform register per tap instead of a pair)
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(f2pk(x)), "l"(f2pk(make_float2(t.lo, t.lo))));
     return f2up(r);
 }
 AVS_FN float2 f2add(float2 a, float2 b, const StreamTap& one) {
@@ -459,7 +461,8 @@ AVS_FN void loader_init(const StreamParams& p, WarpRun<C, IS_V>& w) {
 }
 
 // Issues source group g (must be called for g = 0, 1, 2, ... in order: the pointers advance).
-// STEADY: the caller guarantees issue && every sweep interior (no branches around the copies).
+// STEADY: the caller guarantees that every sweep is interior (no clamping); `issue` is then a
+// uniform predicate of the copies (false in the last rounds of a run, whose groups lie behind it).
 template <class C, bool IS_V, bool STEADY>
 AVS_FN void load_group(const StreamParams& p, WarpRun<C, IS_V>& w, int g, int gslot, bool issue) {
     constexpr int PITCH_B = RingOf<C, IS_V, 0>::PITCH_B;
@@ -472,7 +475,6 @@ AVS_FN void load_group(const StreamParams& p, WarpRun<C, IS_V>& w, int g, int gs
         const int pos0 = w.o0 + g * C::SRC_N + q * 16; // first source position of the sweep
         unsigned char* ring = reinterpret_cast<unsigned char*>(w.ring0) + (size_t)(gslot + q * 16) * PITCH_B;
         const bool interior = STEADY || ((pos0 >= 0) && (pos0 + 16 <= p.src_len));
-        if (STEADY) issue = true;
         if (IS_V) {
             // a position is an intermediate row; the warp's 16 pixel columns are 256 contiguous bytes
             const int piece = lane & 15, rsub = lane >> 4;
@@ -481,7 +483,7 @@ AVS_FN void load_group(const StreamParams& p, WarpRun<C, IS_V>& w, int g, int gs
 #pragma unroll
                 for (int k = 0; k < 8; ++k) w.gp[k] += 16 * rowb;
             }
-            if (!C::MBAR && (STEADY || (issue && interior))) {
+            if (!C::MBAR && issue && interior) {
 #pragma unroll
                 for (int k = 0; k < 8; ++k) cp_async16(d + 2 * k * PITCH_B, w.gp[k]);
             } else if (issue) {
@@ -500,7 +502,7 @@ AVS_FN void load_group(const StreamParams& p, WarpRun<C, IS_V>& w, int g, int gs
 #pragma unroll
                 for (int k = 0; k < 8; ++k) w.gp[k] += 16 * PIXB;
             }
-            if (!C::MBAR && (STEADY || (issue && interior))) {
+            if (!C::MBAR && issue && interior) {
 #pragma unroll
                 for (int k = 0; k < 8; ++k) cp_async_px<PIXB>(d + 2 * k * C::LINE_B, w.gp[k]);
             } else if (issue) {
@@ -545,23 +547,17 @@ AVS_FN void store_v(const StreamParams& p, unsigned char* g, float2 v, int c0) {
         *reinterpret_cast<float2*>(g) = v;
         return;
     }
-    if (EPI == 2) { // integer destination, no output gamma (no double-precision code in the kernel)
-        if (p.tr_mul == 1.0f) {
-            // no bit-depth truncation (the common case): one float->int conversion per sample,
-            // clamp and narrow in integers -- same values as round, clamp, (Tout) in floats
-            const int pk = (int)p.pk_out;
-            const int a = imin_(imax_(round_out_int(v.x, p.round_mode), 0), pk);
-            const int b = imin_(imax_(round_out_int(v.y, p.round_mode), 0), pk);
-            if (p.dst_type == AVIRB200_U8) *reinterpret_cast<unsigned short*>(g) = (unsigned short)(a | (b << 8));
-            else *reinterpret_cast<unsigned*>(g) = (unsigned)a | ((unsigned)b << 16);
-            return;
-        }
-        v.x = epilogue_round(p, v.x);
-        v.y = epilogue_round(p, v.y);
-        if (p.dst_type == AVIRB200_U8)
-            *reinterpret_cast<uchar2*>(g) = make_uchar2((unsigned char)v.x, (unsigned char)v.y);
-        else
-            *reinterpret_cast<ushort2*>(g) = make_ushort2((unsigned short)v.x, (unsigned short)v.y);
+    if (EPI == 2) {
+        // integer destination, no output gamma, no bit-depth truncation (stream_epilogue_code()):
+        // one rounding conversion per sample, clamp and narrow in integers -- the values of round,
+        // clamp, (Tout) in floats -- and no branch: rounding flavour and element size are selects
+        // and predicated stores (branches at every store site cost this pass 40 %, profiles/r02a_u8k_ncu_summary.txt)
+        const int pk = (int)p.pk_out;
+        const int a = imin_(imax_(round_out_int(v.x, p.round_mode), 0), pk);
+        const int b = imin_(imax_(round_out_int(v.y, p.round_mode), 0), pk);
+        const bool narrow = (p.dst_type == AVIRB200_U8);
+        if (narrow) *reinterpret_cast<unsigned short*>(g) = (unsigned short)(a | (b << 8));
+        if (!narrow) *reinterpret_cast<unsigned*>(g) = (unsigned)a | ((unsigned)b << 16);
         return;
     }
     v.x = epilogue_value(p, v.x, c0);
@@ -1005,7 +1001,7 @@ AVS_FN void regwin_round(const StreamParams& p, WarpRun<C, IS_V>& w, RegWin<C>& 
 // gslot / gi: ring slot (positions / group index) the loader fills next; wi: group index the
 // next round waits for (C::MBAR).
 template <class C, bool IS_V, int EPI>
-AVS_FN void run_regwin(const StreamParams& p, WarpRun<C, IS_V>& w, int r, int n, int& gslot, int& gi, int& wi) {
+AVS_FN void run_regwin(const StreamParams& p, WarpRun<C, IS_V>& w, int r, int n, int groups, int& gslot, int& gi, int& wi) {
     using G = RegWinGeom<C>;
     constexpr int PRO = C::H + C::LOOKAHEAD;
     RegWin<C> R;
@@ -1027,12 +1023,13 @@ AVS_FN void run_regwin(const StreamParams& p, WarpRun<C, IS_V>& w, int r, int n,
             }
             AVS_SYNCWARP(); // all lanes' copies have landed; the previous round is done with its slots
             if constexpr (!IS_V) sink_h_readback<C, C::MLAST>(w);
+            const bool issue = (r + PRO < groups); // (the last rounds of a run issue nothing)
             if constexpr (C::MBAR) {
-                bulk_group<C, IS_V>(p, w, grow, gslot, w.mbar0 + gi * 8);
+                if (issue) bulk_group<C, IS_V>(p, w, grow, gslot, w.mbar0 + gi * 8);
                 grow += C::SRC_N;
                 gi = (gi + 1 == C::NG) ? 0 : gi + 1;
             } else {
-                load_group<C, IS_V, true>(p, w, r + PRO, gslot, true);
+                load_group<C, IS_V, true>(p, w, r + PRO, gslot, issue);
                 cp_async_commit();
             }
             gslot = (gslot + C::SRC_N == C::rsp0) ? 0 : gslot + C::SRC_N;
@@ -1103,8 +1100,12 @@ AVS_FN void run_warp(const StreamParams& p, WarpRun<C, IS_V>& w, int strip, int 
     steady_bounds<C, IS_V, 0, S0>(p, w, C::delay0, C::reps0, slo, shi);
     steady_bounds<C, IS_V, 1, S1>(p, w, C::delay1, C::reps1, slo, shi);
     if constexpr (C::NS == 3) steady_bounds<C, IS_V, 2, S2>(p, w, C::delay2, C::reps2, slo, shi);
+    // the group a steady round issues (r + PRO) is interior -- or lies behind the run (not issued)
     slo = imax_(slo, cdiv_(-w.o0, C::SRC_N) - PRO);
-    shi = imin_(shi, imin_(fdiv_(p.src_len - w.o0, C::SRC_N) - 1, groups - 1) - PRO);
+    {
+        const int g_int_hi = fdiv_(p.src_len - w.o0, C::SRC_N) - 1; // last group without clamping
+        if (groups - 1 > g_int_hi) shi = imin_(shi, g_int_hi - PRO);
+    }
 
 #define AVS_ROUND(STEADY)                                                                             \
     {                                                                                                 \
@@ -1112,7 +1113,7 @@ AVS_FN void run_warp(const StreamParams& p, WarpRun<C, IS_V>& w, int strip, int 
         else cp_async_wait<C::LOOKAHEAD - 1>(); /* groups <= r + H have landed (this lane's copies) */ \
         AVS_SYNCWARP();                    /* ... all lanes'; round r-1 is done with its slots */     \
         if constexpr (STEADY) {                                                                       \
-            load_group<C, IS_V, true>(p, w, r + PRO, gslot, true);                                    \
+            load_group<C, IS_V, true>(p, w, r + PRO, gslot, r + PRO < groups);                        \
             cp_async_commit();                                                                        \
             gslot = (gslot + C::SRC_N == C::rsp0) ? 0 : gslot + C::SRC_N;                             \
         } else {                                                                                      \
@@ -1135,7 +1136,7 @@ AVS_FN void run_warp(const StreamParams& p, WarpRun<C, IS_V>& w, int strip, int 
             // trip of the unrolled loop) takes the checked path
             const int n = (shi - r + 1) / C::RW_UNROLL * C::RW_UNROLL;
             if (r == slo && n > 0) {
-                run_regwin<C, IS_V, EPI>(p, w, r, n, gslot, gi, wi);
+                run_regwin<C, IS_V, EPI>(p, w, r, n, groups, gslot, gi, wi);
                 r += n;
                 continue;
             }
@@ -1238,39 +1239,38 @@ stream_pass_kernel(const __grid_constant__ StreamParams p) {
 
 // Source look-ahead in rounds (LAH row pass, LAV column pass) is what shared memory affords at
 // 8 warps per SM: the row pass carries the staging rows, three-step chains a second
-// intermediate ring.  RWU: rounds per trip of the register-window loop (the source window of a
+// intermediate ring.  RWU: rounds per trip of the register-window loop.  The source window of a
 // chain closes on itself -- no register moves at the loop's back edge -- after WR0 / SRC_N rounds,
-// rounded up; more rounds per trip cost instruction-cache reach).  VAR = ChainC MODE.
+// rounded up, but three rounds of the headline chain are 31 KB of code and ran 34 % SLOWER than
+// one round with its ~60 moves (profiles/r02a_sweep.jsonl: the instruction cache is a first-order
+// effect here), so every chain runs one round per trip.  VAR = ChainC MODE.
 #ifndef AVS_RWU_OVERRIDE
 #define AVS_RWU_OVERRIDE 0
 #endif
-// VAR 4 / 5 (tuning experiment, headline chain only): modes 1 / 2 with ONE round per trip of the
-// register-window loop (a third of the code, register moves at the back edge instead).
 template <class S0, class S1, class S2, int REPS_LAST, int LAH, int LAV, int RWU, int VAR, bool IS_V, int SRCT>
-using ChainV = ChainC<S0, S1, S2, REPS_LAST, (IS_V ? LAV : LAH),
-                      ((VAR >= 4 ? VAR - 3 : VAR) == 2 && !IS_V) ? 1 : (VAR >= 4 ? VAR - 3 : VAR),
-                      IS_V ? AVIRB200_F32 : SRCT, AVS_RWU_OVERRIDE ? AVS_RWU_OVERRIDE : (VAR >= 4 ? 1 : RWU)>;
+using ChainV = ChainC<S0, S1, S2, REPS_LAST, (IS_V ? LAV : LAH), (VAR == 2 && !IS_V) ? 1 : VAR, IS_V ? AVIRB200_F32 : SRCT,
+                      AVS_RWU_OVERRIDE ? AVS_RWU_OVERRIDE : RWU>;
 
 // cfg3, float8_dil mirror (k = 2): RESIZE(24 taps, source step 2) -> 8-tap correction FIR
 template <int VAR, bool IS_V, int SRCT = AVIRB200_F32>
 using ChainDil24 = ChainV<StepC<K_RESIZE, AVIRB200_SUM_DIL8, 24, 2>, StepC<K_FIR, AVIRB200_SUM_DIL8, 8, 1>, NoStep,
-                          1, 2, 3, 3, VAR, IS_V, SRCT>;
+                          1, 2, 3, 1, VAR, IS_V, SRCT>;
 // k = 2 in build mode 1, interleaved classes (fpclass_def<float>, fpclass_float4): RESIZE(24) -> FIR(7)
 template <int VAR, bool IS_V, int SRCT = AVIRB200_F32>
 using ChainInl24 = ChainV<StepC<K_RESIZE, AVIRB200_SUM_INL, 24, 2>, StepC<K_FIR, AVIRB200_SUM_INL, 7, 1>, NoStep,
-                          1, 2, 3, 3, VAR, IS_V, SRCT>;
+                          1, 2, 3, 1, VAR, IS_V, SRCT>;
 // cfg3, float4 mirror (k = 2, build mode 0): FIR(7) -> RESIZE(18, source step 2) -> FIR(7)
 template <int VAR, bool IS_V, int SRCT = AVIRB200_F32>
 using ChainInl3 = ChainV<StepC<K_FIR, AVIRB200_SUM_INL, 7, 1>, StepC<K_RESIZE, AVIRB200_SUM_INL, 18, 2>,
-                         StepC<K_FIR, AVIRB200_SUM_INL, 7, 1>, 1, 1, 2, 2, VAR, IS_V, SRCT>;
+                         StepC<K_FIR, AVIRB200_SUM_INL, 7, 1>, 1, 1, 2, 1, VAR, IS_V, SRCT>;
 // cfg4 (k = 4, build mode 0): FIR(15, decimation 2) -> RESIZE(18, source step 2) -> FIR(7)
 template <int VAR, bool IS_V, int SRCT = AVIRB200_F32>
 using ChainInl3D = ChainV<StepC<K_FIR, AVIRB200_SUM_INL, 15, 2>, StepC<K_RESIZE, AVIRB200_SUM_INL, 18, 2>,
-                          StepC<K_FIR, AVIRB200_SUM_INL, 7, 1>, 1, 1, 1, 2, VAR, IS_V, SRCT>;
+                          StepC<K_FIR, AVIRB200_SUM_INL, 7, 1>, 1, 1, 1, 1, VAR, IS_V, SRCT>;
 // cfg5, float8_dil mirror (k = 4, build mode 1): RESIZE(56 taps, source step 4; 4-output batches) -> FIR(8)
 template <int VAR, bool IS_V, int SRCT = AVIRB200_F32>
 using ChainDil56 = ChainV<StepC<K_RESIZE, AVIRB200_SUM_DIL8, 56, 4, 4>, StepC<K_FIR, AVIRB200_SUM_DIL8, 8, 1, 4>, NoStep,
-                          1, 1, 1, 2, VAR, IS_V, SRCT>;
+                          1, 1, 1, 1, VAR, IS_V, SRCT>;
 // cfg2 (k = 0.5): FIR(7) -> RESIZE(24) over the virtual 2X line; 32 final outputs per round
 template <int VAR, bool IS_V, int SRCT = AVIRB200_F32>
 using ChainUp2 = ChainV<StepC<K_FIR, AVIRB200_SUM_INL, 7, 1>, StepC<K_RESIZE2, AVIRB200_SUM_INL, 24, 1>, NoStep,
@@ -1318,18 +1318,6 @@ inline bool stream_dispatch_chain(bool is_v, int variant, int src_type, F&& f) {
     switch (variant) {                                                                    \
         AVS_V(NAME, 0) AVS_V(NAME, 1) AVS_V(NAME, 2) AVS_V3(NAME)                         \
     default: return false;                                                                \
-    }
-    if constexpr (ID == kChainDil24) {
-        // tuning experiment: the register-window modes with one round per loop trip
-        if (variant == 4 && src_type == AVIRB200_F32) {
-            if (is_v) f(ChainTag<ChainDil24<4, true> >(), PassTag<true>());
-            else f(ChainTag<ChainDil24<4, false> >(), PassTag<false>());
-            return true;
-        }
-        if (variant == 5 && src_type == AVIRB200_F32 && is_v) {
-            f(ChainTag<ChainDil24<5, true> >(), PassTag<true>());
-            return true;
-        }
     }
     if (variant < 0 || variant >= kStreamVariants) return false;
     if constexpr (ID == kChainDil24) { AVS_VARIANTS(ChainDil24) }

@@ -201,11 +201,12 @@ inline bool stream_row_source_ok(const avirb200_plan_desc& d) {
 }
 // Output stage of the column pass, a compile-time choice of the kernel: 1 = float
 // destination without output gamma (store as is), 2 = integer destination without output gamma
-// (round, clamp, narrow), 0 = everything (sRGB de-linearisation in double included -- its code
+// and without bit-depth truncation (round, clamp, narrow; branch-free), 0 = everything (sRGB de-linearisation in double included -- its code
 // is large enough to slow the whole kernel down, hence the split).
 inline int stream_epilogue_code(const avirb200_plan_desc& d) {
     if (d.use_gamma & 2) return 0;
-    return d.out_type == AVIRB200_F32 ? 1 : 2;
+    if (d.out_type == AVIRB200_F32) return 1;
+    return d.tr_mul == 1.0f ? 2 : 0; // (bit-depth truncation: the run-time stage)
 }
 inline int stream_row_source_code(const avirb200_plan_desc& d) {
     return (d.use_gamma & 1) ? kSrcU8Srgb : d.in_type;

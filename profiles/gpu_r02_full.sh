@@ -16,19 +16,17 @@ for cfg in cfg3 cfg3f4 cfg4 u8k u8kdil; do
     timeout 300 python profiles/pass_times.py --cfg $cfg --var-h $v --var-v $v >> $out 2>> ${out}.err
   done
 done
-# headline chain: register windows with one round per loop trip (variants 4 / 5)
-timeout 300 python profiles/pass_times.py --cfg cfg3 --var-h 4 --var-v 4 >> $out 2>> ${out}.err
-timeout 300 python profiles/pass_times.py --cfg cfg3 --var-h 4 --var-v 5 >> $out 2>> ${out}.err
-for cfg in cfg2 cfg5 rgb; do
+for v in 0 1 2; do
+  timeout 300 python profiles/pass_times.py --cfg cfg5 --var-h $v --var-v $v >> $out 2>> ${out}.err
+done
+for cfg in cfg2 rgb; do
   timeout 300 python profiles/pass_times.py --cfg $cfg >> $out 2>> ${out}.err
 done
-# the chains the tile kernel beat in round 1, on the streaming kernel
-for v in 0 1 2; do
-  timeout 300 python profiles/pass_times.py --cfg cfg5 --all-chains 1 --var-h $v --var-v $v >> $out 2>> ${out}.err
-done
+timeout 300 python profiles/pass_times.py --cfg cfg5 --family 2 >> $out 2>> ${out}.err   # tile kernel, for reference
+timeout 300 python profiles/pass_times.py --cfg cfg2 --family 2 >> $out 2>> ${out}.err
 timeout 300 python profiles/pass_times.py --cfg cfg2 --all-chains 1 >> $out 2>> ${out}.err
 cut -c1-260 $out; tail -3 ${out}.err
-timeout 900 python bench.py --steps 20 --warmup 3 > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err
+timeout 420 python bench.py --steps 20 --warmup 3 > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err
 cut -c1-6000 gpurun_out/${tag}_bench.json; tail -5 gpurun_out/${tag}_bench.err
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${tag}_bench_ref.json 2> gpurun_out/${tag}_bench_ref.err
 cut -c1-300 gpurun_out/${tag}_bench_ref.json; tail -3 gpurun_out/${tag}_bench_ref.err
