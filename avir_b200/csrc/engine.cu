@@ -806,8 +806,10 @@ struct Staging {
 class CopyPool {
 public:
     static CopyPool& get() {
-        static CopyPool p;
-        return p;
+        // never destroyed: its detached workers wait on the condition variable for the life of the
+        // process, and destroying a condition variable with waiters blocks (process exit would hang)
+        static CopyPool* p = new CopyPool();
+        return *p;
     }
     // rows of `row_bytes` from src (pitch sp) to dst (pitch dp), split over the workers and the caller
     void copy2d(char* dst, size_t dp, const char* src, size_t sp, size_t row_bytes, int rows) {

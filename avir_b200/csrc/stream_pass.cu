@@ -7,7 +7,7 @@ namespace avs {
 int stream_launch(int chain, bool is_v, int epi, int variant, const StreamParams& p, int sm_count, void* stream) {
     // scheduling variant (a per-plan option, AVIRB200_OPT_STREAM_VARIANT_H / _V); every variant
     // computes the same bits (variant 3, all rounds on the checked path, is host-emulation only)
-    const int var = (variant >= 0 && variant < 3) ? variant : (is_v ? kStreamDefaultVariantV : kStreamDefaultVariantH);
+    const int var = (variant >= 0 && variant < 3) ? variant : stream_default_variant(chain, is_v);
 #define AVS_ROUTE(ID)                                                                              \
     case ID:                                                                                       \
         return is_v ? stream_launch_chain<ID, true>(var, epi, p, sm_count, stream)                 \

@@ -79,7 +79,15 @@ enum StreamChainId {
 //   3  = 0 without the straight-line loop for the interior rounds (every round takes the
 //      checked path: the cross-check of the other three)
 constexpr int kStreamVariants = 4;
-constexpr int kStreamDefaultVariantH = 0, kStreamDefaultVariantV = 0;
+// Defaults from profiles/r02c_sweep.jsonl (B200, CUDA events, L2 flushed between launches; same
+// output hash for every variant of a config): register windows win everywhere (cfg3 0.255 ->
+// 0.250 ms, cfg3 float4 mirror 0.293 -> 0.273, cfg4 1.391 -> 1.309, 8K->4K u8 0.266 -> 0.243, cfg5's
+// row pass 0.541 -> 0.231: every u8 source sample goes through the sRGB table once instead of
+// once per window read) except in cfg5's column pass (0.152 vs 0.157); the TMA-staged column
+// pass (2) costs ~3 % against per-lane cp.async (the one-lane issue sequence -- ELECT, five R2UR,
+// UTMALDG -- is ~25 instructions a round, as many as the 8 LDGSTS and their pointer increments
+// it replaces, plus the mbarrier wait).
+inline int stream_default_variant(int chain, bool is_v) { return (is_v && chain == 5 /* kChainDil56 */) ? 0 : 1; }
 
 struct StreamAxisPlan {
     int chain = kChainNone;
