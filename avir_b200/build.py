@@ -97,7 +97,7 @@ def _build_cuda(force=False, verbose=False):
     target = os.path.join(PKG, "libavirb200.so")
     # (source, object, extra flags); stream_chain.cu holds the kernels of ONE pass of ONE streaming
     # chain and is compiled once per chain id (stream_types.h: StreamChainId 1..6) and pass, in parallel
-    chains = list(range(1, 7))
+    chains = list(range(1, 8))
     jobs = [(os.path.join(CSRC, n + ".cu"), os.path.join(PKG, n + ".o"), [])
             for n in ("engine", "lancir")]
     jobs.append((os.path.join(CSRC, "stream_pass.cu"), os.path.join(PKG, "stream_pass.o"), []))

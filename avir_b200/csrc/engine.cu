@@ -1056,15 +1056,15 @@ int avirb200_plan_set_option(avirb200_plan* pl, int option, int value) {
     case AVIRB200_OPT_HOST_BANDS: pl->opt_host_bands = value >= 1 ? value : -1; return 0;
     case AVIRB200_OPT_OVERLAP_HALO: pl->opt_overlap = (value == 0) ? 0 : 1; return 0;
     case AVIRB200_OPT_ALL_STREAM_CHAINS: {
-        const int on = value > 0 ? 1 : 0;
+        const int on = value > 0 ? (value == 2 ? 2 : 1) : 0;
         if (on != pl->opt_all_chains) { // re-decide which passes run on the streaming kernel (host arithmetic only)
             pl->opt_all_chains = on;
             pl->stream_h.chain = pl->stream_v.chain = 0;
             const avirb200_plan_desc& d = pl->desc;
             const int ch = pl->pad4 ? 4 : d.channels;
             if (avs::stream_row_source_ok(d))
-                avs::stream_plan_axis(pl->h.desc, d.sum_mode, ch, pl->stream_h, on != 0, false);
-            avs::stream_plan_axis(pl->v.desc, d.sum_mode, ch, pl->stream_v, on != 0, true);
+                avs::stream_plan_axis(pl->h.desc, d.sum_mode, ch, pl->stream_h, on, false);
+            avs::stream_plan_axis(pl->v.desc, d.sum_mode, ch, pl->stream_v, on, true);
         }
         return 0;
     }
@@ -1192,8 +1192,8 @@ int avirb200_plan_create(const avirb200_plan_desc* desc, avirb200_plan** out) {
         sd.prefix_dc = pl->v.pdc[i].data(); sd.suffix_dc = pl->v.sdc[i].data();
     }
     if (avs::stream_row_source_ok(pl->desc))
-        avs::stream_plan_axis(pl->h.desc, desc->sum_mode, d4.channels, pl->stream_h, false, false);
-    avs::stream_plan_axis(pl->v.desc, desc->sum_mode, d4.channels, pl->stream_v, false, true);
+        avs::stream_plan_axis(pl->h.desc, desc->sum_mode, d4.channels, pl->stream_h, 0, false);
+    avs::stream_plan_axis(pl->v.desc, desc->sum_mode, d4.channels, pl->stream_v, 0, true);
     if (try4) {
         const bool h4 = pl->stream_h.chain != 0 || pl->fast.h_ok, v4 = pl->stream_v.chain != 0 || pl->fast.v_ok;
         if (h4 && v4) {

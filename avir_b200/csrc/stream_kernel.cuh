@@ -98,7 +98,10 @@ constexpr int cdiv(int a, int b) { return (a + b - 1) / b; }
 //              slides through a register window; later steps never touch shared memory),
 //            2 = 1 + mbarrier-tracked source ring filled by one-lane tensor copies (TMA; column pass),
 //            3 = 0 without the separate straight-line loop (every round takes the checked path)
-template <class S0, class S1, class S2, int REPS_LAST, int LA, int MODE_ = 0, int SRCT_ = AVIRB200_F32, int RWU_ = 1>
+//   NWMAX    warps per block the chain aims for (8: two per scheduler; 12 where registers -- at most
+//            168 a thread -- and the per-warp rings allow three)
+template <class S0, class S1, class S2, int REPS_LAST, int LA, int MODE_ = 0, int SRCT_ = AVIRB200_F32, int RWU_ = 1,
+          int NWMAX_ = 8>
 struct ChainC {
     using T0 = S0;
     using T1 = S1;
@@ -124,7 +127,10 @@ struct ChainC {
     static_assert((S1::CH * reps1) % S0::M == 0, "step 0 batches per round");
     static constexpr int B = (NS == 3) ? S2::M * reps2 : S1::M * reps1; // final outputs per round
     static constexpr int SRC_N = S0::CH * reps0;                        // source positions per round
-    static_assert(SRC_N % 16 == 0, "source positions per round must be whole 16-position loads");
+    // the loader moves a group in sweeps of POSW positions x 16 lines, NK copies per lane
+    static constexpr int POSW = (SRC_N >= 16) ? 16 : SRC_N;
+    static constexpr int NK = POSW / 2;
+    static_assert(SRC_N % POSW == 0 && (POSW == 16 || POSW == 8), "source positions per round: whole 8- or 16-position sweeps");
     // consumer i+1 needs its producer d rounds ahead
     static constexpr int d0 = cdiv(cdiv(S1::W, S1::CH) - 1, reps1);
     static constexpr int d1 = (NS == 3) ? cdiv(cdiv(S2::W, S2::CH) - 1, reps2) : 0;
@@ -151,8 +157,8 @@ struct ChainC {
     // warps per block (one block per SM): 8 (two per scheduler; the register windows leave room
     // for no more), fewer where the rings of 8 warps exceed the shared memory of an SM
     static constexpr int kSmemF2 = 227 * 1024 / 8;
-    static constexpr int NWARPS_H = (8 * WARP_F2_H <= kSmemF2) ? 8 : kSmemF2 / WARP_F2_H;
-    static constexpr int NWARPS_V = (8 * WARP_F2_V <= kSmemF2) ? 8 : kSmemF2 / WARP_F2_V;
+    static constexpr int NWARPS_H = (NWMAX_ * WARP_F2_H <= kSmemF2) ? NWMAX_ : kSmemF2 / WARP_F2_H;
+    static constexpr int NWARPS_V = (NWMAX_ * WARP_F2_V <= kSmemF2) ? NWMAX_ : kSmemF2 / WARP_F2_V;
     static_assert(NWARPS_H >= 4 && NWARPS_V >= 4, "per-warp rings too large");
 };
 
@@ -384,7 +390,7 @@ struct WarpRun {
     // (they point one sweep behind and are advanced BEFORE use: the copies read them in place
     // and the next write to them is a whole round away -- no write-after-read wait on the
     // copy queue)
-    const unsigned char* gp[C::MBAR ? 1 : 8];
+    const unsigned char* gp[C::MBAR ? 1 : C::NK];
     // row pass: the previous final batch, read back from the staging rows, waiting to be stored
     float4 pend[C::MLAST / 2];
     int pend_j0;
@@ -447,15 +453,16 @@ AVS_FN void loader_init(const StreamParams& p, WarpRun<C, IS_V>& w) {
     const int lane = w.lane;
     if constexpr (C::MBAR) return; // the checked rounds compute every address afresh, the tensor copies take coordinates
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
+    for (int k = 0; k < C::NK; ++k) {
         if (IS_V) {
             const int piece = lane & 15, rsub = lane >> 4;
-            w.gp[k] = src + (ptrdiff_t)(w.o0 - 16 + rsub + 2 * k - p.src_row_base) * (ptrdiff_t)rowb +
+            w.gp[k] = src + (ptrdiff_t)(w.o0 - C::POSW + rsub + 2 * k - p.src_row_base) * (ptrdiff_t)rowb +
                       (size_t)(w.line0 + imin_(piece, w.nlines - 1)) * 16;
         } else {
-            const int pos = lane & 15, lsub = lane >> 4;
-            w.gp[k] = src + (size_t)(w.line0 + imin_(lsub + 2 * k, w.nlines - 1)) * rowb +
-                      (ptrdiff_t)(w.o0 - 16 + pos) * PIXB;
+            constexpr int LSTEP = 32 / C::POSW; // lines one pass of the lanes covers
+            const int pos = lane & (C::POSW - 1), lsub = lane / C::POSW;
+            w.gp[k] = src + (size_t)(w.line0 + imin_(lsub + LSTEP * k, w.nlines - 1)) * rowb +
+                      (ptrdiff_t)(w.o0 - C::POSW + pos) * PIXB;
         }
     }
 }
@@ -470,47 +477,49 @@ AVS_FN void load_group(const StreamParams& p, WarpRun<C, IS_V>& w, int g, int gs
     const int lane = w.lane;
     const unsigned char* src = static_cast<const unsigned char*>(p.src);
     const size_t rowb = (size_t)p.src_pitch * (PIXB / 4);
+    constexpr int POSW = C::POSW, NK = C::NK;
 #pragma unroll
-    for (int q = 0; q < C::SRC_N / 16; ++q) {
-        const int pos0 = w.o0 + g * C::SRC_N + q * 16; // first source position of the sweep
-        unsigned char* ring = reinterpret_cast<unsigned char*>(w.ring0) + (size_t)(gslot + q * 16) * PITCH_B;
-        const bool interior = STEADY || ((pos0 >= 0) && (pos0 + 16 <= p.src_len));
+    for (int q = 0; q < C::SRC_N / POSW; ++q) {
+        const int pos0 = w.o0 + g * C::SRC_N + q * POSW; // first source position of the sweep
+        unsigned char* ring = reinterpret_cast<unsigned char*>(w.ring0) + (size_t)(gslot + q * POSW) * PITCH_B;
+        const bool interior = STEADY || ((pos0 >= 0) && (pos0 + POSW <= p.src_len));
         if (IS_V) {
             // a position is an intermediate row; the warp's 16 pixel columns are 256 contiguous bytes
             const int piece = lane & 15, rsub = lane >> 4;
             unsigned char* d = ring + rsub * PITCH_B + piece * 16;
             if constexpr (!C::MBAR) {
 #pragma unroll
-                for (int k = 0; k < 8; ++k) w.gp[k] += 16 * rowb;
+                for (int k = 0; k < NK; ++k) w.gp[k] += POSW * rowb;
             }
             if (!C::MBAR && issue && interior) {
 #pragma unroll
-                for (int k = 0; k < 8; ++k) cp_async16(d + 2 * k * PITCH_B, w.gp[k]);
+                for (int k = 0; k < NK; ++k) cp_async16(d + 2 * k * PITCH_B, w.gp[k]);
             } else if (issue) {
                 const unsigned char* col = src + (size_t)(w.line0 + imin_(piece, w.nlines - 1)) * 16;
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
+                for (int k = 0; k < NK; ++k) {
                     const int y = imin_(imax_(pos0 + rsub + 2 * k, 0), p.src_len - 1) - p.src_row_base;
                     cp_async16(d + 2 * k * PITCH_B, col + (ptrdiff_t)y * (ptrdiff_t)rowb);
                 }
             }
         } else {
-            // a position is a pixel of a row: 16 consecutive pixels of one row per half warp
-            const int pos = lane & 15, lsub = lane >> 4;
-            unsigned char* d = ring + pos * PIXB + lsub * C::LINE_B; // line lsub + 2k: + 2k * LINE_B
+            // a position is a pixel of a row: POSW consecutive pixels of one row per group of lanes
+            constexpr int LSTEP = 32 / POSW;
+            const int pos = lane & (POSW - 1), lsub = lane / POSW;
+            unsigned char* d = ring + pos * PIXB + lsub * C::LINE_B; // line lsub + LSTEP k: + LSTEP k * LINE_B
             if constexpr (!C::MBAR) {
 #pragma unroll
-                for (int k = 0; k < 8; ++k) w.gp[k] += 16 * PIXB;
+                for (int k = 0; k < NK; ++k) w.gp[k] += POSW * PIXB;
             }
             if (!C::MBAR && issue && interior) {
 #pragma unroll
-                for (int k = 0; k < 8; ++k) cp_async_px<PIXB>(d + 2 * k * C::LINE_B, w.gp[k]);
+                for (int k = 0; k < NK; ++k) cp_async_px<PIXB>(d + LSTEP * k * C::LINE_B, w.gp[k]);
             } else if (issue) {
                 const int x = imin_(imax_(pos0 + pos, 0), p.src_len - 1);
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const int line = imin_(lsub + 2 * k, w.nlines - 1);
-                    cp_async_px<PIXB>(d + 2 * k * C::LINE_B, src + (size_t)(w.line0 + line) * rowb + (size_t)x * PIXB);
+                for (int k = 0; k < NK; ++k) {
+                    const int line = imin_(lsub + LSTEP * k, w.nlines - 1);
+                    cp_async_px<PIXB>(d + LSTEP * k * C::LINE_B, src + (size_t)(w.line0 + line) * rowb + (size_t)x * PIXB);
                 }
             }
         }
@@ -1247,14 +1256,19 @@ stream_pass_kernel(const __grid_constant__ StreamParams p) {
 #ifndef AVS_RWU_OVERRIDE
 #define AVS_RWU_OVERRIDE 0
 #endif
-template <class S0, class S1, class S2, int REPS_LAST, int LAH, int LAV, int RWU, int VAR, bool IS_V, int SRCT>
+template <class S0, class S1, class S2, int REPS_LAST, int LAH, int LAV, int RWU, int VAR, bool IS_V, int SRCT, int NWMAX = 8>
 using ChainV = ChainC<S0, S1, S2, REPS_LAST, (IS_V ? LAV : LAH), (VAR == 2 && !IS_V) ? 1 : VAR, IS_V ? AVIRB200_F32 : SRCT,
-                      AVS_RWU_OVERRIDE ? AVS_RWU_OVERRIDE : RWU>;
+                      AVS_RWU_OVERRIDE ? AVS_RWU_OVERRIDE : RWU, NWMAX>;
 
 // cfg3, float8_dil mirror (k = 2): RESIZE(24 taps, source step 2) -> 8-tap correction FIR
 template <int VAR, bool IS_V, int SRCT = AVIRB200_F32>
 using ChainDil24 = ChainV<StepC<K_RESIZE, AVIRB200_SUM_DIL8, 24, 2>, StepC<K_FIR, AVIRB200_SUM_DIL8, 8, 1>, NoStep,
                           1, 2, 3, 1, VAR, IS_V, SRCT>;
+// the same chain in 4-output batches: a 30-position window and half the code per round, small
+// enough (<= 168 registers, <= 18.9 KB of rings) for THREE warps per scheduler
+template <int VAR, bool IS_V, int SRCT = AVIRB200_F32>
+using ChainDil24Q = ChainV<StepC<K_RESIZE, AVIRB200_SUM_DIL8, 24, 2, 4>, StepC<K_FIR, AVIRB200_SUM_DIL8, 8, 1, 4>, NoStep,
+                           1, 3, 3, 1, VAR, IS_V, SRCT, 12>;
 // k = 2 in build mode 1, interleaved classes (fpclass_def<float>, fpclass_float4): RESIZE(24) -> FIR(7)
 template <int VAR, bool IS_V, int SRCT = AVIRB200_F32>
 using ChainInl24 = ChainV<StepC<K_RESIZE, AVIRB200_SUM_INL, 24, 2>, StepC<K_FIR, AVIRB200_SUM_INL, 7, 1>, NoStep,
@@ -1326,6 +1340,7 @@ inline bool stream_dispatch_chain(bool is_v, int variant, int src_type, F&& f) {
     else if constexpr (ID == kChainInl3D) { AVS_VARIANTS(ChainInl3D) }
     else if constexpr (ID == kChainDil56) { AVS_VARIANTS(ChainDil56) }
     else if constexpr (ID == kChainUp2) { AVS_VARIANTS(ChainUp2) }
+    else if constexpr (ID == kChainDil24Q) { AVS_VARIANTS(ChainDil24Q) }
     else return false;
 #undef AVS_VARIANTS
 #undef AVS_INT_SRC
@@ -1343,6 +1358,7 @@ inline bool stream_dispatch(int id, bool is_v, int variant, int src_type, F&& f)
     case kChainInl3D: return stream_dispatch_chain<kChainInl3D>(is_v, variant, src_type, f);
     case kChainDil56: return stream_dispatch_chain<kChainDil56>(is_v, variant, src_type, f);
     case kChainUp2: return stream_dispatch_chain<kChainUp2>(is_v, variant, src_type, f);
+    case kChainDil24Q: return stream_dispatch_chain<kChainDil24Q>(is_v, variant, src_type, f);
     default: return false;
     }
 }

@@ -25,6 +25,7 @@ AVS_DECL_CHAIN(kChainInl3)
 AVS_DECL_CHAIN(kChainInl3D)
 AVS_DECL_CHAIN(kChainDil56)
 AVS_DECL_CHAIN(kChainUp2)
+AVS_DECL_CHAIN(kChainDil24Q)
 #undef AVS_DECL_CHAIN
 
 } // namespace avs

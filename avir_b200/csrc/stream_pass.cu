@@ -19,6 +19,7 @@ int stream_launch(int chain, bool is_v, int epi, int variant, const StreamParams
         AVS_ROUTE(kChainInl3D)
         AVS_ROUTE(kChainDil56)
         AVS_ROUTE(kChainUp2)
+        AVS_ROUTE(kChainDil24Q)
     default: return -2;
     }
 #undef AVS_ROUTE

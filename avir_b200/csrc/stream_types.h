@@ -66,6 +66,8 @@ enum StreamChainId {
     kChainInl3D, // FIR15/2 -> RESIZE(18, D2) -> FIR7      cfg4 (k = 4, build mode 0)
     kChainDil56, // RESIZE(56, D4) -> FIR8                 cfg5, float8_dil mirror (k = 4, build mode 1)
     kChainUp2,   // FIR7 -> RESIZE2(24)                    cfg2 (k = 0.5, build mode 1)
+    kChainDil24Q, // = kChainDil24 in 4-output batches, three warps per scheduler (selected instead of it
+                  //   with AVIRB200_OPT_ALL_STREAM_CHAINS = 2)
     kChainCount
 };
 
@@ -111,7 +113,7 @@ inline const StepSpec* chain_spec(int id, int* nsteps) {
                                      {K_FIR, AVIRB200_SUM_INL, 7, 1}};
     static const StepSpec up2[] = {{K_FIR, AVIRB200_SUM_INL, 7, 1}, {K_RESIZE2, AVIRB200_SUM_INL, 24, 1}};
     switch (id) {
-    case kChainDil24: *nsteps = 2; return dil24;
+    case kChainDil24: case kChainDil24Q: *nsteps = 2; return dil24;
     case kChainInl24: *nsteps = 2; return inl24;
     case kChainInl3: *nsteps = 3; return inl3;
     case kChainInl3D: *nsteps = 3; return inl3d;
@@ -170,7 +172,7 @@ inline bool stream_match_step(const avirb200_step_desc& d, const StepSpec& sp, S
 // Decides whether the axis runs on the streaming kernel; on success `out` holds everything
 // the kernel parameters need.
 inline bool stream_plan_axis(const avirb200_axis_desc& ad, int sum_mode, int channels, StreamAxisPlan& out,
-                             bool allow_deselected = false, bool is_v = false) {
+                             int allow_deselected = 0, bool is_v = false) {
     out.chain = kChainNone;
     if (channels != 4) return false;
     // allow_deselected (AVIRB200_OPT_ALL_STREAM_CHAINS): the upsizing chain is instantiated and
@@ -179,6 +181,8 @@ inline bool stream_plan_axis(const avirb200_axis_desc& ad, int sum_mode, int cha
     // other way round, 0.044 vs 0.057 ms; profiles/r02a_sweep.jsonl).
     for (int id = 1; id < kChainCount; ++id) {
         if (id == kChainUp2 && is_v && !allow_deselected) continue;
+        if (id == kChainDil24Q && allow_deselected != 2) continue;
+        if (id == kChainDil24 && allow_deselected == 2) continue;
         int ns = 0;
         const StepSpec* spec = chain_spec(id, &ns);
         if (ns != ad.nsteps) continue;

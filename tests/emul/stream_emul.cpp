@@ -70,18 +70,20 @@ extern "C" {
 // 1 when both axes of the descriptor run on the streaming kernel (f32 source only).
 int stream_emul_applicable(const avirb200_plan_desc* d) {
     StreamAxisPlan h, v;
-    return stream_row_source_ok(*d) && stream_plan_axis(d->h, d->sum_mode, d->channels, h, true) &&
-           stream_plan_axis(d->v, d->sum_mode, d->channels, v, true);
+    return stream_row_source_ok(*d) && stream_plan_axis(d->h, d->sum_mode, d->channels, h, 1) &&
+           stream_plan_axis(d->v, d->sum_mode, d->channels, v, 1);
 }
 
 // Row pass with `warps_h` emulated warps, then the column pass in `bands` destination bands
 // (as the sharded schedule runs it) with `warps_v` warps each.
 // lut: the 256-entry u8 sRGB linearisation table (read for sRGB sources only).
+// allow: 1 = every chain (as AVIRB200_OPT_ALL_STREAM_CHAINS = 1), 2 = the 4-output-batch twin of the
+// headline chain where it applies.
 int stream_emul_resize(const avirb200_plan_desc* d, const void* src, size_t src_pitch, void* dst,
-                       size_t dst_pitch, int warps_h, int warps_v, int bands, int variant, const float* lut) {
+                       size_t dst_pitch, int warps_h, int warps_v, int bands, int variant, const float* lut, int allow) {
     StreamAxisPlan h, v;
-    if (!stream_row_source_ok(*d) || !stream_plan_axis(d->h, d->sum_mode, d->channels, h, true) ||
-        !stream_plan_axis(d->v, d->sum_mode, d->channels, v, true))
+    if (!stream_row_source_ok(*d) || !stream_plan_axis(d->h, d->sum_mode, d->channels, h, allow) ||
+        !stream_plan_axis(d->v, d->sum_mode, d->channels, v, allow))
         return -4;
     std::vector<float> mid((size_t)d->src_h * d->dst_w * 4);
     StreamParams p;
@@ -124,9 +126,9 @@ int stream_emul_variants(void) { return kStreamVariants; }
 // out[3] = column-pass epilogue code.  all_chains: as with AVIRB200_STREAM_ALL=1.
 void stream_emul_selection(const avirb200_plan_desc* d, int all_chains, int* out) {
     StreamAxisPlan h, v;
-    out[0] = (stream_row_source_ok(*d) && stream_plan_axis(d->h, d->sum_mode, d->channels, h, all_chains != 0, false))
+    out[0] = (stream_row_source_ok(*d) && stream_plan_axis(d->h, d->sum_mode, d->channels, h, all_chains, false))
                  ? h.chain : 0;
-    out[1] = stream_plan_axis(d->v, d->sum_mode, d->channels, v, all_chains != 0, true) ? v.chain : 0;
+    out[1] = stream_plan_axis(d->v, d->sum_mode, d->channels, v, all_chains, true) ? v.chain : 0;
     out[2] = stream_row_source_code(*d);
     out[3] = stream_epilogue_code(*d);
 }

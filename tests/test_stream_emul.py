@@ -22,7 +22,7 @@ def emul():
     from avir_b200 import build as b
     lib = C.CDLL(b.build_emul())
     lib.stream_emul_resize.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t,
-                                       C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+                                       C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
     lib.stream_emul_resize.restype = C.c_int
     lib.stream_emul_applicable.argtypes = [C.c_void_p]
     lib.stream_emul_applicable.restype = C.c_int
@@ -101,7 +101,32 @@ def test_stream_kernel_emulation_matches_port(emul, ec, variant):
         lut = np.zeros(256, np.float32)
         cs.port().avir_port_srgb_lut(lut.ctypes.data)
         assert emul.stream_emul_resize(dp, src.ctypes.data, sw * ch, got.ctypes.data, nw * ch, wh, wv, bands,
-                                       variant, lut.ctypes.data) == 0
+                                       variant, lut.ctypes.data, 1) == 0
+    finally:
+        rs.free_descriptor(h)
+    want, _ = cs.port_output(case, src)
+    assert cs.count_mismatch(want, got) == 0
+
+
+# the headline chain's 4-output-batch twin (sweeps of 8 source positions, 12 warps per block on the device)
+@pytest.mark.parametrize("variant", range(4))
+@pytest.mark.parametrize("ec", [e for e in EMUL_CASES if e[0][0] == 2 and e[0][9].get("buildmode") == 1
+                                and e[0][2] == 2 * e[0][4] and not e[0][9].get("gamma")], ids=_id)
+def test_stream_kernel_emulation_q_chain_matches_port(emul, ec, variant):
+    case, wh, wv, bands = ec
+    fp, sw, sh, nw, nh, ch, ti, to, rb, kw = case
+    src = cs.make_input(case)
+    rs, v = cs.resizer_and_vars(case)
+    h, dp, modes = rs.descriptor(src.shape, src.dtype, nw, nh, to, kw.get("k", 0.0), v)
+    try:
+        out = (C.c_int * 4)()
+        emul.stream_emul_selection.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int)]
+        emul.stream_emul_selection(dp, 2, out)
+        assert (out[0], out[1]) == (7, 7), list(out)
+        got = np.zeros((nh, nw, ch), to)
+        lut = np.zeros(256, np.float32)
+        assert emul.stream_emul_resize(dp, src.ctypes.data, sw * ch, got.ctypes.data, nw * ch, wh, wv, bands,
+                                       variant, lut.ctypes.data, 2) == 0
     finally:
         rs.free_descriptor(h)
     want, _ = cs.port_output(case, src)
@@ -203,7 +228,7 @@ def test_stream_kernel_emulation_fuzz(emul):
             wh, wv = int(rng.integers(1, 9)), int(rng.integers(1, 9))
             bands, var = int(rng.integers(1, 5)), int(rng.integers(0, 4))
             assert emul.stream_emul_resize(dp, src.ctypes.data, sw * 4, got.ctypes.data, nw * 4, wh, wv, bands,
-                                           var, lut.ctypes.data) == 0
+                                           var, lut.ctypes.data, 1 + (it & 1)) == 0
         finally:
             rs.free_descriptor(h)
         want, _ = cs.port_output(case, src)
