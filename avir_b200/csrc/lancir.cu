@@ -198,13 +198,15 @@ __device__ __forceinline__ float4 ladd4(float4 a, float4 b) {
 
 constexpr int kLColRows = 32; // output rows a block of the column pass walks
 
-template <typename TIN>
+// KL: compile-time kernel length (all taps' loads of an output are issued before the first
+// product: the loop is unrolled) for the common lengths, 0 = run-time length.
+template <typename TIN, int KL>
 __global__ void __launch_bounds__(256) lancir_col4_kernel(const __grid_constant__ LParams p) {
     const int px = blockIdx.x * 256 + threadIdx.x;
     if (px >= p.src_w) return;
     const int y0 = blockIdx.y * kLColRows;
     const int y1 = (y0 + kLColRows < p.dst_h) ? y0 + kLColRows : p.dst_h;
-    const int kl = p.v.kl, src_h = p.src_h;
+    const int kl = KL ? KL : p.v.kl, src_h = p.src_h;
     const long long pitch = p.src_pitch;
     for (int y = y0; y < y1; ++y) {
         const float* f = p.v.taps + (size_t)__ldg(p.v.phase + y) * kl;
@@ -214,22 +216,35 @@ __global__ void __launch_bounds__(256) lancir_col4_kernel(const __grid_constant_
             sy = sy < 0 ? 0 : (sy >= src_h ? src_h - 1 : sy);
             return LPix<TIN>::load(p.src, (long long)sy * pitch + (long long)px * 4);
         };
-        float4 ev = lmul4(__ldg(f), S(0)), od = lmul4(__ldg(f + 1), S(1));
-        for (int t = 2; t < kl; t += 2) {
-            ev = ladd4(ev, lmul4(__ldg(f + t), S(t)));
-            od = ladd4(od, lmul4(__ldg(f + t + 1), S(t + 1)));
+        float4 ev, od;
+        if (KL) {
+            float4 x[KL ? KL : 1];
+#pragma unroll
+            for (int t = 0; t < KL; ++t) x[t] = S(t);
+            ev = lmul4(__ldg(f), x[0]); od = lmul4(__ldg(f + 1), x[1]);
+#pragma unroll
+            for (int t = 2; t < KL; t += 2) {
+                ev = ladd4(ev, lmul4(__ldg(f + t), x[t]));
+                od = ladd4(od, lmul4(__ldg(f + t + 1), x[t + 1]));
+            }
+        } else {
+            ev = lmul4(__ldg(f), S(0)); od = lmul4(__ldg(f + 1), S(1));
+            for (int t = 2; t < kl; t += 2) {
+                ev = ladd4(ev, lmul4(__ldg(f + t), S(t)));
+                od = ladd4(od, lmul4(__ldg(f + t + 1), S(t + 1)));
+            }
         }
         reinterpret_cast<float4*>(p.mid + (size_t)y * p.src_w * 4)[px] = ladd4(ev, od);
     }
 }
 
 // OUT: 0 float, 1 u8, 2 u16
-template <int OUT>
+template <int OUT, int KL>
 __global__ void __launch_bounds__(256) lancir_row4_kernel(const __grid_constant__ LParams p) {
     const int x = blockIdx.x * 256 + threadIdx.x;
     const int y = blockIdx.y;
     if (x >= p.dst_w) return;
-    const int kl = p.h.kl, src_w = p.src_w;
+    const int kl = KL ? KL : p.h.kl, src_w = p.src_w;
     const float* f = p.h.taps + (size_t)__ldg(p.h.phase + x) * kl;
     const int s0 = __ldg(p.h.src_pos + x);
     const float4* row = reinterpret_cast<const float4*>(p.mid + (size_t)y * src_w * 4);
@@ -238,10 +253,23 @@ __global__ void __launch_bounds__(256) lancir_row4_kernel(const __grid_constant_
         sx = sx < 0 ? 0 : (sx >= src_w ? src_w - 1 : sx);
         return row[sx];
     };
-    float4 ev = lmul4(__ldg(f), M(0)), od = lmul4(__ldg(f + 1), M(1));
-    for (int t = 2; t < kl; t += 2) {
-        ev = ladd4(ev, lmul4(__ldg(f + t), M(t)));
-        od = ladd4(od, lmul4(__ldg(f + t + 1), M(t + 1)));
+    float4 ev, od;
+    if (KL) {
+        float4 xw[KL ? KL : 1];
+#pragma unroll
+        for (int t = 0; t < KL; ++t) xw[t] = M(t);
+        ev = lmul4(__ldg(f), xw[0]); od = lmul4(__ldg(f + 1), xw[1]);
+#pragma unroll
+        for (int t = 2; t < KL; t += 2) {
+            ev = ladd4(ev, lmul4(__ldg(f + t), xw[t]));
+            od = ladd4(od, lmul4(__ldg(f + t + 1), xw[t + 1]));
+        }
+    } else {
+        ev = lmul4(__ldg(f), M(0)); od = lmul4(__ldg(f + 1), M(1));
+        for (int t = 2; t < kl; t += 2) {
+            ev = ladd4(ev, lmul4(__ldg(f + t), M(t)));
+            od = ladd4(od, lmul4(__ldg(f + t + 1), M(t + 1)));
+        }
     }
     float4 v = ladd4(ev, od);
     if (!p.unity) v = lmul4(p.out_mul, v);
@@ -368,18 +396,40 @@ int lancirb200_resize_device(const lancirb200_plan* pl, const void* d_src, size_
                          ((uintptr_t)d_ws % 16) == 0;
     if (vec_in) {
         dim3 g1((d.src_w + 255) / 256, (d.dst_h + kLColRows - 1) / kLColRows);
-        if (d.in_type == AVIRB200_U8) lancir_col4_kernel<unsigned char><<<g1, 256, 0, st>>>(p);
-        else if (d.in_type == AVIRB200_U16) lancir_col4_kernel<unsigned short><<<g1, 256, 0, st>>>(p);
-        else lancir_col4_kernel<float><<<g1, 256, 0, st>>>(p);
+#define LCOL(KL)                                                                                        \
+    do {                                                                                                \
+        if (d.in_type == AVIRB200_U8) lancir_col4_kernel<unsigned char, KL><<<g1, 256, 0, st>>>(p);     \
+        else if (d.in_type == AVIRB200_U16) lancir_col4_kernel<unsigned short, KL><<<g1, 256, 0, st>>>(p); \
+        else lancir_col4_kernel<float, KL><<<g1, 256, 0, st>>>(p);                                      \
+    } while (0)
+        switch (pl->dv.kl) { // la = 3: 6 taps when upsizing, 12 at k = 2, 18 at k = 3, 24 at k = 4
+        case 6: LCOL(6); break;
+        case 12: LCOL(12); break;
+        case 18: LCOL(18); break;
+        case 24: LCOL(24); break;
+        default: LCOL(0); break;
+        }
+#undef LCOL
     } else {
         dim3 g1((d.src_w * d.channels + 255) / 256, d.dst_h);
         lancir_col_kernel<<<g1, 256, 0, st>>>(p);
     }
     if (vec_out) {
         dim3 g2((d.dst_w + 255) / 256, d.dst_h);
-        if (d.out_type == AVIRB200_U8) lancir_row4_kernel<1><<<g2, 256, 0, st>>>(p);
-        else if (d.out_type == AVIRB200_U16) lancir_row4_kernel<2><<<g2, 256, 0, st>>>(p);
-        else lancir_row4_kernel<0><<<g2, 256, 0, st>>>(p);
+#define LROW(KL)                                                                                        \
+    do {                                                                                                \
+        if (d.out_type == AVIRB200_U8) lancir_row4_kernel<1, KL><<<g2, 256, 0, st>>>(p);                \
+        else if (d.out_type == AVIRB200_U16) lancir_row4_kernel<2, KL><<<g2, 256, 0, st>>>(p);          \
+        else lancir_row4_kernel<0, KL><<<g2, 256, 0, st>>>(p);                                          \
+    } while (0)
+        switch (pl->dh.kl) {
+        case 6: LROW(6); break;
+        case 12: LROW(12); break;
+        case 18: LROW(18); break;
+        case 24: LROW(24); break;
+        default: LROW(0); break;
+        }
+#undef LROW
     } else {
         dim3 g2((d.dst_w * d.channels + 255) / 256, d.dst_h);
         lancir_row_kernel<<<g2, 256, 0, st>>>(p);
