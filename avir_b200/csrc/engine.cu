@@ -342,6 +342,9 @@ size_t pad4_dst_bytes(const avirb200_plan* pl, int rows) {
 int run_row_pass(const avirb200_plan* pl, const void* d_src, size_t src_pitch, float* d_mid,
                  int rows, cudaStream_t st, int* launches, void* scratch4 = nullptr) {
     if (rows <= 0) return 0;
+    // (a non-sticky error another library left in this thread -- NCCL's peer-access probing leaves
+    // cudaErrorPeerAccessAlreadyEnabled once the IPC mailboxes have enabled it -- is not this launch's)
+    (void)cudaGetLastError();
     const avirb200_plan_desc& d = pl->desc;
     const bool p4 = use_pad4(pl);
     if (p4) {
@@ -404,6 +407,7 @@ int run_row_pass(const avirb200_plan* pl, const void* d_src, size_t src_pitch, f
 int run_col_pass(const avirb200_plan* pl, const float* d_mid, int mid_row_base, void* d_dst,
                  size_t dst_pitch, int out0, int out1, cudaStream_t st, int* launches, void* scratch4 = nullptr) {
     if (out1 <= out0) return 0;
+    (void)cudaGetLastError(); // (see run_row_pass)
     const avirb200_plan_desc& d = pl->desc;
     const bool p4 = use_pad4(pl);
     void* const user_dst = d_dst;
@@ -930,6 +934,7 @@ struct Halo {
     size_t up_bytes = 0, down_bytes = 0, slot_bytes = 0;             // my own layout
     size_t nb_up_off = 0, nb_up_slot = 0, nb_up_bytes = 0;           // where my top rows go in rank-1's box
     size_t nb_down_off = 0, nb_down_slot = 0, nb_down_bytes = 0;     // where my bottom rows go in rank+1's box
+    unsigned long long off_up = 0, off_down = 0; // the neighbours' mailboxes inside their allocations
     unsigned seq = 0;
     unsigned* h_seq = nullptr; // pinned ring of sequence numbers the flag copies read
 };
@@ -950,9 +955,12 @@ __global__ void halo_wait_kernel(const volatile unsigned* flags, unsigned seq, i
 
 void halo_free(Halo* h) {
     if (h == nullptr) return;
-    if (h->box_up) cudaIpcCloseMemHandle(h->box_up);
-    if (h->box_down) cudaIpcCloseMemHandle(h->box_down);
-    cudaFree(h->box);
+    if (h->box_up) cudaIpcCloseMemHandle(h->box_up - h->off_up);
+    if (h->box_down) cudaIpcCloseMemHandle(h->box_down - h->off_down);
+    // The mailbox itself is NOT freed: a neighbour process may still have it mapped (plans are
+    // destroyed without a collective), and freeing exported memory before every importer has closed
+    // it is undefined behaviour (CUDA IPC).  A few MB per sharded plan stay allocated until the
+    // process ends.
     cudaFreeHost(h->h_seq);
     delete h;
 }
@@ -991,17 +999,36 @@ int halo_setup(avirb200_plan* pl, void* comm, int rank, int nranks, cudaStream_t
     }
     cudaIpcMemHandle_t mine;
     std::memset(&mine, 0, sizeof mine);
-    if (ok) ok = cudaMalloc(&h->box, 256 + 2 * h->slot_bytes + 256) == cudaSuccess;
+    // its own allocation (the driver carves small requests out of shared blocks, and an IPC handle
+    // names the whole block): at least 2 MiB, in multiples of 2 MiB
+    const size_t box_bytes = ((256 + 2 * h->slot_bytes + 256) + (2u << 20) - 1) / (2u << 20) * (2u << 20);
+    if (ok) ok = cudaMalloc(&h->box, box_bytes) == cudaSuccess;
     if (ok) ok = cudaMemset(h->box, 0, 256) == cudaSuccess;
     if (ok) ok = cudaHostAlloc(&h->h_seq, 64 * sizeof(unsigned), cudaHostAllocPortable) == cudaSuccess;
     if (ok) ok = cudaIpcGetMemHandle(&mine, h->box) == cudaSuccess;
-    // all-gather (handle, ok) records
-    const size_t rec = sizeof(cudaIpcMemHandle_t) + 8;
+    // (an IPC handle names the allocation the pointer lies in; importers add the pointer's offset in it)
+    unsigned long long box_off = 0;
+    if (ok) {
+        typedef int (*RangeFn)(unsigned long long*, size_t*, unsigned long long);
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        unsigned long long base = 0;
+        size_t len = 0;
+        if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &f, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess && f != nullptr &&
+            reinterpret_cast<RangeFn>(f)(&base, &len, (unsigned long long)(uintptr_t)h->box) == 0)
+            box_off = (unsigned long long)(uintptr_t)h->box - base;
+        else
+            cudaGetLastError();
+    }
+    // all-gather (handle, ok, offset) records
+    const size_t rec = sizeof(cudaIpcMemHandle_t) + 16;
     std::vector<char> hostrec((size_t)nranks * rec, 0);
     char* drec = nullptr;
     if (cudaMalloc(&drec, (size_t)nranks * rec) != cudaSuccess) { cudaGetLastError(); return fail(AVIRB200_ERR_ALLOC, "halo setup"); }
     std::memcpy(&hostrec[(size_t)rank * rec], &mine, sizeof mine);
     hostrec[(size_t)rank * rec + sizeof mine] = ok ? 1 : 0;
+    std::memcpy(&hostrec[(size_t)rank * rec + sizeof mine + 8], &box_off, 8);
     cudaMemcpyAsync(drec + (size_t)rank * rec, &hostrec[(size_t)rank * rec], rec, cudaMemcpyHostToDevice, st);
     int nr = nc->AllGather ? nc->AllGather(drec + (size_t)rank * rec, drec, rec, /*ncclChar*/ 0, comm, st) : 1;
     cudaError_t ce = cudaMemcpyAsync(hostrec.data(), drec, (size_t)nranks * rec, cudaMemcpyDeviceToHost, st);
@@ -1016,11 +1043,19 @@ int halo_setup(avirb200_plan* pl, void* comm, int rank, int nranks, cudaStream_t
         cudaIpcMemHandle_t hh;
         std::memcpy(&hh, &hostrec[(size_t)(rank - 1) * rec], sizeof hh);
         mapped = mapped && cudaIpcOpenMemHandle((void**)&h->box_up, hh, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+        unsigned long long off = 0;
+        std::memcpy(&off, &hostrec[(size_t)(rank - 1) * rec + sizeof hh + 8], 8);
+        if (mapped) h->box_up += off;
+        h->off_up = off;
     }
     if (all_ok && rank + 1 < nranks) {
         cudaIpcMemHandle_t hh;
         std::memcpy(&hh, &hostrec[(size_t)(rank + 1) * rec], sizeof hh);
         mapped = mapped && cudaIpcOpenMemHandle((void**)&h->box_down, hh, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+        unsigned long long off = 0;
+        std::memcpy(&off, &hostrec[(size_t)(rank + 1) * rec + sizeof hh + 8], 8);
+        if (mapped) h->box_down += off;
+        h->off_down = off;
     }
     cudaGetLastError();
     std::vector<char> flags((size_t)nranks, 0);
@@ -1671,6 +1706,7 @@ int avirb200_resize_sharded(const avirb200_plan* cpl, void* comm, int rank, int 
         const int need_up = (rank > 0 && si.halo_up > 0) ? 1 : 0;
         const int need_down = (rank + 1 < nranks && si.halo_down > 0) ? 1 : 0;
         if (need_up || need_down) {
+            (void)cudaGetLastError();
             halo_wait_kernel<<<1, 32, 0, st>>>(reinterpret_cast<const volatile unsigned*>(h->box), seq, need_up, need_down);
             ++launches;
             CUDA_TRY(cudaGetLastError());

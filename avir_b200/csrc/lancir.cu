@@ -389,6 +389,7 @@ int lancirb200_resize_device(const lancirb200_plan* pl, const void* d_src, size_
     p.dst = d_dst; p.dst_pitch = (long long)dst_pitch;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (d.dst_h > 65535) return lfail(AVIRB200_ERR_UNSUPPORTED, "image too tall");
+    (void)cudaGetLastError(); // (a stale non-sticky error of another library is not this launch's)
     // 4-channel images whose pixels are aligned to their own size: the vector kernels
     const bool vec_in = d.channels == 4 && (src_pitch % 4) == 0 && ((uintptr_t)d_src % (4 * lsize(d.in_type))) == 0 &&
                         ((uintptr_t)d_ws % 16) == 0;

@@ -57,8 +57,15 @@ def main():
     assert lib.avirb200_comm_create(raw, rank, world, C.byref(comm)) == 0, lib.avirb200_last_error()
     st = torch.cuda.current_stream().cuda_stream
     bad = 0
+    overlaps = [int(v) for v in os.environ.get("AVIR_NCCL_OVERLAPS", "1,0").split(",")]
+    debug = os.environ.get("AVIR_NCCL_DEBUG") == "1"
+
+    def dbg(*a):
+        if debug:
+            torch.cuda.synchronize()
+            print("[rank %d]" % rank, *a, flush=True)
     for case in CASES:
-        for overlap in (1, 0):
+        for overlap in overlaps:
             fp, sw, sh, nw, nh, ch, ti, to, rb, kw = case
             src = cs.make_input(case, seed=77)  # same image on every rank
             rs, v = cs.resizer_and_vars(case)
@@ -75,10 +82,12 @@ def main():
             d_band = d_all[si.src_row0:si.src_row0 + si.src_rows].contiguous()
             d_dst = torch.zeros((si.dst_rows, nw, ch), device="cuda", dtype=TT[to])
             d_ws = torch.empty(wsb.value, dtype=torch.uint8, device="cuda")
-            for _ in range(2):  # twice: the second call reuses the exchange buffers / flags
+            dbg("plan ready", cs.case_id(case), "overlap", overlap, "halo", si.halo_up, si.halo_down, "ws", wsb.value)
+            for it in range(2):  # twice: the second call reuses the exchange buffers / flags
                 assert lib.avirb200_resize_sharded(plan, comm, rank, world, d_band.data_ptr(), sw * ch,
                                                    d_dst.data_ptr(), nw * ch, d_ws.data_ptr(), st) == 0, \
                     lib.avirb200_last_error()
+                dbg("sharded call", it, "done")
             torch.cuda.synchronize()
             whole = torch.zeros((nh, nw, ch), device="cuda", dtype=TT[to])
             ws2 = torch.empty(wsf.value, dtype=torch.uint8, device="cuda")
@@ -94,8 +103,10 @@ def main():
                 print("%s overlap=%d ranks=%d halo=%d/%d mismatches=%d" % (cs.case_id(case), overlap, world,
                                                                           si.halo_up, si.halo_down, int(n.item())), flush=True)
             bad += int(n.item())
+            dist.barrier()  # (a rank's mailbox is freed only after every rank is done with the case)
             lib.avirb200_plan_destroy(plan)
             rs.free_descriptor(h)
+            dbg("plan destroyed")
     lib.avirb200_comm_destroy(comm)
     dist.destroy_process_group()
     sys.exit(1 if bad else 0)
