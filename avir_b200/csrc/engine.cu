@@ -404,8 +404,10 @@ int run_row_pass(const avirb200_plan* pl, const void* d_src, size_t src_pitch, f
 }
 
 // scratch4: where the band's 4-channel destination rows go when use_pad4(pl) (then narrowed into d_dst).
+// mid_rows: intermediate rows the buffer holds from mid_row_base on (< 0: up to the image's last row).
 int run_col_pass(const avirb200_plan* pl, const float* d_mid, int mid_row_base, void* d_dst,
-                 size_t dst_pitch, int out0, int out1, cudaStream_t st, int* launches, void* scratch4 = nullptr) {
+                 size_t dst_pitch, int out0, int out1, cudaStream_t st, int* launches, void* scratch4 = nullptr,
+                 int mid_rows = -1) {
     if (out1 <= out0) return 0;
     (void)cudaGetLastError(); // (see run_row_pass)
     const avirb200_plan_desc& d = pl->desc;
@@ -436,6 +438,8 @@ int run_col_pass(const avirb200_plan* pl, const float* d_mid, int mid_row_base, 
             sp.src = d_mid;
             sp.src_pitch = (long long)d.dst_w * 4;
             sp.src_row_base = mid_row_base;
+            sp.src_lo = mid_row_base;
+            sp.src_hi = (mid_rows >= 0) ? mid_row_base + mid_rows : d.src_h;
             sp.dst = d_dst;
             sp.dst_pitch = (long long)dst_pitch;
             sp.dst_type = d.out_type;
@@ -1642,7 +1646,8 @@ int avirb200_resize_sharded(const avirb200_plan* cpl, void* comm, int rank, int 
     if (nranks <= 1) {
         r = run_row_pass(pl, d_src, src_pitch, own, si.src_rows, st, &launches, src4);
         if (r != 0) return r;
-        r = run_col_pass(pl, mid, si.need_row0, d_dst, dst_pitch, si.dst_row0, si.dst_row0 + si.dst_rows, st, &launches, dst4);
+        r = run_col_pass(pl, mid, si.need_row0, d_dst, dst_pitch, si.dst_row0, si.dst_row0 + si.dst_rows, st, &launches, dst4,
+                         si.need_rows);
         pl->last_launches = launches;
         return r;
     }
@@ -1716,7 +1721,8 @@ int avirb200_resize_sharded(const avirb200_plan* cpl, void* comm, int rank, int 
                 CUDA_TRY(cudaMemcpyAsync(own + (size_t)si.src_rows * rowf, sl + align256(h->up_bytes), h->down_bytes,
                                          cudaMemcpyDeviceToDevice, st));
         }
-        r = run_col_pass(pl, mid, si.need_row0, d_dst, dst_pitch, si.dst_row0, si.dst_row0 + si.dst_rows, st, &launches, dst4);
+        r = run_col_pass(pl, mid, si.need_row0, d_dst, dst_pitch, si.dst_row0, si.dst_row0 + si.dst_rows, st, &launches, dst4,
+                         si.need_rows);
         // the pushes read this call's workspace: the caller's stream does not end before them
         CUDA_TRY(cudaStreamWaitEvent(st, pl->ev_x1, 0));
         pl->last_launches = launches;
@@ -1737,7 +1743,8 @@ int avirb200_resize_sharded(const avirb200_plan* cpl, void* comm, int rank, int 
             NCCL_TRY(nc->Recv(own + (size_t)si.src_rows * rowf, (size_t)si.halo_down * rowf, 7, rank + 1, comm, st));
     }
     NCCL_TRY(nc->GroupEnd());
-    r = run_col_pass(pl, mid, si.need_row0, d_dst, dst_pitch, si.dst_row0, si.dst_row0 + si.dst_rows, st, &launches, dst4);
+    r = run_col_pass(pl, mid, si.need_row0, d_dst, dst_pitch, si.dst_row0, si.dst_row0 + si.dst_rows, st, &launches, dst4,
+                     si.need_rows);
     pl->last_launches = launches;
     return r;
 }
@@ -1820,7 +1827,7 @@ int avirb200_resize_sharded_local(const avirb200_plan* pl, int nranks, const voi
     for (int r = 0; r < nranks; ++r) {
         char* dst = static_cast<char*>(d_dst) + (size_t)si[r].dst_row0 * dst_pitch * out_el;
         int e = run_col_pass(pl, mid[r], si[r].need_row0, dst, dst_pitch, si[r].dst_row0,
-                             si[r].dst_row0 + si[r].dst_rows, st, &launches, dst4[r]);
+                             si[r].dst_row0 + si[r].dst_rows, st, &launches, dst4[r], si[r].need_rows);
         if (e != 0) return e;
     }
     pl->last_launches = launches;

@@ -271,9 +271,22 @@ AVS_FN void mbar_arrive(unsigned) {}
 AVS_FN void mbar_arrive_expect_tx(unsigned, unsigned) {}
 AVS_FN void mbar_arrive_cp_async(unsigned) {}
 AVS_FN void mbar_wait(unsigned, unsigned) {}
-AVS_FN void cp_async16(void* smem, const void* gmem) { memcpy(smem, gmem, 16); }
+// (every source read of the emulation is checked against the buffer the pass was given)
+extern thread_local const unsigned char* avs_emul_src_lo;
+extern thread_local const unsigned char* avs_emul_src_hi;
+void avs_emul_count_oob();
+AVS_FN void emul_copy(void* smem, const void* gmem, int n) {
+    const unsigned char* g = static_cast<const unsigned char*>(gmem);
+    if (avs_emul_src_lo != nullptr && (g < avs_emul_src_lo || g + n > avs_emul_src_hi)) {
+        avs_emul_count_oob();
+        memset(smem, 0xff, n);
+        return;
+    }
+    memcpy(smem, gmem, n);
+}
+AVS_FN void cp_async16(void* smem, const void* gmem) { emul_copy(smem, gmem, 16); }
 template <int N>
-AVS_FN void cp_async_px(void* smem, const void* gmem) { memcpy(smem, gmem, N); }
+AVS_FN void cp_async_px(void* smem, const void* gmem) { emul_copy(smem, gmem, N); }
 AVS_FN void cp_async_commit() {}
 template <int N>
 AVS_FN void cp_async_wait() {}
@@ -482,7 +495,7 @@ AVS_FN void load_group(const StreamParams& p, WarpRun<C, IS_V>& w, int g, int gs
     for (int q = 0; q < C::SRC_N / POSW; ++q) {
         const int pos0 = w.o0 + g * C::SRC_N + q * POSW; // first source position of the sweep
         unsigned char* ring = reinterpret_cast<unsigned char*>(w.ring0) + (size_t)(gslot + q * POSW) * PITCH_B;
-        const bool interior = STEADY || ((pos0 >= 0) && (pos0 + POSW <= p.src_len));
+        const bool interior = STEADY || ((pos0 >= p.src_lo) && (pos0 + POSW <= p.src_hi));
         if (IS_V) {
             // a position is an intermediate row; the warp's 16 pixel columns are 256 contiguous bytes
             const int piece = lane & 15, rsub = lane >> 4;
@@ -498,7 +511,7 @@ AVS_FN void load_group(const StreamParams& p, WarpRun<C, IS_V>& w, int g, int gs
                 const unsigned char* col = src + (size_t)(w.line0 + imin_(piece, w.nlines - 1)) * 16;
 #pragma unroll
                 for (int k = 0; k < NK; ++k) {
-                    const int y = imin_(imax_(pos0 + rsub + 2 * k, 0), p.src_len - 1) - p.src_row_base;
+                    const int y = imin_(imax_(pos0 + rsub + 2 * k, p.src_lo), p.src_hi - 1) - p.src_row_base;
                     cp_async16(d + 2 * k * PITCH_B, col + (ptrdiff_t)y * (ptrdiff_t)rowb);
                 }
             }
@@ -515,7 +528,7 @@ AVS_FN void load_group(const StreamParams& p, WarpRun<C, IS_V>& w, int g, int gs
 #pragma unroll
                 for (int k = 0; k < NK; ++k) cp_async_px<PIXB>(d + LSTEP * k * C::LINE_B, w.gp[k]);
             } else if (issue) {
-                const int x = imin_(imax_(pos0 + pos, 0), p.src_len - 1);
+                const int x = imin_(imax_(pos0 + pos, p.src_lo), p.src_hi - 1);
 #pragma unroll
                 for (int k = 0; k < NK; ++k) {
                     const int line = imin_(lsub + LSTEP * k, w.nlines - 1);
@@ -937,7 +950,7 @@ AVS_FN void bulk_group(const StreamParams& p, WarpRun<C, IS_V>& w, int row, int 
         const unsigned char* src = static_cast<const unsigned char*>(p.src);
         const size_t rowb = (size_t)p.src_pitch * 4;
         for (int k = 0; k < C::SRC_N; ++k)
-            memcpy(d + k * (kPitchL * 8), src + (size_t)(row + k) * rowb + (size_t)w.line0 * 16, (size_t)w.nlines * 16);
+            emul_copy(d + k * (kPitchL * 8), src + (size_t)(row + k) * rowb + (size_t)w.line0 * 16, w.nlines * 16);
     }
     (void)bar;
 #endif
@@ -1110,9 +1123,9 @@ AVS_FN void run_warp(const StreamParams& p, WarpRun<C, IS_V>& w, int strip, int 
     steady_bounds<C, IS_V, 1, S1>(p, w, C::delay1, C::reps1, slo, shi);
     if constexpr (C::NS == 3) steady_bounds<C, IS_V, 2, S2>(p, w, C::delay2, C::reps2, slo, shi);
     // the group a steady round issues (r + PRO) is interior -- or lies behind the run (not issued)
-    slo = imax_(slo, cdiv_(-w.o0, C::SRC_N) - PRO);
+    slo = imax_(slo, cdiv_(p.src_lo - w.o0, C::SRC_N) - PRO);
     {
-        const int g_int_hi = fdiv_(p.src_len - w.o0, C::SRC_N) - 1; // last group without clamping
+        const int g_int_hi = fdiv_(p.src_hi - w.o0, C::SRC_N) - 1; // last group without clamping
         if (groups - 1 > g_int_hi) shi = imin_(shi, g_int_hi - PRO);
     }
 

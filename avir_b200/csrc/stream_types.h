@@ -45,6 +45,11 @@ struct StreamParams {
     float in_gamma_mult;   // kSrcU8Srgb: multiplier of the alpha channel
     long long src_pitch;  // elements between rows
     int src_row_base;     // column pass: global row held by source row 0 (shards)
+    // Source positions the buffer actually holds, [src_lo, src_hi) (the whole line, or a shard's
+    // band of intermediate rows).  A run starts and ends on round boundaries, so its first / last
+    // round may compute outputs outside [out0, out1) (never stored) whose windows reach past the
+    // band: reads clamp to this range, not just to the line.
+    int src_lo, src_hi;
     void* dst;
     long long dst_pitch;
     int dst_type, dst_row_base;
@@ -229,6 +234,8 @@ inline void stream_fill_params(StreamParams& p, const StreamAxisPlan& ap, const 
     memset(&p, 0, sizeof p);
     for (int i = 0; i < ap.nsteps; ++i) p.s[i] = ap.s[i];
     p.src_len = ap.src_len;
+    p.src_lo = 0;
+    p.src_hi = ap.src_len;
     p.src_type = AVIRB200_F32;
     p.in_gamma_mult = d.in_gamma_mult;
     p.gamma_out = (d.use_gamma & 2) ? 1 : 0;

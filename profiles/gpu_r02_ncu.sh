@@ -10,6 +10,7 @@ for a in "$@"; do
   case $a in keep=*) keep=1; a=${a#keep=};; esac
   case $a in
     cfg=*) cfg=${a#cfg=}; vh=-1; vv=-1; name=${tag}_${cfg};;
+    default) cfg=cfg3; vh=-1; vv=-1; name=${tag}_cfg3_default;;
     *) cfg=cfg3; vh=${a%%:*}; vv=${a##*:}; name=${tag}_cfg3_v${vh}_${vv};;
   esac
   # --only col: the script runs the row pass once (the column pass's input), then column passes

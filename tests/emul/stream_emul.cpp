@@ -17,8 +17,18 @@
 #include <thread>
 #include <vector>
 
+#include <atomic>
+
 static thread_local pthread_barrier_t* g_bar = nullptr;
 void avs_emul_syncwarp() { pthread_barrier_wait(g_bar); }
+static std::atomic<long> g_oob(0);
+namespace avs {
+thread_local const unsigned char* avs_emul_src_lo = nullptr;
+thread_local const unsigned char* avs_emul_src_hi = nullptr;
+void avs_emul_count_oob() { ++g_oob; }
+} // namespace avs
+static const unsigned char* g_lo = nullptr; // bounds of the pass's source buffer (copied into every lane thread)
+static const unsigned char* g_hi = nullptr;
 
 #include "stream_kernel.cuh"
 
@@ -39,6 +49,8 @@ void emul_pass(const StreamParams& p, int nwarps) {
         for (int lane = 0; lane < 32; ++lane) {
             th.emplace_back([&, lane] {
                 g_bar = &bar;
+                avs_emul_src_lo = g_lo;
+                avs_emul_src_hi = g_hi;
                 stream_warp_main<C, IS_V, EPI>(p, gw, nwarps, lane, sm.data(), p.srgb_lut);
             });
         }
@@ -79,8 +91,12 @@ int stream_emul_applicable(const avirb200_plan_desc* d) {
 // lut: the 256-entry u8 sRGB linearisation table (read for sRGB sources only).
 // allow: 1 = every chain (as AVIRB200_OPT_ALL_STREAM_CHAINS = 1), 2 = the 4-output-batch twin of the
 // headline chain where it applies.
+// need: per band (need_row0, need_rows) of avirb200_shard_query_desc, or null.  With it every band's
+// column pass gets a buffer holding exactly those intermediate rows, as a rank of the sharded
+// schedule does, and every source read is bounds-checked: returns -5 if any read left its buffer.
 int stream_emul_resize(const avirb200_plan_desc* d, const void* src, size_t src_pitch, void* dst,
-                       size_t dst_pitch, int warps_h, int warps_v, int bands, int variant, const float* lut, int allow) {
+                       size_t dst_pitch, int warps_h, int warps_v, int bands, int variant, const float* lut, int allow,
+                       const int* need) {
     StreamAxisPlan h, v;
     if (!stream_row_source_ok(*d) || !stream_plan_axis(d->h, d->sum_mode, d->channels, h, allow) ||
         !stream_plan_axis(d->v, d->sum_mode, d->channels, v, allow))
@@ -98,6 +114,12 @@ int stream_emul_resize(const avirb200_plan_desc* d, const void* src, size_t src_
     p.dst = mid.data();
     p.dst_pitch = (long long)d->dst_w * 4;
     p.dst_type = AVIRB200_F32;
+    g_oob = 0;
+    {
+        const size_t esz = (d->in_type == AVIRB200_U8) ? 1 : (d->in_type == AVIRB200_U16 ? 2 : 4);
+        g_lo = static_cast<const unsigned char*>(src);
+        g_hi = g_lo + ((size_t)(d->src_h - 1) * src_pitch + (size_t)d->src_w * 4) * esz;
+    }
     if (!emul_dispatch<false>(h.chain, variant, p, warps_h, 0)) return -4;
 
     const int epi = stream_epilogue_code(*d);
@@ -110,13 +132,28 @@ int stream_emul_resize(const avirb200_plan_desc* d, const void* src, size_t src_
         p.src = mid.data();
         p.src_pitch = (long long)d->dst_w * 4;
         p.src_row_base = 0;
+        g_lo = reinterpret_cast<const unsigned char*>(mid.data());
+        g_hi = g_lo + mid.size() * sizeof(float);
+        std::vector<float> bandbuf;
+        if (need != nullptr) { // the band's own rows only, as on a rank of the sharded schedule
+            const int r0 = need[2 * b], nr = need[2 * b + 1];
+            const size_t rowf = (size_t)d->dst_w * 4;
+            bandbuf.assign(mid.begin() + (size_t)r0 * rowf, mid.begin() + (size_t)(r0 + nr) * rowf);
+            p.src = bandbuf.data();
+            p.src_row_base = r0;
+            p.src_lo = r0;
+            p.src_hi = r0 + nr;
+            g_lo = reinterpret_cast<const unsigned char*>(bandbuf.data());
+            g_hi = g_lo + bandbuf.size() * sizeof(float);
+        }
         p.dst = dst;
         p.dst_pitch = (long long)dst_pitch;
         p.dst_type = d->out_type;
         p.dst_row_base = 0;
         if (!emul_dispatch<true>(v.chain, variant, p, warps_v, epi)) return -4;
     }
-    return 0;
+    g_lo = g_hi = nullptr;
+    return g_oob.load() ? -5 : 0;
 }
 
 int stream_emul_variants(void) { return kStreamVariants; }

@@ -64,7 +64,8 @@ def main():
         if debug:
             torch.cuda.synchronize()
             print("[rank %d]" % rank, *a, flush=True)
-    for case in CASES:
+    ncases = int(os.environ.get("AVIR_NCCL_CASES", "0")) or len(CASES)
+    for case in CASES[:ncases]:
         for overlap in overlaps:
             fp, sw, sh, nw, nh, ch, ti, to, rb, kw = case
             src = cs.make_input(case, seed=77)  # same image on every rank

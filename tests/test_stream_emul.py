@@ -17,12 +17,30 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 u8, u16, f32 = np.uint8, np.uint16, np.float32
 
 
+class _SI(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("src_row0", "src_rows", "dst_row0", "dst_rows",
+                                          "need_row0", "need_rows", "halo_up", "halo_down")]
+
+
+def band_needs(dp, bands):
+    """(need_row0, need_rows) of every band of the sharded schedule, or None where the product
+    refuses the split (bands too small): the emulation then runs over the whole intermediate."""
+    import avir_b200 as ab
+    out = (C.c_int * (2 * bands))()
+    for b in range(bands):
+        si = _SI()
+        if ab.lib().avirb200_shard_query_desc(C.c_void_p(dp), b, bands, C.byref(si)) != 0:
+            return None
+        out[2 * b], out[2 * b + 1] = si.need_row0, si.need_rows
+    return out
+
+
 @pytest.fixture(scope="module")
 def emul():
     from avir_b200 import build as b
     lib = C.CDLL(b.build_emul())
     lib.stream_emul_resize.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t,
-                                       C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
+                                       C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
     lib.stream_emul_resize.restype = C.c_int
     lib.stream_emul_applicable.argtypes = [C.c_void_p]
     lib.stream_emul_applicable.restype = C.c_int
@@ -101,7 +119,7 @@ def test_stream_kernel_emulation_matches_port(emul, ec, variant):
         lut = np.zeros(256, np.float32)
         cs.port().avir_port_srgb_lut(lut.ctypes.data)
         assert emul.stream_emul_resize(dp, src.ctypes.data, sw * ch, got.ctypes.data, nw * ch, wh, wv, bands,
-                                       variant, lut.ctypes.data, 1) == 0
+                                       variant, lut.ctypes.data, 1, band_needs(dp, bands)) == 0
     finally:
         rs.free_descriptor(h)
     want, _ = cs.port_output(case, src)
@@ -126,7 +144,7 @@ def test_stream_kernel_emulation_q_chain_matches_port(emul, ec, variant):
         got = np.zeros((nh, nw, ch), to)
         lut = np.zeros(256, np.float32)
         assert emul.stream_emul_resize(dp, src.ctypes.data, sw * ch, got.ctypes.data, nw * ch, wh, wv, bands,
-                                       variant, lut.ctypes.data, 2) == 0
+                                       variant, lut.ctypes.data, 2, band_needs(dp, bands)) == 0
     finally:
         rs.free_descriptor(h)
     want, _ = cs.port_output(case, src)
@@ -228,7 +246,7 @@ def test_stream_kernel_emulation_fuzz(emul):
             wh, wv = int(rng.integers(1, 9)), int(rng.integers(1, 9))
             bands, var = int(rng.integers(1, 5)), int(rng.integers(0, 4))
             assert emul.stream_emul_resize(dp, src.ctypes.data, sw * 4, got.ctypes.data, nw * 4, wh, wv, bands,
-                                           var, lut.ctypes.data, 1 + (it & 1)) == 0
+                                           var, lut.ctypes.data, 1 + (it & 1), band_needs(dp, bands)) == 0
         finally:
             rs.free_descriptor(h)
         want, _ = cs.port_output(case, src)
