@@ -328,6 +328,10 @@ int launch_narrow(int type, const void* src, void* dst, size_t dst_pitch, int w,
 
 // 1..3-channel plans whose passes run on the 4-channel kernels in this call (avirb200_plan::pad4)
 bool use_pad4(const avirb200_plan* pl) { return pl->pad4 && pl->opt_family != 1; }
+bool row_pass_can_segment(const avirb200_plan* pl, const void* d_src, size_t src_pitch, const float* d_mid) {
+    return pl->opt_family == 0 && pl->stream_h.chain != 0 && !use_pad4(pl) &&
+           ((uintptr_t)d_src % (4 * dtype_size(pl->desc.in_type))) == 0 && (src_pitch % 4) == 0 && ((uintptr_t)d_mid % 16) == 0;
+}
 size_t pad4_src_bytes(const avirb200_plan* pl, int rows) {
     return pl->pad4 ? ((size_t)rows * pl->desc.src_w * 4 * dtype_size(pl->desc.in_type) + 255) / 256 * 256 : 0;
 }
@@ -339,8 +343,11 @@ size_t pad4_dst_bytes(const avirb200_plan* pl, int rows) {
 // starting at d_mid; column pass producing dst rows [out0, out1) from an intermediate
 // buffer whose row 0 is global row mid_row_base.
 // scratch4: where the band's widened (4-channel) copy goes when use_pad4(pl).
+// seg_top / seg_bot (streaming kernel, 4-channel plans only -- the caller checks row_pass_can_segment()):
+// filter only the band's first seg_top and last seg_bot rows, in ONE launch.
+bool row_pass_can_segment(const avirb200_plan* pl, const void* d_src, size_t src_pitch, const float* d_mid);
 int run_row_pass(const avirb200_plan* pl, const void* d_src, size_t src_pitch, float* d_mid,
-                 int rows, cudaStream_t st, int* launches, void* scratch4 = nullptr) {
+                 int rows, cudaStream_t st, int* launches, void* scratch4 = nullptr, int seg_top = 0, int seg_bot = 0) {
     if (rows <= 0) return 0;
     // (a non-sticky error another library left in this thread -- NCCL's peer-access probing leaves
     // cudaErrorPeerAccessAlreadyEnabled once the IPC mailboxes have enabled it -- is not this launch's)
@@ -364,6 +371,13 @@ int run_row_pass(const avirb200_plan* pl, const void* d_src, size_t src_pitch, f
         sp.src_type = avs::stream_row_source_code(d);
         sp.srgb_lut = pl->d_lut;
         sp.n_lines = rows;
+        if (seg_bot > 0) {
+            sp.seg_a = seg_top;
+            sp.seg_b = seg_bot;
+            sp.seg_b_line0 = rows - seg_bot;
+        } else if (seg_top > 0) {
+            sp.n_lines = seg_top;
+        }
         sp.out0 = 0;
         sp.out1 = d.dst_w;
         sp.src = d_src;
@@ -945,16 +959,26 @@ struct Halo {
 
 size_t align256(size_t v) { return (v + 255) / 256 * 256; }
 
-__global__ void halo_wait_kernel(const volatile unsigned* flags, unsigned seq, int need_up, int need_down) {
-    const int t = threadIdx.x;
-    if ((t == 0 && need_up) || (t == 1 && need_down)) {
-        long long spins = 0;
-        while ((int)(flags[t] - seq) < 0) {
-            if (++spins > (1ll << 31)) __trap(); // a neighbour never delivered: fail instead of hanging
-            __nanosleep(200);
+// Waits for the neighbours' sequence numbers, then moves their rows from the mailbox into the
+// workspace (both directions, one launch).
+__global__ void __launch_bounds__(256) halo_pull_kernel(const volatile unsigned* flags, unsigned seq, int need_up,
+                                                        int need_down, const float4* up_src, float4* up_dst, size_t up_n,
+                                                        const float4* down_src, float4* down_dst, size_t down_n) {
+    if (threadIdx.x < 2) {
+        const int t = threadIdx.x;
+        if ((t == 0 && need_up) || (t == 1 && need_down)) {
+            long long spins = 0;
+            while ((int)(flags[t] - seq) < 0) {
+                if (++spins > (1ll << 31)) __trap(); // a neighbour never delivered: fail instead of hanging
+                __nanosleep(100);
+            }
+            __threadfence_system();
         }
-        __threadfence_system();
     }
+    __syncthreads();
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < up_n; i += stride) up_dst[i] = __ldcv(up_src + i);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < down_n; i += stride) down_dst[i] = __ldcv(down_src + i);
 }
 
 void halo_free(Halo* h) {
@@ -1684,9 +1708,14 @@ int avirb200_resize_sharded(const avirb200_plan* cpl, void* comm, int rank, int 
             return run_row_pass(pl, srcb + (size_t)row0 * src_pitch * in_el, src_pitch, own + (size_t)row0 * rowf,
                                 nrows, st, &launches, src4 + (size_t)row0 * src4_row);
         };
-        // 1. the rows the neighbours need, 2. their push on the exchange stream, 3. the interior rows
+        // 1. the rows the neighbours need (one launch on the streaming kernel: two line segments),
+        // 2. their push on the exchange stream, 3. the interior rows
         const bool split = top_rows + bot_rows < si.src_rows;
-        if (split) {
+        if (split && row_pass_can_segment(pl, d_src, src_pitch, own)) {
+            if (top_rows + bot_rows > 0 &&
+                (r = run_row_pass(pl, d_src, src_pitch, own, si.src_rows, st, &launches, nullptr, top_rows, bot_rows)) != 0)
+                return r;
+        } else if (split) {
             if ((r = rows_pass(0, top_rows)) != 0) return r;
             if ((r = rows_pass(si.src_rows - bot_rows, bot_rows)) != 0) return r;
         } else if ((r = rows_pass(0, si.src_rows)) != 0) {
@@ -1712,14 +1741,15 @@ int avirb200_resize_sharded(const avirb200_plan* cpl, void* comm, int rank, int 
         const int need_down = (rank + 1 < nranks && si.halo_down > 0) ? 1 : 0;
         if (need_up || need_down) {
             (void)cudaGetLastError();
-            halo_wait_kernel<<<1, 32, 0, st>>>(reinterpret_cast<const volatile unsigned*>(h->box), seq, need_up, need_down);
+            const char* sl = h->box + 256 + (size_t)slot * h->slot_bytes;
+            halo_pull_kernel<<<64, 256, 0, st>>>(reinterpret_cast<const volatile unsigned*>(h->box), seq, need_up, need_down,
+                                                 reinterpret_cast<const float4*>(sl), reinterpret_cast<float4*>(mid),
+                                                 need_up ? h->up_bytes / 16 : 0,
+                                                 reinterpret_cast<const float4*>(sl + align256(h->up_bytes)),
+                                                 reinterpret_cast<float4*>(own + (size_t)si.src_rows * rowf),
+                                                 need_down ? h->down_bytes / 16 : 0);
             ++launches;
             CUDA_TRY(cudaGetLastError());
-            const char* sl = h->box + 256 + (size_t)slot * h->slot_bytes;
-            if (need_up) CUDA_TRY(cudaMemcpyAsync(mid, sl, h->up_bytes, cudaMemcpyDeviceToDevice, st));
-            if (need_down)
-                CUDA_TRY(cudaMemcpyAsync(own + (size_t)si.src_rows * rowf, sl + align256(h->up_bytes), h->down_bytes,
-                                         cudaMemcpyDeviceToDevice, st));
         }
         r = run_col_pass(pl, mid, si.need_row0, d_dst, dst_pitch, si.dst_row0, si.dst_row0 + si.dst_rows, st, &launches, dst4,
                          si.need_rows);

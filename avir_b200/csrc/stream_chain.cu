@@ -62,7 +62,7 @@ int launch_one(const StreamParams& p_in, int sm_count, cudaStream_t st) {
         return -1;
     // one persistent block per SM; fewer when the pass has fewer rounds than warps
     const long long rps = (long long)(p.out1 - 1) / C::B - p.out0 / C::B + 1;
-    const long long units = rps * ((p.n_lines + kLines - 1) / kLines);
+    const long long units = rps * stream_strip_count(p);
     long long blocks = (units + NW - 1) / NW;
     if (blocks > sm_count) blocks = sm_count;
     if (blocks < 1) return 0;

@@ -1074,6 +1074,15 @@ AVS_FN void run_warp(const StreamParams& p, WarpRun<C, IS_V>& w, int strip, int 
     using S2 = typename C::T2;
     w.line0 = strip * kLines;
     w.nlines = imin_(kLines, p.n_lines - w.line0);
+    if (p.seg_b > 0) { // two segments, each with its own strips (stream_types.h)
+        const int sa = (p.seg_a + kLines - 1) / kLines;
+        if (strip < sa) {
+            w.nlines = imin_(kLines, p.seg_a - w.line0);
+        } else {
+            w.line0 = p.seg_b_line0 + (strip - sa) * kLines;
+            w.nlines = imin_(kLines, p.seg_b_line0 + p.seg_b - w.line0);
+        }
+    }
     if (C::NS == 3) {
         w.a[2] = C::B * rho0;
         w.a[1] = in_first<S2>(p.s[2], w.a[2]);
@@ -1222,7 +1231,7 @@ AVS_FN void stream_warp_main(const StreamParams& p, long long gw, long long nwar
     }
     const int rho_first = p.out0 / C::B, rho_last = (p.out1 - 1) / C::B;
     const int rps = rho_last - rho_first + 1;
-    const int nstrips = (p.n_lines + kLines - 1) / kLines;
+    const int nstrips = stream_strip_count(p);
     const long long units = (long long)nstrips * rps;
     long long u0 = gw * units / nwarps;
     const long long u1 = (gw + 1) * units / nwarps;

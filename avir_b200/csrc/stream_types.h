@@ -37,6 +37,10 @@ struct StreamStep {
 struct StreamParams {
     StreamStep s[kMaxSteps];
     int n_lines;          // rows (row pass) or pixel columns (column pass)
+    // Two line segments in one launch (the rows a sharded call's neighbours need: the band's first
+    // seg_a lines and its last seg_b lines, each cut into its own 16-line strips): seg_b > 0 turns it on;
+    // the lines are 0 .. seg_a - 1 and seg_b_line0 .. seg_b_line0 + seg_b - 1 of the buffers.
+    int seg_a, seg_b, seg_b_line0;
     int src_len;          // positions of the source line
     int out0, out1;       // final outputs [out0, out1) to produce
     const void* src;      // 4 interleaved channels; fp32, or (row pass) the caller's u8 / u16 pixels
@@ -220,6 +224,14 @@ inline bool stream_row_source_ok(const avirb200_plan_desc& d) {
 // destination without output gamma (store as is), 2 = integer destination without output gamma
 // and without bit-depth truncation (round, clamp, narrow; branch-free), 0 = everything (sRGB de-linearisation in double included -- its code
 // is large enough to slow the whole kernel down, hence the split).
+// 16-line strips of a launch (a segmented launch cuts each segment into strips of its own).
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+inline int stream_strip_count(const StreamParams& p) {
+    if (p.seg_b > 0) return (p.seg_a + 15) / 16 + (p.seg_b + 15) / 16;
+    return (p.n_lines + 15) / 16;
+}
 inline int stream_epilogue_code(const avirb200_plan_desc& d) {
     if (d.use_gamma & 2) return 0;
     if (d.out_type == AVIRB200_F32) return 1;

@@ -96,7 +96,7 @@ int stream_emul_applicable(const avirb200_plan_desc* d) {
 // schedule does, and every source read is bounds-checked: returns -5 if any read left its buffer.
 int stream_emul_resize(const avirb200_plan_desc* d, const void* src, size_t src_pitch, void* dst,
                        size_t dst_pitch, int warps_h, int warps_v, int bands, int variant, const float* lut, int allow,
-                       const int* need) {
+                       const int* need, int seg_top, int seg_bot) {
     StreamAxisPlan h, v;
     if (!stream_row_source_ok(*d) || !stream_plan_axis(d->h, d->sum_mode, d->channels, h, allow) ||
         !stream_plan_axis(d->v, d->sum_mode, d->channels, v, allow))
@@ -120,7 +120,20 @@ int stream_emul_resize(const avirb200_plan_desc* d, const void* src, size_t src_
         g_lo = static_cast<const unsigned char*>(src);
         g_hi = g_lo + ((size_t)(d->src_h - 1) * src_pitch + (size_t)d->src_w * 4) * esz;
     }
-    if (!emul_dispatch<false>(h.chain, variant, p, warps_h, 0)) return -4;
+    if (seg_top + seg_bot > 0 && seg_top + seg_bot < d->src_h) {
+        // as a sharded call schedules the row pass: the first seg_top and last seg_bot rows in one
+        // segmented launch, then the rows between
+        StreamParams q = p;
+        if (seg_bot > 0) { q.seg_a = seg_top; q.seg_b = seg_bot; q.seg_b_line0 = d->src_h - seg_bot; }
+        else q.n_lines = seg_top;
+        if (!emul_dispatch<false>(h.chain, variant, q, warps_h, 0)) return -4;
+        const size_t esz = (d->in_type == AVIRB200_U8) ? 1 : (d->in_type == AVIRB200_U16 ? 2 : 4);
+        q = p;
+        q.n_lines = d->src_h - seg_top - seg_bot;
+        q.src = static_cast<const unsigned char*>(src) + (size_t)seg_top * src_pitch * esz;
+        q.dst = mid.data() + (size_t)seg_top * d->dst_w * 4;
+        if (!emul_dispatch<false>(h.chain, variant, q, warps_h, 0)) return -4;
+    } else if (!emul_dispatch<false>(h.chain, variant, p, warps_h, 0)) return -4;
 
     const int epi = stream_epilogue_code(*d);
     for (int b = 0; b < bands; ++b) {

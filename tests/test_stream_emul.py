@@ -40,7 +40,7 @@ def emul():
     from avir_b200 import build as b
     lib = C.CDLL(b.build_emul())
     lib.stream_emul_resize.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t,
-                                       C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+                                       C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int]
     lib.stream_emul_resize.restype = C.c_int
     lib.stream_emul_applicable.argtypes = [C.c_void_p]
     lib.stream_emul_applicable.restype = C.c_int
@@ -119,7 +119,7 @@ def test_stream_kernel_emulation_matches_port(emul, ec, variant):
         lut = np.zeros(256, np.float32)
         cs.port().avir_port_srgb_lut(lut.ctypes.data)
         assert emul.stream_emul_resize(dp, src.ctypes.data, sw * ch, got.ctypes.data, nw * ch, wh, wv, bands,
-                                       variant, lut.ctypes.data, 1, band_needs(dp, bands)) == 0
+                                       variant, lut.ctypes.data, 1, band_needs(dp, bands), (3 * variant + wh) % 23, (5 * variant + wv) % 19) == 0
     finally:
         rs.free_descriptor(h)
     want, _ = cs.port_output(case, src)
@@ -144,7 +144,7 @@ def test_stream_kernel_emulation_q_chain_matches_port(emul, ec, variant):
         got = np.zeros((nh, nw, ch), to)
         lut = np.zeros(256, np.float32)
         assert emul.stream_emul_resize(dp, src.ctypes.data, sw * ch, got.ctypes.data, nw * ch, wh, wv, bands,
-                                       variant, lut.ctypes.data, 2, band_needs(dp, bands)) == 0
+                                       variant, lut.ctypes.data, 2, band_needs(dp, bands), wh % 7, 17 * (variant & 1)) == 0
     finally:
         rs.free_descriptor(h)
     want, _ = cs.port_output(case, src)
@@ -246,7 +246,7 @@ def test_stream_kernel_emulation_fuzz(emul):
             wh, wv = int(rng.integers(1, 9)), int(rng.integers(1, 9))
             bands, var = int(rng.integers(1, 5)), int(rng.integers(0, 4))
             assert emul.stream_emul_resize(dp, src.ctypes.data, sw * 4, got.ctypes.data, nw * 4, wh, wv, bands,
-                                           var, lut.ctypes.data, 1 + (it & 1), band_needs(dp, bands)) == 0
+                                           var, lut.ctypes.data, 1 + (it & 1), band_needs(dp, bands), int(rng.integers(0, 20)), int(rng.integers(0, 20))) == 0
         finally:
             rs.free_descriptor(h)
         want, _ = cs.port_output(case, src)
