@@ -1117,7 +1117,7 @@ int avirb200_plan_set_option(avirb200_plan* pl, int option, int value) {
     case AVIRB200_OPT_STREAM_VARIANT_H: pl->opt_var_h = (value >= 0 && value < 3) ? value : -1; return 0;
     case AVIRB200_OPT_STREAM_VARIANT_V: pl->opt_var_v = (value >= 0 && value < 3) ? value : -1; return 0;
     case AVIRB200_OPT_HOST_BANDS: pl->opt_host_bands = value >= 1 ? value : -1; return 0;
-    case AVIRB200_OPT_OVERLAP_HALO: pl->opt_overlap = (value == 0) ? 0 : 1; return 0;
+    case AVIRB200_OPT_OVERLAP_HALO: pl->opt_overlap = (value == 0) ? 0 : (value == 2 ? 2 : 1); return 0;
     case AVIRB200_OPT_ALL_STREAM_CHAINS: {
         const int on = value > 0 ? (value == 2 ? 2 : 1) : 0;
         if (on != pl->opt_all_chains) { // re-decide which passes run on the streaming kernel (host arithmetic only)
@@ -1710,7 +1710,10 @@ int avirb200_resize_sharded(const avirb200_plan* cpl, void* comm, int rank, int 
         };
         // 1. the rows the neighbours need (one launch on the streaming kernel: two line segments),
         // 2. their push on the exchange stream, 3. the interior rows
-        const bool split = top_rows + bot_rows < si.src_rows;
+        // (boundary rows first only on request, AVIRB200_OPT_OVERLAP_HALO = 2: the copy-engine push
+        // takes ~4 us for cfg3's 1.2 MB, less than the extra launch costs; measured on 2 x B200,
+        // profiles/r02d_*: 0.2573 / 0.2607 ms with the split vs the single row launch)
+        const bool split = pl->opt_overlap == 2 && top_rows + bot_rows < si.src_rows;
         if (split && row_pass_can_segment(pl, d_src, src_pitch, own)) {
             if (top_rows + bot_rows > 0 &&
                 (r = run_row_pass(pl, d_src, src_pitch, own, si.src_rows, st, &launches, nullptr, top_rows, bot_rows)) != 0)

@@ -181,9 +181,10 @@ typedef enum avirb200_option {
     AVIRB200_OPT_HOST_BANDS = 3,
     /* 1: also select the streaming chains that measured slower than the tile kernel (upsizing, 56-tap) */
     AVIRB200_OPT_ALL_STREAM_CHAINS = 4,
-    /* avirb200_resize_sharded: 1 (default) = boundary rows first, halo rows pushed into the
-     * neighbours' mailboxes over NVLink while the interior rows are filtered; 0 = NCCL send/recv
-     * between the two passes */
+    /* avirb200_resize_sharded: 1 (default) = halo rows pushed by the copy engines into the neighbours'
+     * mailboxes over NVLink after the row pass; 2 = the same with the rows the neighbours need
+     * filtered FIRST (one segmented launch) so that the push overlaps the interior rows; 0 = NCCL
+     * send/recv between the two passes */
     AVIRB200_OPT_OVERLAP_HALO = 5
 } avirb200_option;
 int avirb200_plan_set_option(avirb200_plan* plan, int option, int value);
@@ -217,10 +218,10 @@ void avirb200_comm_destroy(void* comm);
  * (dst_rows rows).  Row pass -> NCCL halo send/recv with rank-1/rank+1 -> column pass, all
  * enqueued on `stream`.  `comm` is an ncclComm_t (from avirb200_comm_create or the
  * caller's own).  Output is bit-identical to the single-GPU path.
- * Default schedule (AVIRB200_OPT_OVERLAP_HALO): the rows the neighbours need are filtered first
- * and pushed (copy engine, NVLink peer memory mapped through CUDA IPC; the handles travel over
- * `comm` once per plan) into the neighbours' mailboxes while the interior rows are filtered; the
- * column pass waits for the neighbours' flags.  The first call on a plan is collective (every
+ * Default schedule (AVIRB200_OPT_OVERLAP_HALO): after the row pass the rows the neighbours need are
+ * pushed (copy engines, NVLink peer memory mapped through CUDA IPC; the handles travel over `comm`
+ * once per plan) into the neighbours' mailboxes, followed by a sequence number; one small kernel
+ * waits for the neighbours' numbers and moves their rows into the workspace; then the column pass.  The first call on a plan is collective (every
  * rank must make it).  Where peer mapping is unavailable the NCCL send/recv schedule runs. */
 int avirb200_resize_sharded(const avirb200_plan* plan, void* comm, int rank, int nranks,
                             const void* d_src, size_t src_pitch, void* d_dst, size_t dst_pitch,
