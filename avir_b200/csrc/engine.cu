@@ -346,8 +346,11 @@ size_t pad4_dst_bytes(const avirb200_plan* pl, int rows) {
 // seg_top / seg_bot (streaming kernel, 4-channel plans only -- the caller checks row_pass_can_segment()):
 // filter only the band's first seg_top and last seg_bot rows, in ONE launch.
 bool row_pass_can_segment(const avirb200_plan* pl, const void* d_src, size_t src_pitch, const float* d_mid);
+// xs (sharded calls, fused halo exchange): the StreamParams xs_* fields of this launch; *xs_done tells
+// whether the streaming kernel took the pass (and so delivered the neighbours' rows).
 int run_row_pass(const avirb200_plan* pl, const void* d_src, size_t src_pitch, float* d_mid,
-                 int rows, cudaStream_t st, int* launches, void* scratch4 = nullptr, int seg_top = 0, int seg_bot = 0) {
+                 int rows, cudaStream_t st, int* launches, void* scratch4 = nullptr, int seg_top = 0, int seg_bot = 0,
+                 const avs::StreamParams* xs = nullptr, bool* xs_done = nullptr) {
     if (rows <= 0) return 0;
     // (a non-sticky error another library left in this thread -- NCCL's peer-access probing leaves
     // cudaErrorPeerAccessAlreadyEnabled once the IPC mailboxes have enabled it -- is not this launch's)
@@ -385,9 +388,15 @@ int run_row_pass(const avirb200_plan* pl, const void* d_src, size_t src_pitch, f
         sp.dst = d_mid;
         sp.dst_pitch = (long long)d.dst_w * 4;
         sp.dst_type = AVIRB200_F32;
+        if (xs != nullptr) {
+            sp.xs_up_dst = xs->xs_up_dst; sp.xs_dn_dst = xs->xs_dn_dst;
+            sp.xs_up_flag = xs->xs_up_flag; sp.xs_dn_flag = xs->xs_dn_flag;
+            sp.xs_count = xs->xs_count; sp.xs_units[0] = xs->xs_units[0]; sp.xs_units[1] = xs->xs_units[1];
+            sp.xs_seq = xs->xs_seq; sp.xs_top = xs->xs_top; sp.xs_bot0 = xs->xs_bot0; sp.xs_bot = xs->xs_bot;
+        }
         const int r = avs::stream_launch(pl->stream_h.chain, false, 0, pl->opt_var_h, sp, pl->sm_count, st);
         if (r == -1) return fail(AVIRB200_ERR_CUDA, "streaming row pass launch failed");
-        if (r == 0) { ++*launches; return 0; }
+        if (r == 0) { ++*launches; if (xs_done) *xs_done = (xs != nullptr); return 0; }
     }
     if (pl->opt_family != 1 && pl->fast.h_ok) {
         const int r = fast_row_pass(pl->fast, d, d_src, src_pitch, d_mid, rows, pl->d_lut, st);
@@ -419,9 +428,12 @@ int run_row_pass(const avirb200_plan* pl, const void* d_src, size_t src_pitch, f
 
 // scratch4: where the band's 4-channel destination rows go when use_pad4(pl) (then narrowed into d_dst).
 // mid_rows: intermediate rows the buffer holds from mid_row_base on (< 0: up to the image's last row).
+// xr (sharded calls, fused halo exchange): the StreamParams xr_* fields -- the neighbours' rows are read in
+// place from the mailbox.  Returns 1, nothing launched, when the streaming kernel cannot take the pass
+// (the caller moves the rows into the workspace and calls again without xr).
 int run_col_pass(const avirb200_plan* pl, const float* d_mid, int mid_row_base, void* d_dst,
                  size_t dst_pitch, int out0, int out1, cudaStream_t st, int* launches, void* scratch4 = nullptr,
-                 int mid_rows = -1) {
+                 int mid_rows = -1, const avs::StreamParams* xr = nullptr) {
     if (out1 <= out0) return 0;
     (void)cudaGetLastError(); // (see run_row_pass)
     const avirb200_plan_desc& d = pl->desc;
@@ -458,11 +470,16 @@ int run_col_pass(const avirb200_plan* pl, const float* d_mid, int mid_row_base, 
             sp.dst_pitch = (long long)dst_pitch;
             sp.dst_type = d.out_type;
             sp.dst_row_base = out0;
+            if (xr != nullptr) {
+                sp.xr_up_src = xr->xr_up_src; sp.xr_dn_src = xr->xr_dn_src; sp.xr_flags = xr->xr_flags;
+                sp.xr_seq = xr->xr_seq; sp.xr_own_lo = xr->xr_own_lo; sp.xr_own_hi = xr->xr_own_hi;
+            }
             const int r = avs::stream_launch(pl->stream_v.chain, true, avs::stream_epilogue_code(d), pl->opt_var_v, sp,
                                              pl->sm_count, st);
             if (r == -1) return fail(AVIRB200_ERR_CUDA, "streaming column pass launch failed");
             if (r == 0) { ++*launches; return finish(); }
         }
+        if (xr != nullptr) return 1;
     }
     if (pl->opt_family != 1 && pl->fast.v_ok) {
         const int r = fast_col_pass(pl->fast, d, d_mid, mid_row_base, d_dst, dst_pitch, out0, out1,
@@ -1102,6 +1119,28 @@ int halo_setup(avirb200_plan* pl, void* comm, int rank, int nranks, cudaStream_t
     return 0;
 }
 
+// Sharded calls: after the row pass (stream st) the first top_rows / last bot_rows rows of the band go to the
+// neighbours' mailboxes on the exchange stream (copy engines), each followed by the call's sequence number.
+int sharded_push(avirb200_plan* pl, Halo* h, cudaStream_t st, const float* own, size_t rowf, int top_rows, int bot_rows,
+                 int src_rows, char* up_dst, char* down_dst, const unsigned* hs) {
+    if (pl->stream_x == nullptr) CUDA_TRY(cudaStreamCreateWithFlags(&pl->stream_x, cudaStreamNonBlocking));
+    if (pl->ev_x0 == nullptr) CUDA_TRY(cudaEventCreateWithFlags(&pl->ev_x0, cudaEventDisableTiming));
+    if (pl->ev_x1 == nullptr) CUDA_TRY(cudaEventCreateWithFlags(&pl->ev_x1, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventRecord(pl->ev_x0, st));
+    CUDA_TRY(cudaStreamWaitEvent(pl->stream_x, pl->ev_x0, 0));
+    if (top_rows > 0) {
+        CUDA_TRY(cudaMemcpyAsync(up_dst, own, (size_t)top_rows * rowf * 4, cudaMemcpyDefault, pl->stream_x));
+        CUDA_TRY(cudaMemcpyAsync(h->box_up + 4, hs, 4, cudaMemcpyDefault, pl->stream_x)); // its flag "from below"
+    }
+    if (bot_rows > 0) {
+        CUDA_TRY(cudaMemcpyAsync(down_dst, own + (size_t)(src_rows - bot_rows) * rowf, (size_t)bot_rows * rowf * 4,
+                                 cudaMemcpyDefault, pl->stream_x));
+        CUDA_TRY(cudaMemcpyAsync(h->box_down, hs, 4, cudaMemcpyDefault, pl->stream_x));    // its flag "from above"
+    }
+    CUDA_TRY(cudaEventRecord(pl->ev_x1, pl->stream_x));
+    return 0;
+}
+
 bool plan_has_f64(const avirb200_plan* pl) { // plans that only run as a whole image through resize_device / _host
     return pl->io_in_type == AVIRB200_F64 || pl->io_out_type == AVIRB200_F64 || pl->errd;
 }
@@ -1117,7 +1156,7 @@ int avirb200_plan_set_option(avirb200_plan* pl, int option, int value) {
     case AVIRB200_OPT_STREAM_VARIANT_H: pl->opt_var_h = (value >= 0 && value < 3) ? value : -1; return 0;
     case AVIRB200_OPT_STREAM_VARIANT_V: pl->opt_var_v = (value >= 0 && value < 3) ? value : -1; return 0;
     case AVIRB200_OPT_HOST_BANDS: pl->opt_host_bands = value >= 1 ? value : -1; return 0;
-    case AVIRB200_OPT_OVERLAP_HALO: pl->opt_overlap = (value == 0) ? 0 : (value == 2 ? 2 : 1); return 0;
+    case AVIRB200_OPT_OVERLAP_HALO: pl->opt_overlap = (value >= 0 && value <= 3) ? value : 1; return 0;
     case AVIRB200_OPT_ALL_STREAM_CHAINS: {
         const int on = value > 0 ? (value == 2 ? 2 : 1) : 0;
         if (on != pl->opt_all_chains) { // re-decide which passes run on the streaming kernel (host arithmetic only)
@@ -1695,9 +1734,6 @@ int avirb200_resize_sharded(const avirb200_plan* cpl, void* comm, int rank, int 
     }
     Halo* h = (pl->opt_overlap && pl->halo && pl->halo->usable) ? pl->halo : nullptr;
     if (h != nullptr) {
-        if (pl->stream_x == nullptr) CUDA_TRY(cudaStreamCreateWithFlags(&pl->stream_x, cudaStreamNonBlocking));
-        if (pl->ev_x0 == nullptr) CUDA_TRY(cudaEventCreateWithFlags(&pl->ev_x0, cudaEventDisableTiming));
-        if (pl->ev_x1 == nullptr) CUDA_TRY(cudaEventCreateWithFlags(&pl->ev_x1, cudaEventDisableTiming));
         const unsigned seq = ++h->seq;
         const int slot = (int)(seq & 1u);
         unsigned* hs = &h->h_seq[seq & 63u];
@@ -1708,56 +1744,104 @@ int avirb200_resize_sharded(const avirb200_plan* cpl, void* comm, int rank, int 
             return run_row_pass(pl, srcb + (size_t)row0 * src_pitch * in_el, src_pitch, own + (size_t)row0 * rowf,
                                 nrows, st, &launches, src4 + (size_t)row0 * src4_row);
         };
-        // 1. the rows the neighbours need (one launch on the streaming kernel: two line segments),
-        // 2. their push on the exchange stream, 3. the interior rows
-        // (boundary rows first only on request, AVIRB200_OPT_OVERLAP_HALO = 2: the copy-engine push
-        // takes ~4 us for cfg3's 1.2 MB, less than the extra launch costs; measured on 2 x B200,
-        // profiles/r02d_*: 0.2573 / 0.2607 ms with the split vs the single row launch)
-        const bool split = pl->opt_overlap == 2 && top_rows + bot_rows < si.src_rows;
-        if (split && row_pass_can_segment(pl, d_src, src_pitch, own)) {
-            if (top_rows + bot_rows > 0 &&
-                (r = run_row_pass(pl, d_src, src_pitch, own, si.src_rows, st, &launches, nullptr, top_rows, bot_rows)) != 0)
-                return r;
-        } else if (split) {
-            if ((r = rows_pass(0, top_rows)) != 0) return r;
-            if ((r = rows_pass(si.src_rows - bot_rows, bot_rows)) != 0) return r;
-        } else if ((r = rows_pass(0, si.src_rows)) != 0) {
-            return r;
-        }
-        CUDA_TRY(cudaEventRecord(pl->ev_x0, st));
-        CUDA_TRY(cudaStreamWaitEvent(pl->stream_x, pl->ev_x0, 0));
-        if (top_rows > 0) {
-            char* dst = h->box_up + h->nb_up_off + (size_t)slot * h->nb_up_slot;
-            CUDA_TRY(cudaMemcpyAsync(dst, own, (size_t)top_rows * rowf * 4, cudaMemcpyDefault, pl->stream_x));
-            CUDA_TRY(cudaMemcpyAsync(h->box_up + 4, hs, 4, cudaMemcpyDefault, pl->stream_x)); // its flag_from_down
-        }
-        if (bot_rows > 0) {
-            char* dst = h->box_down + h->nb_down_off + (size_t)slot * h->nb_down_slot;
-            CUDA_TRY(cudaMemcpyAsync(dst, own + (size_t)(si.src_rows - bot_rows) * rowf, (size_t)bot_rows * rowf * 4,
-                                     cudaMemcpyDefault, pl->stream_x));
-            CUDA_TRY(cudaMemcpyAsync(h->box_down, hs, 4, cudaMemcpyDefault, pl->stream_x));    // its flag_from_up
-        }
-        CUDA_TRY(cudaEventRecord(pl->ev_x1, pl->stream_x));
-        if (split && (r = rows_pass(top_rows, si.src_rows - top_rows - bot_rows)) != 0) return r;
-        // 4. the neighbours' rows: wait for their sequence numbers, mailbox -> workspace
         const int need_up = (rank > 0 && si.halo_up > 0) ? 1 : 0;
         const int need_down = (rank + 1 < nranks && si.halo_down > 0) ? 1 : 0;
-        if (need_up || need_down) {
-            (void)cudaGetLastError();
-            const char* sl = h->box + 256 + (size_t)slot * h->slot_bytes;
-            halo_pull_kernel<<<64, 256, 0, st>>>(reinterpret_cast<const volatile unsigned*>(h->box), seq, need_up, need_down,
-                                                 reinterpret_cast<const float4*>(sl), reinterpret_cast<float4*>(mid),
-                                                 need_up ? h->up_bytes / 16 : 0,
-                                                 reinterpret_cast<const float4*>(sl + align256(h->up_bytes)),
-                                                 reinterpret_cast<float4*>(own + (size_t)si.src_rows * rowf),
-                                                 need_down ? h->down_bytes / 16 : 0);
-            ++launches;
-            CUDA_TRY(cudaGetLastError());
+        char* const up_dst = h->box_up + h->nb_up_off + (size_t)slot * h->nb_up_slot;         // my first rows, in rank-1's mailbox
+        char* const down_dst = h->box_down + h->nb_down_off + (size_t)slot * h->nb_down_slot; // my last rows, in rank+1's
+        const char* const my_slot = h->box + 256 + (size_t)slot * h->slot_bytes;
+        // AVIRB200_OPT_OVERLAP_HALO = 3, the fused exchange: the row kernel stores the rows the neighbours need
+        // into their mailboxes as it produces them (peer stores over NVLink) and raises their flags when the
+        // last of them is out; the column kernel reads the neighbours' rows in place from this rank's mailbox,
+        // waiting on the flags only in the runs that touch them.  No exchange stream, no copy, no extra launch.
+        // Either half falls back on its own (the mailbox protocol is the same): a row pass that is not on the
+        // streaming kernel pushes with the copy engines, a column pass that is not pulls into the workspace.
+        // (Slots alternate per call and are reused two calls later; what orders the reuse is that a rank's
+        // call n+1 needs its neighbour's call-n+1 rows, sent after the neighbour's call-n column pass: so the
+        // fused halves run only between neighbours that exchange rows in BOTH directions.)
+        const bool both_ways = (rank == 0 || ((top_rows > 0) == (si.halo_up > 0))) &&
+                               (rank + 1 >= nranks || ((bot_rows > 0) == (si.halo_down > 0)));
+        const bool fused = pl->opt_overlap == 3 && both_ways;
+        // (the fused sender keeps one mailbox per 16-line strip: not for bands so short that a strip holds
+        // rows of both neighbours)
+        const bool fused_tx = fused && !(top_rows > 0 && bot_rows > 0 && (top_rows + 15) / 16 > (si.src_rows - bot_rows) / 16);
+        bool sent = false, pushed = false;
+        if (fused_tx && top_rows + bot_rows > 0) {
+            avs::StreamParams xs;
+            std::memset(&xs, 0, sizeof xs);
+            const int L = 16; // lines of a strip (avs::kLines)
+            xs.xs_seq = seq;
+            xs.xs_count = reinterpret_cast<unsigned long long*>(h->box + 64);
+            if (top_rows > 0) {
+                xs.xs_up_dst = reinterpret_cast<float*>(up_dst);
+                xs.xs_up_flag = reinterpret_cast<unsigned*>(h->box_up + 4); // its flag "from below"
+                xs.xs_top = top_rows;
+                xs.xs_units[0] = (unsigned long long)((top_rows + L - 1) / L);
+            }
+            if (bot_rows > 0) {
+                xs.xs_dn_dst = reinterpret_cast<float*>(down_dst);
+                xs.xs_dn_flag = reinterpret_cast<unsigned*>(h->box_down); // its flag "from above"
+                xs.xs_bot0 = si.src_rows - bot_rows;
+                xs.xs_bot = bot_rows;
+                xs.xs_units[1] = (unsigned long long)((si.src_rows + L - 1) / L - xs.xs_bot0 / L);
+            }
+            if ((r = run_row_pass(pl, d_src, src_pitch, own, si.src_rows, st, &launches, src4, 0, 0, &xs, &sent)) != 0) return r;
+        } else {
+            // 1. the rows the neighbours need (one launch on the streaming kernel: two line segments),
+            // 2. their push on the exchange stream, 3. the interior rows
+            // (boundary rows first only on request, AVIRB200_OPT_OVERLAP_HALO = 2: the copy-engine push
+            // takes ~4 us for cfg3's 1.2 MB, less than the extra launch costs; measured on 2 x B200,
+            // profiles/r02d_*: 0.2573 / 0.2607 ms with the split vs the single row launch)
+            const bool split = pl->opt_overlap == 2 && top_rows + bot_rows < si.src_rows;
+            if (split && row_pass_can_segment(pl, d_src, src_pitch, own)) {
+                if (top_rows + bot_rows > 0 &&
+                    (r = run_row_pass(pl, d_src, src_pitch, own, si.src_rows, st, &launches, nullptr, top_rows, bot_rows)) != 0)
+                    return r;
+            } else if (split) {
+                if ((r = rows_pass(0, top_rows)) != 0) return r;
+                if ((r = rows_pass(si.src_rows - bot_rows, bot_rows)) != 0) return r;
+            } else if ((r = rows_pass(0, si.src_rows)) != 0) {
+                return r;
+            }
+            if ((r = sharded_push(pl, h, st, own, rowf, top_rows, bot_rows, si.src_rows, up_dst, down_dst, hs)) != 0) return r;
+            sent = pushed = true;
+            if (split && (r = rows_pass(top_rows, si.src_rows - top_rows - bot_rows)) != 0) return r;
         }
-        r = run_col_pass(pl, mid, si.need_row0, d_dst, dst_pitch, si.dst_row0, si.dst_row0 + si.dst_rows, st, &launches, dst4,
-                         si.need_rows);
+        if (!sent && top_rows + bot_rows > 0) { // the fused row pass did not run on the streaming kernel
+            if ((r = sharded_push(pl, h, st, own, rowf, top_rows, bot_rows, si.src_rows, up_dst, down_dst, hs)) != 0) return r;
+            pushed = true;
+        }
+        // 4. the neighbours' rows: in place (fused), or wait for their sequence numbers and move them
+        // mailbox -> workspace
+        r = 1;
+        if (fused && (need_up || need_down)) {
+            avs::StreamParams xr;
+            std::memset(&xr, 0, sizeof xr);
+            xr.xr_up_src = reinterpret_cast<const float*>(my_slot);
+            xr.xr_dn_src = reinterpret_cast<const float*>(my_slot + align256(h->up_bytes));
+            xr.xr_flags = reinterpret_cast<const volatile unsigned*>(h->box);
+            xr.xr_seq = seq;
+            xr.xr_own_lo = si.src_row0;
+            xr.xr_own_hi = si.src_row0 + si.src_rows;
+            r = run_col_pass(pl, mid, si.need_row0, d_dst, dst_pitch, si.dst_row0, si.dst_row0 + si.dst_rows, st, &launches,
+                             dst4, si.need_rows, &xr);
+        }
+        if (r == 1) {
+            if (need_up || need_down) {
+                (void)cudaGetLastError();
+                halo_pull_kernel<<<64, 256, 0, st>>>(reinterpret_cast<const volatile unsigned*>(h->box), seq, need_up, need_down,
+                                                     reinterpret_cast<const float4*>(my_slot), reinterpret_cast<float4*>(mid),
+                                                     need_up ? h->up_bytes / 16 : 0,
+                                                     reinterpret_cast<const float4*>(my_slot + align256(h->up_bytes)),
+                                                     reinterpret_cast<float4*>(own + (size_t)si.src_rows * rowf),
+                                                     need_down ? h->down_bytes / 16 : 0);
+                ++launches;
+                CUDA_TRY(cudaGetLastError());
+            }
+            r = run_col_pass(pl, mid, si.need_row0, d_dst, dst_pitch, si.dst_row0, si.dst_row0 + si.dst_rows, st, &launches,
+                             dst4, si.need_rows);
+        }
         // the pushes read this call's workspace: the caller's stream does not end before them
-        CUDA_TRY(cudaStreamWaitEvent(st, pl->ev_x1, 0));
+        if (pushed) CUDA_TRY(cudaStreamWaitEvent(st, pl->ev_x1, 0));
         pl->last_launches = launches;
         return r;
     }

@@ -84,7 +84,8 @@ int stream_launch_chain<AVS_CHAIN_ID, (AVS_CHAIN_PASS != 0)>(int variant, int ep
             if constexpr (decltype(pass)::is_v != IS_V) {
                 (void)rc; // (the dispatcher instantiates the callback for both passes)
             } else if constexpr (!IS_V) {
-                rc = launch_one<C, false, 0>(p, sm_count, st);
+                rc = (p.xs_count != nullptr) ? launch_one<C, false, kEpiXs>(p, sm_count, st) // sender of the fused halo exchange
+                                             : launch_one<C, false, 0>(p, sm_count, st);
             } else {
                 rc = (epi == 1) ? launch_one<C, true, 1>(p, sm_count, st)
                                 : (epi == 2 ? launch_one<C, true, 2>(p, sm_count, st) : launch_one<C, true, 0>(p, sm_count, st));

@@ -58,6 +58,7 @@ using avb::round_out;
 using avb::round_out_int;
 
 constexpr int kLines = 16;      // lines per warp (2 lanes per line)
+constexpr int kEpiXs = 4;       // row pass "epilogue" code: sender of the fused halo exchange (StreamParams xs_*)
 constexpr int kPitchL = 32;     // float2 units: [position][lane] rows of 256 bytes
 // Row pass, source ring and output staging: [line][position][4 channels] with one pixel of
 // padding per line.  The copies into it (cp.async) and out of the staging rows then move
@@ -274,10 +275,14 @@ AVS_FN void mbar_wait(unsigned, unsigned) {}
 // (every source read of the emulation is checked against the buffer the pass was given)
 extern thread_local const unsigned char* avs_emul_src_lo;
 extern thread_local const unsigned char* avs_emul_src_hi;
+extern thread_local const unsigned char* avs_emul_alt_lo[2]; // (fused halo exchange: the two mailbox areas)
+extern thread_local const unsigned char* avs_emul_alt_hi[2];
 void avs_emul_count_oob();
 AVS_FN void emul_copy(void* smem, const void* gmem, int n) {
     const unsigned char* g = static_cast<const unsigned char*>(gmem);
-    if (avs_emul_src_lo != nullptr && (g < avs_emul_src_lo || g + n > avs_emul_src_hi)) {
+    const bool in_alt = (avs_emul_alt_lo[0] != nullptr && g >= avs_emul_alt_lo[0] && g + n <= avs_emul_alt_hi[0]) ||
+                        (avs_emul_alt_lo[1] != nullptr && g >= avs_emul_alt_lo[1] && g + n <= avs_emul_alt_hi[1]);
+    if (avs_emul_src_lo != nullptr && !in_alt && (g < avs_emul_src_lo || g + n > avs_emul_src_hi)) {
         avs_emul_count_oob();
         memset(smem, 0xff, n);
         return;
@@ -290,6 +295,32 @@ AVS_FN void cp_async_px(void* smem, const void* gmem) { emul_copy(smem, gmem, N)
 AVS_FN void cp_async_commit() {}
 template <int N>
 AVS_FN void cp_async_wait() {}
+#endif
+
+// ---- fused halo exchange: counters and flags ------------------------------------------------------------------
+#if defined(__CUDACC__)
+AVS_FN unsigned long long xs_add(unsigned long long* c, unsigned long long v) { return atomicAdd(c, v); }
+AVS_FN void xs_publish(unsigned* flag, unsigned seq) {
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(seq) : "memory");
+}
+AVS_FN void xs_fence() { __threadfence_system(); }
+AVS_FN void xr_wait(const volatile unsigned* flag, unsigned seq) {
+    long long spins = 0;
+    while ((int)(*flag - seq) < 0) {
+        if (++spins > (1ll << 30)) __trap(); // the neighbour never delivered: fail instead of hanging
+        __nanosleep(64);
+    }
+    __threadfence_system();
+}
+#else
+unsigned long long avs_emul_xs_add(unsigned long long* c, unsigned long long v); // (atomic in the emulator)
+AVS_FN unsigned long long xs_add(unsigned long long* c, unsigned long long v) { return avs_emul_xs_add(c, v); }
+AVS_FN void xs_publish(unsigned* flag, unsigned seq) { *flag = seq; }
+AVS_FN void xs_fence() {}
+AVS_FN void xr_wait(const volatile unsigned* flag, unsigned seq) { // (bands run one after another: must be there)
+    if ((int)(*flag - seq) < 0) avs_emul_count_oob();
+}
 #endif
 
 // First input position output j of a step reads.
@@ -410,6 +441,10 @@ struct WarpRun {
     // source ring tracked by mbarriers (C::MBAR): shared address of slot 0's barrier, the phase
     // parity each slot's next completion will have (bit s = slot s)
     unsigned mbar0, mpar;
+    // row pass of a sharded band, fused halo exchange: lines [xs_l0, xs_l1) of this run's strip are rows a
+    // neighbour rank needs (xs_dir: 0 the rank above, 1 below); their copies live xs_delta bytes away
+    int xs_l0, xs_l1, xs_dir;
+    ptrdiff_t xs_delta;
 };
 
 template <class C, bool IS_V, int I>
@@ -495,7 +530,8 @@ AVS_FN void load_group(const StreamParams& p, WarpRun<C, IS_V>& w, int g, int gs
     for (int q = 0; q < C::SRC_N / POSW; ++q) {
         const int pos0 = w.o0 + g * C::SRC_N + q * POSW; // first source position of the sweep
         unsigned char* ring = reinterpret_cast<unsigned char*>(w.ring0) + (size_t)(gslot + q * POSW) * PITCH_B;
-        const bool interior = STEADY || ((pos0 >= p.src_lo) && (pos0 + POSW <= p.src_hi));
+        const bool interior = STEADY || ((pos0 >= p.src_lo) && (pos0 + POSW <= p.src_hi) &&
+                                         (!IS_V || p.xr_flags == nullptr || (pos0 >= p.xr_own_lo && pos0 + POSW <= p.xr_own_hi)));
         if (IS_V) {
             // a position is an intermediate row; the warp's 16 pixel columns are 256 contiguous bytes
             const int piece = lane & 15, rsub = lane >> 4;
@@ -508,11 +544,19 @@ AVS_FN void load_group(const StreamParams& p, WarpRun<C, IS_V>& w, int g, int gs
 #pragma unroll
                 for (int k = 0; k < NK; ++k) cp_async16(d + 2 * k * PITCH_B, w.gp[k]);
             } else if (issue) {
-                const unsigned char* col = src + (size_t)(w.line0 + imin_(piece, w.nlines - 1)) * 16;
+                const size_t coff = (size_t)(w.line0 + imin_(piece, w.nlines - 1)) * 16;
+                const unsigned char* col = src + coff;
 #pragma unroll
                 for (int k = 0; k < NK; ++k) {
-                    const int y = imin_(imax_(pos0 + rsub + 2 * k, p.src_lo), p.src_hi - 1) - p.src_row_base;
-                    cp_async16(d + 2 * k * PITCH_B, col + (ptrdiff_t)y * (ptrdiff_t)rowb);
+                    const int yg = imin_(imax_(pos0 + rsub + 2 * k, p.src_lo), p.src_hi - 1);
+                    const unsigned char* g = col + (ptrdiff_t)(yg - p.src_row_base) * (ptrdiff_t)rowb;
+                    if (p.xr_flags != nullptr) { // fused halo exchange: the neighbours' rows, in place in the mailbox
+                        if (yg < p.xr_own_lo)
+                            g = reinterpret_cast<const unsigned char*>(p.xr_up_src) + coff + (size_t)(yg - p.src_lo) * rowb;
+                        else if (yg >= p.xr_own_hi)
+                            g = reinterpret_cast<const unsigned char*>(p.xr_dn_src) + coff + (size_t)(yg - p.xr_own_hi) * rowb;
+                    }
+                    cp_async16(d + 2 * k * PITCH_B, g);
                 }
             }
         } else {
@@ -630,7 +674,9 @@ AVS_FN void sink_h_readback(WarpRun<C, false>& w) {
         w.pend[k] = *reinterpret_cast<const float4*>(w.stage + (lsub + (32 / M) * k) * C::STAGE_LINE + pos * 2);
 }
 
-template <class C, int M>
+// XS: the row pass of a sharded band with the fused halo exchange (its own instantiation, kEpiXs: the
+// plain kernel's loop carries none of it).
+template <class C, int M, bool XS = false>
 AVS_FN void sink_h_store(const StreamParams& p, WarpRun<C, false>& w) {
     const int pos = w.lane & (M - 1), lsub = w.lane / M;
     const int j = w.pend_j0 + pos;
@@ -642,6 +688,18 @@ AVS_FN void sink_h_store(const StreamParams& p, WarpRun<C, false>& w) {
     for (int k = 0; k < M / 2; ++k) {
         if (jok && lsub + (32 / M) * k < w.nlines) *g = w.pend[k];
         g += gstep;
+    }
+    if constexpr (XS) {
+        // fused halo exchange: the lines [xs_l0, xs_l1) of this strip (empty outside the first / last strips of
+        // a sharded band) also go straight into a neighbour's mailbox -- peer memory over NVLink, xs_delta
+        // bytes from the line's own address.  Predicated stores, no branch: the loop stays straight-line.
+        unsigned char* ga = reinterpret_cast<unsigned char*>(reinterpret_cast<float4*>(dst + (size_t)(w.line0 + lsub) * (size_t)p.dst_pitch) + j) + w.xs_delta;
+#pragma unroll
+        for (int k = 0; k < M / 2; ++k) {
+            const int l = lsub + (32 / M) * k;
+            if (jok && l >= w.xs_l0 && l < w.xs_l1) *reinterpret_cast<float4*>(ga) = w.pend[k];
+            ga += gstep * sizeof(float4);
+        }
     }
     w.pend_j0 = kNoPend;
 }
@@ -795,7 +853,7 @@ AVS_FN void run_batch(const StreamParams& p, WarpRun<C, IS_V>& w) {
     } else if constexpr (IS_V) {
         if (STEADY || have) sink_v<C, EPI, M, STEADY>(p, w, j0, o);
     } else {
-        sink_h_store<C, M>(p, w);
+        sink_h_store<C, M, EPI == kEpiXs>(p, w);
         if (STEADY || have) sink_h_stage<C, M>(w, j0, o);
     }
 }
@@ -1013,7 +1071,7 @@ AVS_FN void regwin_round(const StreamParams& p, WarpRun<C, IS_V>& w, RegWin<C>& 
             sink_v<C, EPI, ML, true>(p, w, jout + q * ML, o + q * ML);
         } else {
             if (q > 0) sink_h_readback<C, ML>(w);
-            sink_h_store<C, ML>(p, w);
+            sink_h_store<C, ML, EPI == kEpiXs>(p, w);
             sink_h_stage<C, ML>(w, jout + q * ML, o + q * ML);
         }
     }
@@ -1096,11 +1154,37 @@ AVS_FN void run_warp(const StreamParams& p, WarpRun<C, IS_V>& w, int strip, int 
 
     const int total = rounds + C::DELAY_LAST;  // wall rounds; step 0 runs all of them
     const int groups = total + C::H;           // source groups step 0 reads
+    const bool fused_rx = IS_V && p.xr_flags != nullptr;
+    const int int_lo = fused_rx ? p.xr_own_lo : p.src_lo, int_hi = fused_rx ? p.xr_own_hi : p.src_hi;
+    if (fused_rx) {
+        // fused halo exchange: a run that reads the neighbours' rows waits for them here, once
+        const int first = w.o0, last = w.o0 + groups * C::SRC_N;
+        if (first < p.xr_own_lo && p.xr_own_lo > p.src_lo) xr_wait(p.xr_flags + 0, p.xr_seq);
+        if (last > p.xr_own_hi && p.xr_own_hi < p.src_hi) xr_wait(p.xr_flags + 1, p.xr_seq);
+    }
     int gslot = 0;
     int gi = 0, wi = 0; // C::MBAR: group index (ring slot / SRC_N) the loader fills / a round waits for next
     constexpr int PRO = C::H + C::LOOKAHEAD;
     loader_init<C, IS_V>(p, w);
     if constexpr (!IS_V) w.pend_j0 = kNoPend;
+    if constexpr (!IS_V) {
+        w.xs_l0 = w.xs_l1 = w.xs_dir = 0;
+        w.xs_delta = 0;
+    }
+    if constexpr (!IS_V && EPI == kEpiXs) {
+        // (the host launches this kernel only when no strip holds rows of both neighbours)
+        const ptrdiff_t rowb = (ptrdiff_t)p.dst_pitch * 4;
+        if (p.xs_up_dst != nullptr && w.line0 < p.xs_top) {
+            w.xs_l1 = imin_(w.nlines, p.xs_top - w.line0);
+            w.xs_delta = reinterpret_cast<const unsigned char*>(p.xs_up_dst) - static_cast<const unsigned char*>(p.dst);
+        } else if (p.xs_dn_dst != nullptr && w.line0 + w.nlines > p.xs_bot0 && w.line0 < p.xs_bot0 + p.xs_bot) {
+            w.xs_dir = 1;
+            w.xs_l0 = imax_(0, p.xs_bot0 - w.line0);
+            w.xs_l1 = imin_(w.nlines, p.xs_bot0 + p.xs_bot - w.line0);
+            w.xs_delta = reinterpret_cast<const unsigned char*>(p.xs_dn_dst) - static_cast<const unsigned char*>(p.dst) -
+                         (ptrdiff_t)p.xs_bot0 * rowb;
+        }
+    }
     // one checked group: per-lane copies (clamped at the line's ends), completion through the
     // lane's cp.async group or, C::MBAR, the group's mbarrier
 #define AVS_ISSUE_CHECKED(G)                                                                          \
@@ -1132,9 +1216,9 @@ AVS_FN void run_warp(const StreamParams& p, WarpRun<C, IS_V>& w, int strip, int 
     steady_bounds<C, IS_V, 1, S1>(p, w, C::delay1, C::reps1, slo, shi);
     if constexpr (C::NS == 3) steady_bounds<C, IS_V, 2, S2>(p, w, C::delay2, C::reps2, slo, shi);
     // the group a steady round issues (r + PRO) is interior -- or lies behind the run (not issued)
-    slo = imax_(slo, cdiv_(p.src_lo - w.o0, C::SRC_N) - PRO);
+    slo = imax_(slo, cdiv_(int_lo - w.o0, C::SRC_N) - PRO);
     {
-        const int g_int_hi = fdiv_(p.src_hi - w.o0, C::SRC_N) - 1; // last group without clamping
+        const int g_int_hi = fdiv_(int_hi - w.o0, C::SRC_N) - 1; // last group without clamping
         if (groups - 1 > g_int_hi) shi = imin_(shi, g_int_hi - PRO);
     }
 
@@ -1192,10 +1276,26 @@ AVS_FN void run_warp(const StreamParams& p, WarpRun<C, IS_V>& w, int strip, int 
     if constexpr (!IS_V) {
         // the last batch is still in the staging rows
         sink_h_readback<C, C::MLAST>(w);
-        sink_h_store<C, C::MLAST>(p, w);
+        sink_h_store<C, C::MLAST, EPI == kEpiXs>(p, w);
     }
     if constexpr (!C::MBAR) cp_async_wait<0>(); // (C::MBAR: every issued group has been waited for)
     AVS_SYNCWARP(); // the next run refills the rings
+    if constexpr (!IS_V && EPI == kEpiXs) {
+        if (w.xs_l1 > w.xs_l0) {
+            // fused halo exchange: this run's rows are in the neighbour's mailbox; the warp that
+            // completes the call's total of boundary-strip rounds publishes the sequence number
+            xs_fence();
+            AVS_SYNCWARP();
+            if (w.lane == 0) {
+                const unsigned long long rps = (unsigned long long)((p.out1 - 1) / C::B - p.out0 / C::B + 1); // rounds per strip
+                const unsigned long long done = xs_add(p.xs_count + w.xs_dir, (unsigned long long)rounds) + (unsigned long long)rounds;
+                if (done == p.xs_units[w.xs_dir] * rps) {
+                    p.xs_count[w.xs_dir] = 0;
+                    xs_publish(w.xs_dir ? p.xs_dn_flag : p.xs_up_flag, p.xs_seq);
+                }
+            }
+        }
+    }
 }
 
 // ---- a warp's share of the pass -------------------------------------------------------------------------

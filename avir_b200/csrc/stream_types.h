@@ -61,6 +61,29 @@ struct StreamParams {
     float out_gamma_mult;
     int round_mode;
     float tr_mul, tr_mul_inv, pk_out;
+    // ---- fused halo exchange of sharded calls (engine.cu: AVIRB200_OPT_OVERLAP_HALO = 3) -----------
+    // Row pass (sender): lines [0, xs_top) of the band are ALSO stored into the mailbox of the rank
+    // above (xs_up_dst: its row 0), lines [xs_bot0, xs_bot0 + xs_bot) into the mailbox of the rank
+    // below (xs_dn_dst); a warp that finishes a run over such lines adds its rounds to xs_count[0 / 1]
+    // (this rank's memory, zero between calls; the total to reach is xs_units[..] strips x the rounds
+    // of a strip), and the warp that completes the total zeroes the counter and writes xs_seq to the
+    // neighbour's flag.  Null pointers: off.
+    float* xs_up_dst;
+    float* xs_dn_dst;
+    unsigned* xs_up_flag;
+    unsigned* xs_dn_flag;
+    unsigned long long* xs_count;
+    unsigned long long xs_units[2];
+    unsigned xs_seq;
+    int xs_top, xs_bot0, xs_bot;
+    // Column pass (receiver): source rows below xr_own_lo come from xr_up_src (row need_row0 first),
+    // rows from xr_own_hi on from xr_dn_src (row xr_own_hi first) -- the mailbox, read in place; a run
+    // that touches them first waits for xr_flags[0 / 1] >= xr_seq.  xr_flags null: off.
+    const float* xr_up_src;
+    const float* xr_dn_src;
+    const volatile unsigned* xr_flags;
+    unsigned xr_seq;
+    int xr_own_lo, xr_own_hi;
     // column pass, scheduling variant 2: CUtensorMap over the intermediate buffer (2-D, fp32:
     // n_lines * 4 elements per row, rows from p.src on; box 64 elements x SRC_N rows), encoded by
     // the launcher (stream_chain.cu)

@@ -205,8 +205,9 @@ def workload_config(args, n):
                         % ({"dil": "fpclass_float8_dil", "f4": "fpclass_float4",
                             "def": "fpclass_def<float>"}[args.mirror], SRC_H * n, DST_H * n),
             "mirror": args.mirror, "frames_per_step": n,
-            "parallelism": "single GPU" if n == 1 else "row-sharded x%d, halo exchange over NVLink "
-                                                       "(NCCL send/recv overlapped with the interior rows)" % n,
+            "parallelism": "single GPU" if n == 1 else "row-sharded x%d, halo rows exchanged through peer "
+                                                       "mailboxes over NVLink (AVIRB200_OPT_OVERLAP_HALO = %s)"
+                                                       % (n, "library default" if args.halo_mode is None else args.halo_mode),
             "input": "SURVEY 8(d) xorshift32, seed 12345 (+rank)",
             "l2": "inputs larger than L2 (531 MB source + 265 MB intermediate per GPU per step)"}
 
@@ -234,6 +235,7 @@ def declare(lib):
 
 class Plan:
     """A C-ABI plan for one call shape (the descriptor comes from the C++ front-end)."""
+    halo_mode = None  # --halo-mode: AVIRB200_OPT_OVERLAP_HALO of every plan (None: the library's default)
 
     def __init__(self, ab, fp, shape, tin, nw, nh, tout, rb, kw=None):
         kw = kw or {}
@@ -245,6 +247,9 @@ class Plan:
         if self.lib.avirb200_plan_create(C.c_void_p(dp), C.byref(self.plan)) != 0:
             raise SystemExit("plan_create: " + self.lib.avirb200_last_error().decode())
         self.vars = v
+        if Plan.halo_mode is not None:
+            self.lib.avirb200_plan_set_option.argtypes = [C.c_void_p, C.c_int, C.c_int]
+            assert self.lib.avirb200_plan_set_option(self.plan, 5, Plan.halo_mode) == 0  # AVIRB200_OPT_OVERLAP_HALO
 
     def workspace(self):
         b = C.c_size_t()
@@ -790,8 +795,11 @@ def main():
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--mirror", default="dil", choices=sorted(MIRRORS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--halo-mode", type=int, default=None, choices=[0, 1, 2, 3],
+                    help="sharded runs: AVIRB200_OPT_OVERLAP_HALO (default: the library's)")
     ap.add_argument("--no-extras", action="store_true", help="headline only (no secondary configs / LANCIR / variants)")
     args = ap.parse_args()
+    Plan.halo_mode = args.halo_mode
     args.warmup = max(args.warmup, 3) if args.impl == "own" else args.warmup
     if args.impl == "reference":
         run_reference(args)

@@ -183,8 +183,12 @@ typedef enum avirb200_option {
     AVIRB200_OPT_ALL_STREAM_CHAINS = 4,
     /* avirb200_resize_sharded: 1 (default) = halo rows pushed by the copy engines into the neighbours'
      * mailboxes over NVLink after the row pass; 2 = the same with the rows the neighbours need
-     * filtered FIRST (one segmented launch) so that the push overlaps the interior rows; 0 = NCCL
-     * send/recv between the two passes */
+     * filtered FIRST (one segmented launch) so that the push overlaps the interior rows; 3 = the
+     * FUSED exchange: the row kernel itself stores the rows the neighbours need into their mailboxes
+     * (peer stores over NVLink) and raises their flags, the column kernel reads the neighbours' rows
+     * in place from the mailbox -- no exchange stream, no copies, no extra launch (passes that are not
+     * on the streaming kernel fall back to the push / pull of 1, per pass); 0 = NCCL send/recv
+     * between the two passes */
     AVIRB200_OPT_OVERLAP_HALO = 5
 } avirb200_option;
 int avirb200_plan_set_option(avirb200_plan* plan, int option, int value);

@@ -57,7 +57,7 @@ def main():
     assert lib.avirb200_comm_create(raw, rank, world, C.byref(comm)) == 0, lib.avirb200_last_error()
     st = torch.cuda.current_stream().cuda_stream
     bad = 0
-    overlaps = [int(v) for v in os.environ.get("AVIR_NCCL_OVERLAPS", "1,2,0").split(",")]
+    overlaps = [int(v) for v in os.environ.get("AVIR_NCCL_OVERLAPS", "3,1,2,0").split(",")]
     debug = os.environ.get("AVIR_NCCL_DEBUG") == "1"
 
     def dbg(*a):

@@ -35,6 +35,19 @@ def band_needs(dp, bands):
     return out
 
 
+def band_infos(dp, bands):
+    """avirb200_shard_info of every band (8 ints each), or None where the product refuses the split."""
+    import avir_b200 as ab
+    out = (C.c_int * (8 * bands))()
+    for b in range(bands):
+        si = _SI()
+        if ab.lib().avirb200_shard_query_desc(C.c_void_p(dp), b, bands, C.byref(si)) != 0:
+            return None
+        for i, (n, _) in enumerate(_SI._fields_):
+            out[8 * b + i] = getattr(si, n)
+    return out
+
+
 @pytest.fixture(scope="module")
 def emul():
     from avir_b200 import build as b
@@ -42,6 +55,9 @@ def emul():
     lib.stream_emul_resize.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t,
                                        C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int]
     lib.stream_emul_resize.restype = C.c_int
+    lib.stream_emul_resize_fused.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t,
+                                             C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+    lib.stream_emul_resize_fused.restype = C.c_int
     lib.stream_emul_applicable.argtypes = [C.c_void_p]
     lib.stream_emul_applicable.restype = C.c_int
     return lib
@@ -120,6 +136,45 @@ def test_stream_kernel_emulation_matches_port(emul, ec, variant):
         cs.port().avir_port_srgb_lut(lut.ctypes.data)
         assert emul.stream_emul_resize(dp, src.ctypes.data, sw * ch, got.ctypes.data, nw * ch, wh, wv, bands,
                                        variant, lut.ctypes.data, 1, band_needs(dp, bands), (3 * variant + wh) % 23, (5 * variant + wv) % 19) == 0
+    finally:
+        rs.free_descriptor(h)
+    want, _ = cs.port_output(case, src)
+    assert cs.count_mismatch(want, got) == 0
+
+
+# The sharded schedule with the fused halo exchange (AVIRB200_OPT_OVERLAP_HALO = 3): row passes store the
+# boundary rows into the neighbours' mailboxes and raise their flags, column passes read them in place.
+FUSED_CASES = [(ec[0], ec[1], ec[2], b) for ec in EMUL_CASES[::2] for b in (2, 3, 4)] + [
+    # tall narrow images: middle bands with two neighbours, several strips between their rows
+    ((2, 64, 400, 32, 200, 4, f32, f32, 16, {"buildmode": 1}), 3, 4, 3),
+    ((2, 64, 400, 32, 200, 4, f32, f32, 16, {"buildmode": 1}), 5, 2, 4),
+    ((1, 64, 400, 32, 200, 4, u16, u16, 16, {"buildmode": 0}), 2, 3, 4),
+    ((2, 96, 640, 24, 160, 4, u8, u8, 8, {"gamma": True, "alpha": 3, "buildmode": 1}), 3, 2, 3),
+    ((1, 48, 200, 96, 400, 4, u8, u8, 8, {"buildmode": 1}), 2, 3, 3),
+    ((1, 128, 640, 32, 160, 4, u16, u16, 16, {"buildmode": 0}), 4, 3, 4),
+]
+
+
+@pytest.mark.parametrize("variant", (0, 1, 2))
+@pytest.mark.parametrize("ec", FUSED_CASES, ids=_id)
+def test_stream_kernel_emulation_fused_exchange_matches_port(emul, ec, variant):
+    case, wh, wv, bands = ec
+    fp, sw, sh, nw, nh, ch, ti, to, rb, kw = case
+    src = cs.make_input(case)
+    rs, v = cs.resizer_and_vars(case)
+    h, dp, modes = rs.descriptor(src.shape, src.dtype, nw, nh, to, kw.get("k", 0.0), v)
+    try:
+        infos = band_infos(dp, bands)
+        if infos is None:
+            pytest.skip("bands too small for the sharded schedule")
+        got = np.zeros((nh, nw, ch), to)
+        lut = np.zeros(256, np.float32)
+        cs.port().avir_port_srgb_lut(lut.ctypes.data)
+        rc = emul.stream_emul_resize_fused(dp, src.ctypes.data, sw * ch, got.ctypes.data, nw * ch, wh, wv, bands,
+                                           variant, lut.ctypes.data, 1, infos)
+        if rc == 1:
+            pytest.skip("a strip with rows of both neighbours: the product pushes with the copy engines")
+        assert rc == 0
     finally:
         rs.free_descriptor(h)
     want, _ = cs.port_output(case, src)
