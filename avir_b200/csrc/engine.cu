@@ -135,7 +135,7 @@ struct avirb200_plan {
     int opt_var_h = -1, opt_var_v = -1; // scheduling variant of the streaming passes (-1: default)
     int opt_host_bands = -1;  // resize_host band count (-1: by size)
     int opt_all_chains = 0;
-    int opt_overlap = 1;      // sharded: mailbox exchange overlapped with the interior rows
+    int opt_overlap = 3;      // sharded: how the halo rows travel (AVIRB200_OPT_OVERLAP_HALO; 3 = fused into the kernels)
     int sm_count = 148;       // of `device`
     Halo* halo = nullptr; // sharded: peer mailboxes (created by the first sharded call)
     cudaStream_t stream_x = nullptr; // sharded: exchange stream
@@ -1156,7 +1156,7 @@ int avirb200_plan_set_option(avirb200_plan* pl, int option, int value) {
     case AVIRB200_OPT_STREAM_VARIANT_H: pl->opt_var_h = (value >= 0 && value < 3) ? value : -1; return 0;
     case AVIRB200_OPT_STREAM_VARIANT_V: pl->opt_var_v = (value >= 0 && value < 3) ? value : -1; return 0;
     case AVIRB200_OPT_HOST_BANDS: pl->opt_host_bands = value >= 1 ? value : -1; return 0;
-    case AVIRB200_OPT_OVERLAP_HALO: pl->opt_overlap = (value >= 0 && value <= 3) ? value : 1; return 0;
+    case AVIRB200_OPT_OVERLAP_HALO: pl->opt_overlap = (value >= 0 && value <= 3) ? value : 3; return 0;
     case AVIRB200_OPT_ALL_STREAM_CHAINS: {
         const int on = value > 0 ? (value == 2 ? 2 : 1) : 0;
         if (on != pl->opt_all_chains) { // re-decide which passes run on the streaming kernel (host arithmetic only)

@@ -181,14 +181,15 @@ typedef enum avirb200_option {
     AVIRB200_OPT_HOST_BANDS = 3,
     /* 1: also select the streaming chains that measured slower than the tile kernel (upsizing, 56-tap) */
     AVIRB200_OPT_ALL_STREAM_CHAINS = 4,
-    /* avirb200_resize_sharded: 1 (default) = halo rows pushed by the copy engines into the neighbours'
-     * mailboxes over NVLink after the row pass; 2 = the same with the rows the neighbours need
-     * filtered FIRST (one segmented launch) so that the push overlaps the interior rows; 3 = the
-     * FUSED exchange: the row kernel itself stores the rows the neighbours need into their mailboxes
-     * (peer stores over NVLink) and raises their flags, the column kernel reads the neighbours' rows
-     * in place from the mailbox -- no exchange stream, no copies, no extra launch (passes that are not
-     * on the streaming kernel fall back to the push / pull of 1, per pass); 0 = NCCL send/recv
-     * between the two passes */
+    /* avirb200_resize_sharded, how the halo rows travel.  3 (default) = the FUSED exchange: the row
+     * kernel itself stores the rows the neighbours need into their mailboxes (peer stores over NVLink)
+     * and raises their flags, the column kernel reads the neighbours' rows in place from the mailbox --
+     * no exchange stream, no copies, no extra launch (a pass that is not on the streaming kernel falls
+     * back to the push / pull of 1, per pass).  1 = rows pushed by the copy engines into the
+     * neighbours' mailboxes after the row pass, pulled into the workspace by a small kernel; 2 = the
+     * same with the rows the neighbours need filtered FIRST (one segmented launch) so that the push
+     * overlaps the interior rows; 0 = NCCL send/recv between the two passes.  Measured, cfg3 weak
+     * scaling on 2 x B200 (profiles/r02i_*): 0.2507 ms (3), 0.2609 ms (1); one GPU 0.2440 ms. */
     AVIRB200_OPT_OVERLAP_HALO = 5
 } avirb200_option;
 int avirb200_plan_set_option(avirb200_plan* plan, int option, int value);
@@ -222,11 +223,13 @@ void avirb200_comm_destroy(void* comm);
  * (dst_rows rows).  Row pass -> NCCL halo send/recv with rank-1/rank+1 -> column pass, all
  * enqueued on `stream`.  `comm` is an ncclComm_t (from avirb200_comm_create or the
  * caller's own).  Output is bit-identical to the single-GPU path.
- * Default schedule (AVIRB200_OPT_OVERLAP_HALO): after the row pass the rows the neighbours need are
- * pushed (copy engines, NVLink peer memory mapped through CUDA IPC; the handles travel over `comm`
- * once per plan) into the neighbours' mailboxes, followed by a sequence number; one small kernel
- * waits for the neighbours' numbers and moves their rows into the workspace; then the column pass.  The first call on a plan is collective (every
- * rank must make it).  Where peer mapping is unavailable the NCCL send/recv schedule runs. */
+ * Default schedule (AVIRB200_OPT_OVERLAP_HALO = 3): every rank owns a mailbox in device memory that its
+ * neighbours map through CUDA IPC (the handles travel over `comm` once per plan).  The row kernel
+ * stores the rows a neighbour needs into that neighbour's mailbox as it produces them and, when the
+ * last one is out, the call's sequence number into the neighbour's flag; the column kernel reads
+ * the neighbours' rows in place from its own mailbox, and only the runs that touch them wait for
+ * the flag.  The first call on a plan is collective (every rank must make it).  Where peer mapping
+ * is unavailable the NCCL send/recv schedule runs. */
 int avirb200_resize_sharded(const avirb200_plan* plan, void* comm, int rank, int nranks,
                             const void* d_src, size_t src_pitch, void* d_dst, size_t dst_pitch,
                             void* d_workspace, void* stream);
