@@ -24,9 +24,9 @@ cut -c1-200 gpurun_out/${tag}_bench_reference_n1.json
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
     --log-file gpurun_out/${tag}_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-extras > gpurun_out/${tag}_ncu_bench.log 2>&1
 tail -3 gpurun_out/${tag}_launches.csv | cut -c1-260
-bash profiles/gpu_r02_ncu.sh ${tag} keep=default cfg=u8k cfg=cfg5 cfg=cfg2 cfg=cfg4 | tail -30
+bash profiles/gpu_r02_ncu.sh ${tag} keep=default cfg=cfg5 cfg=cfg4 | tail -30
 out=gpurun_out/${tag}_sweep.jsonl; : > $out
-for cfg in cfg3 cfg3f4 cfg4 u8k u8kdil cfg5; do
+for cfg in cfg3 cfg4 cfg5; do
   for v in 0 1 2; do
     timeout 120 python profiles/pass_times.py --cfg $cfg --var-h $v --var-v $v >> $out 2>> ${out}.err
   done
