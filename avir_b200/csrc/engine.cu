@@ -1922,6 +1922,74 @@ int avirb200_resize_sharded_local(const avirb200_plan* pl, int nranks, const voi
     }
     int launches = 0;
     const size_t in_el = dtype_size(d.in_type), out_el = dtype_size(d.out_type);
+    // The fused halo exchange of avirb200_resize_sharded (AVIRB200_OPT_OVERLAP_HALO = 3), with every band's
+    // mailbox in this device's memory: the same two kernels, parameters and protocol as between ranks.
+    bool fused = pl->opt_overlap == 3 && nranks > 1 && pl->opt_family == 0 && pl->stream_h.chain != 0 &&
+                 pl->stream_v.chain != 0 && (src_pitch % 4) == 0 && (dst_pitch % 2) == 0 &&
+                 (use_pad4(pl) || ((uintptr_t)d_src % (4 * in_el)) == 0) &&
+                 (use_pad4(pl) || ((uintptr_t)d_dst % (2 * fast_elsize(d.out_type))) == 0);
+    std::vector<size_t> box_off(nranks + 1, 0);
+    for (int r = 0; r < nranks && fused; ++r) {
+        const int top = (r > 0) ? si[r - 1].halo_down : 0, bot = (r + 1 < nranks) ? si[r + 1].halo_up : 0;
+        if ((r > 0 && (top > 0) != (si[r].halo_up > 0)) || (r + 1 < nranks && (bot > 0) != (si[r].halo_down > 0)) ||
+            (top > 0 && bot > 0 && (top + 15) / 16 > (si[r].src_rows - bot) / 16) || top > si[r].src_rows || bot > si[r].src_rows)
+            fused = false;
+        box_off[r + 1] = box_off[r] + 256 + align256((size_t)si[r].halo_up * rowf * 4) + align256((size_t)si[r].halo_down * rowf * 4);
+    }
+    if (fused) {
+        char* boxes = nullptr;
+        CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&boxes), box_off[nranks], st));
+        auto box = [&](int r) { return boxes + box_off[r]; };
+        auto box_up_area = [&](int r) { return box(r) + 256; };
+        auto box_dn_area = [&](int r) { return box(r) + 256 + align256((size_t)si[r].halo_up * rowf * 4); };
+        int e = 0;
+        for (int r = 0; r < nranks && e == 0; ++r)
+            if (cudaMemsetAsync(box(r), 0, 256, st) != cudaSuccess) e = fail(AVIRB200_ERR_CUDA, "sharded_local: mailbox header");
+        const unsigned seq = 1;
+        for (int r = 0; r < nranks && e == 0; ++r) {
+            float* own = mid[r] + (size_t)si[r].halo_up * rowf;
+            const char* src = static_cast<const char*>(d_src) + (size_t)si[r].src_row0 * src_pitch * in_el;
+            const int top = (r > 0) ? si[r - 1].halo_down : 0, bot = (r + 1 < nranks) ? si[r + 1].halo_up : 0;
+            avs::StreamParams xs;
+            std::memset(&xs, 0, sizeof xs);
+            xs.xs_seq = seq;
+            xs.xs_count = reinterpret_cast<unsigned long long*>(box(r) + 64);
+            if (top > 0) {
+                xs.xs_up_dst = reinterpret_cast<float*>(box_dn_area(r - 1));
+                xs.xs_up_flag = reinterpret_cast<unsigned*>(box(r - 1) + 4);
+                xs.xs_top = top;
+                xs.xs_units[0] = (unsigned long long)((top + 15) / 16);
+            }
+            if (bot > 0) {
+                xs.xs_dn_dst = reinterpret_cast<float*>(box_up_area(r + 1));
+                xs.xs_dn_flag = reinterpret_cast<unsigned*>(box(r + 1));
+                xs.xs_bot0 = si[r].src_rows - bot;
+                xs.xs_bot = bot;
+                xs.xs_units[1] = (unsigned long long)((si[r].src_rows + 15) / 16 - xs.xs_bot0 / 16);
+            }
+            bool sent = false;
+            e = run_row_pass(pl, src, src_pitch, own, si[r].src_rows, st, &launches, src4[r], 0, 0,
+                             (top + bot > 0) ? &xs : nullptr, &sent);
+            if (e == 0 && top + bot > 0 && !sent) e = fail(AVIRB200_ERR_CUDA, "sharded_local: the streaming row pass did not take the band");
+        }
+        for (int r = 0; r < nranks && e == 0; ++r) {
+            char* dst = static_cast<char*>(d_dst) + (size_t)si[r].dst_row0 * dst_pitch * out_el;
+            avs::StreamParams xr;
+            std::memset(&xr, 0, sizeof xr);
+            xr.xr_up_src = reinterpret_cast<const float*>(box_up_area(r));
+            xr.xr_dn_src = reinterpret_cast<const float*>(box_dn_area(r));
+            xr.xr_flags = reinterpret_cast<const volatile unsigned*>(box(r));
+            xr.xr_seq = seq;
+            xr.xr_own_lo = si[r].src_row0;
+            xr.xr_own_hi = si[r].src_row0 + si[r].src_rows;
+            e = run_col_pass(pl, mid[r], si[r].need_row0, dst, dst_pitch, si[r].dst_row0, si[r].dst_row0 + si[r].dst_rows, st,
+                             &launches, dst4[r], si[r].need_rows, &xr);
+            if (e == 1) e = fail(AVIRB200_ERR_CUDA, "sharded_local: the streaming column pass did not take the band");
+        }
+        cudaFreeAsync(boxes, st);
+        pl->last_launches = launches;
+        return e;
+    }
     for (int r = 0; r < nranks; ++r) { // every band's row pass
         float* own = mid[r] + (size_t)si[r].halo_up * rowf;
         const char* src = static_cast<const char*>(d_src) + (size_t)si[r].src_row0 * src_pitch * in_el;

@@ -241,8 +241,11 @@ int avirb200_resize_sharded_host(avirb200_plan* plan, void* comm, int rank, int 
                                  const void* h_src, size_t src_pitch, void* h_dst, size_t dst_pitch);
 
 /* Validation aid: runs the `nranks` bands of the sharded schedule one after another on the
- * CURRENT device (halo rows moved with device copies instead of NCCL).  Full-image device
- * buffers; d_workspace must hold the sum of all ranks' avirb200_shard_workspace_bytes. */
+ * CURRENT device.  With the default AVIRB200_OPT_OVERLAP_HALO (3) the bands exchange their halo rows
+ * exactly as ranks do -- the row kernel stores them into the neighbour band's mailbox (here in local
+ * memory) and raises its flag, the column kernel reads them in place; otherwise with device copies.
+ * Full-image device buffers; d_workspace must hold the sum of all ranks'
+ * avirb200_shard_workspace_bytes. */
 int avirb200_resize_sharded_local(const avirb200_plan* plan, int nranks, const void* d_src,
                                   size_t src_pitch, void* d_dst, size_t dst_pitch,
                                   void* d_workspace, void* stream);

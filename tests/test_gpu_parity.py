@@ -351,6 +351,58 @@ def test_sharded_local_matches_unsharded(nranks):
     assert cs.count_mismatch(ref, d_dst.cpu().numpy()) == 0
 
 
+# The fused halo exchange (AVIRB200_OPT_OVERLAP_HALO = 3: the row kernel stores the neighbours' rows into
+# their mailboxes and raises flags, the column kernel reads them in place) on ONE device: the bands of the
+# sharded schedule run one after another with every mailbox in local memory -- the same kernels, parameters
+# and protocol as between ranks (tests/test_gpu_nccl.py is the multi-process form).
+FUSED_LOCAL = [
+    (2, 640, 720, 320, 360, 4, np.float32, np.float32, 16, {}),                              # headline chain
+    (1, 640, 720, 320, 360, 4, np.float32, np.float32, 16, {}),                              # three-step chain
+    (1, 1024, 1536, 256, 384, 4, np.uint16, np.uint16, 16, {}),                              # cfg4 chain
+    (2, 1024, 1536, 256, 384, 4, np.uint8, np.uint8, 8, {"gamma": True, "alpha": 3}),        # cfg5 chain, sRGB table
+    (1, 640, 720, 320, 360, 4, np.uint8, np.uint8, 8, {}),                                   # integer source and output
+    (0, 512, 600, 256, 300, 3, np.uint8, np.uint8, 8, {}),                                   # 3 channels on the 4-channel kernels
+]
+
+
+@pytest.mark.parametrize("overlap", [3, 1])
+@pytest.mark.parametrize("nranks", [2, 3, 5])
+@pytest.mark.parametrize("case", FUSED_LOCAL, ids=cs.case_id)
+def test_sharded_local_fused_exchange_matches_unsharded(case, nranks, overlap):
+    import torch
+    fp, sw, sh, nw, nh, ch, ti, to, rb, kw = case
+    src = cs.make_input(case, seed=33)
+    whole = _device_run(case, src)
+    rs, v = cs.resizer_and_vars(case)
+    h, dp, _ = rs.descriptor(src.shape, ti, nw, nh, to, 0.0, v)
+    lib = ab.lib()
+    plan = C.c_void_p()
+    assert lib.avirb200_plan_create(C.c_void_p(dp), C.byref(plan)) == 0
+    try:
+        lib.avirb200_plan_set_option.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        assert lib.avirb200_plan_set_option(plan, ab.OPT_OVERLAP_HALO, overlap) == 0
+        total = 0
+        for r in range(nranks):
+            b = C.c_size_t()
+            assert lib.avirb200_shard_workspace_bytes(plan, r, nranks, C.byref(b)) == 0, lib.avirb200_last_error()
+            total += b.value
+        d_src = torch.from_numpy(src).cuda()
+        tmap = {np.uint8: torch.uint8, np.uint16: torch.uint16, np.float32: torch.float32}
+        d_dst = torch.zeros(nh * nw * ch * np.dtype(to).itemsize, dtype=torch.uint8, device="cuda").view(tmap[to]).reshape(nh, nw, ch)
+        d_ws = torch.empty(total, dtype=torch.uint8, device="cuda")
+        lib.avirb200_resize_sharded_local.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t,
+                                                      C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
+        for _ in range(2):  # (a second call: counters and flags start from what the first left)
+            assert lib.avirb200_resize_sharded_local(plan, nranks, d_src.data_ptr(), sw * ch, d_dst.data_ptr(),
+                                                     nw * ch, d_ws.data_ptr(), None) == 0, lib.avirb200_last_error()
+            torch.cuda.synchronize()
+        got = d_dst.cpu().numpy()
+    finally:
+        lib.avirb200_plan_destroy(plan)
+        rs.free_descriptor(h)
+    assert cs.count_mismatch(whole, got) == 0
+
+
 # ---- LANCIR ---------------------------------------------------------------------------------
 
 LANCIR = [
