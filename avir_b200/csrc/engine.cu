@@ -998,6 +998,46 @@ __global__ void __launch_bounds__(256) halo_pull_kernel(const volatile unsigned*
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < down_n; i += stride) down_dst[i] = __ldcv(down_src + i);
 }
 
+// avirb200_selftest_lin2srgb: every float bit pattern, eight consecutive patterns per thread and step
+__global__ void __launch_bounds__(256) lin2srgb_selftest_kernel(unsigned long long* out) {
+    unsigned long long checked = 0, bad = 0;
+    const unsigned long long nthreads = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long base = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) * 8; base < (1ull << 32);
+         base += nthreads * 8) {
+        float v[8], ref[8];
+        bool ok = true;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            v[i] = __uint_as_float((unsigned)(base + i));
+            ok = ok && avb::lin2srgb_batch_ok(v[i]);
+        }
+        if (!ok) { // (the product takes the one-sample path for such a batch; compare the patterns it accepts singly)
+#pragma unroll 1
+            for (int i = 0; i < 8; ++i) {
+                if (!avb::lin2srgb_batch_ok(v[i])) continue;
+                float one[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) one[k] = v[i];
+                avb::lin2srgb_batch<8>(one);
+                const float r = avb::lin2srgb(v[i]);
+                ++checked;
+                if (__float_as_uint(r) != __float_as_uint(one[3])) ++bad;
+            }
+            continue;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) ref[i] = avb::lin2srgb(v[i]);
+        avb::lin2srgb_batch<8>(v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            ++checked;
+            if (__float_as_uint(ref[i]) != __float_as_uint(v[i])) ++bad;
+        }
+    }
+    atomicAdd(out, checked);
+    atomicAdd(out + 1, bad);
+}
+
 void halo_free(Halo* h) {
     if (h == nullptr) return;
     if (h->box_up) cudaIpcCloseMemHandle(h->box_up - h->off_up);
@@ -1186,6 +1226,25 @@ int avirb200_shard_query_desc(const avirb200_plan_desc* desc, int rank, int nran
     if (desc->v.nsteps < 1 || desc->v.nsteps > AVIRB200_MAX_STEPS)
         return fail(AVIRB200_ERR_BAD_ARG, "axis: nsteps out of range");
     return shard_compute_axis(host_axis_view(desc->v), rank, nranks, info);
+}
+
+int avirb200_selftest_lin2srgb(unsigned long long* checked, unsigned long long* mismatches) {
+    if (checked == nullptr || mismatches == nullptr) return fail(AVIRB200_ERR_BAD_ARG, "null argument");
+    (void)cudaGetLastError();
+    unsigned long long* d = nullptr;
+    CUDA_TRY(cudaMalloc(&d, 2 * sizeof(unsigned long long)));
+    cudaError_t e = cudaMemset(d, 0, 2 * sizeof(unsigned long long));
+    if (e == cudaSuccess) {
+        lin2srgb_selftest_kernel<<<148 * 8, 256>>>(d);
+        e = cudaGetLastError();
+    }
+    unsigned long long h[2] = {0, 0};
+    if (e == cudaSuccess) e = cudaMemcpy(h, d, sizeof h, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(AVIRB200_ERR_CUDA, cudaGetErrorString(e));
+    *checked = h[0];
+    *mismatches = h[1];
+    return 0;
 }
 
 const char* avirb200_status_string(int s) {

@@ -400,13 +400,41 @@ AVS_FN float epilogue_round(const StreamParams& p, float v) {
     return v < 0.0f ? 0.0f : (v > p.pk_out ? p.pk_out : v);
 }
 
-AVS_FN float epilogue_value(const StreamParams& p, float v, int c) {
-    if (p.gamma_out) {
+// gamma_done: the output gamma has been applied to v already (epilogue_gamma_batch)
+AVS_FN float epilogue_value(const StreamParams& p, float v, int c, bool gamma_done = false) {
+    if (p.gamma_out && !gamma_done) {
         if (c == p.alpha_index) v = __fmul_rn(v, p.out_gamma_mult);
         else v = __fmul_rn(lin2srgb(v), p.out_gamma_mult);
     }
     if (p.dst_type != AVIRB200_F32) v = epilogue_round(p, v);
     return v;
+}
+
+// The output gamma of a lane's whole batch (M outputs x 2 channels, first channel c0) at once: the
+// samples' square-root chains advance together (pixel_ops.cuh, lin2srgb_batch) instead of one after
+// another.  Returns false, o untouched, when a sample needs the one-sample path (NaN, infinity).
+template <int M>
+AVS_FN bool epilogue_gamma_batch(const StreamParams& p, float2 (&o)[M], int c0) {
+    float v[2 * M];
+    bool ok = true;
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+        v[2 * m] = o[m].x;
+        v[2 * m + 1] = o[m].y;
+        ok = ok && avb::lin2srgb_batch_ok(o[m].x) && avb::lin2srgb_batch_ok(o[m].y);
+    }
+    if (!ok) return false;
+    // (at most 8 chains in flight: 16 would not fit the registers beside the windows)
+    constexpr int G = (2 * M > 8) ? 8 : 2 * M;
+#pragma unroll
+    for (int i = 0; i < 2 * M; i += G) avb::lin2srgb_batch<G>(v + i);
+    const bool a0 = (c0 == p.alpha_index), a1 = (c0 + 1 == p.alpha_index); // the alpha channel is exempt
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+        o[m].x = __fmul_rn(avb::fsel(a0, o[m].x, v[2 * m]), p.out_gamma_mult);
+        o[m].y = __fmul_rn(avb::fsel(a1, o[m].y, v[2 * m + 1]), p.out_gamma_mult);
+    }
+    return true;
 }
 
 // ---- per-warp state of a run -------------------------------------------------------------------------
@@ -608,7 +636,7 @@ AVS_FN float2 slow_one(const StreamStep& sp, const SrcConv& cv, const unsigned c
 
 // Column pass: lane = (pixel column, channel pair); a batch is M destination rows.
 template <int EPI>
-AVS_FN void store_v(const StreamParams& p, unsigned char* g, float2 v, int c0) {
+AVS_FN void store_v(const StreamParams& p, unsigned char* g, float2 v, int c0, bool gamma_done = false) {
     if (EPI == 1) { // float destination, no output gamma
         *reinterpret_cast<float2*>(g) = v;
         return;
@@ -626,8 +654,8 @@ AVS_FN void store_v(const StreamParams& p, unsigned char* g, float2 v, int c0) {
         if (!narrow) *reinterpret_cast<unsigned*>(g) = (unsigned)a | ((unsigned)b << 16);
         return;
     }
-    v.x = epilogue_value(p, v.x, c0);
-    v.y = epilogue_value(p, v.y, c0 + 1);
+    v.x = epilogue_value(p, v.x, c0, gamma_done);
+    v.y = epilogue_value(p, v.y, c0 + 1, gamma_done);
     if (p.dst_type == AVIRB200_F32) *reinterpret_cast<float2*>(g) = v;
     else if (p.dst_type == AVIRB200_U8)
         *reinterpret_cast<uchar2*>(g) = make_uchar2((unsigned char)v.x, (unsigned char)v.y);
@@ -643,6 +671,19 @@ AVS_FN void sink_v(const StreamParams& p, const WarpRun<C, true>& w, int j0, con
     const size_t rowb = (size_t)p.dst_pitch * esz;
     unsigned char* g = static_cast<unsigned char*>(p.dst) + ((size_t)(w.line0 + q) * 4 + c0) * esz +
                        (ptrdiff_t)(j0 - p.dst_row_base) * (ptrdiff_t)rowb;
+    if constexpr (EPI == 0) {
+        // the run-time output stage: gamma for the whole batch first (when the plan has one)
+        float2 t[M];
+#pragma unroll
+        for (int m = 0; m < M; ++m) t[m] = o[m];
+        const bool gamma_done = p.gamma_out && epilogue_gamma_batch<M>(p, t, c0);
+#pragma unroll
+        for (int m = 0; m < M; ++m) {
+            if (STEADY || (j0 + m >= p.out0 && j0 + m < p.out1)) store_v<EPI>(p, g, t[m], c0, gamma_done);
+            g += rowb;
+        }
+        return;
+    }
     if (STEADY || (j0 >= p.out0 && j0 + M <= p.out1)) {
 #pragma unroll
         for (int m = 0; m < M; ++m) {

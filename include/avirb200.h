@@ -290,6 +290,13 @@ const char* avirb200_status_string(int status);
 const char* avirb200_last_error(void); /* thread-local detail of the last failure */
 int avirb200_device_count(void);
 
+/* Self-test on the current device: the batched, branch-free output gamma of the streaming column pass
+ * (pixel_ops.cuh, lin2srgb_batch: the library square root's fast path spelled out so that several
+ * samples' chains interleave) against the one-sample path (upstream avir.h:288-310 evaluated with
+ * sqrt.rn.f64) on EVERY float bit pattern the batched path accepts.  *checked = patterns compared,
+ * *mismatches = patterns whose results differ in any bit (must be 0). */
+int avirb200_selftest_lin2srgb(unsigned long long* checked, unsigned long long* mismatches);
+
 #ifdef __cplusplus
 }
 #endif

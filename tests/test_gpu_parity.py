@@ -403,6 +403,19 @@ def test_sharded_local_fused_exchange_matches_unsharded(case, nranks, overlap):
     assert cs.count_mismatch(whole, got) == 0
 
 
+def test_lin2srgb_batch_is_exhaustively_bit_identical():
+    """The streaming column pass applies the output gamma to a lane's whole batch with the library
+    square root's fast path written out (so that the samples' chains interleave).  The library's
+    self-test compares it with the one-sample path on every float bit pattern it accepts."""
+    lib = ab.lib()
+    lib.avirb200_selftest_lin2srgb.argtypes = [C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]
+    checked, bad = C.c_ulonglong(), C.c_ulonglong()
+    assert lib.avirb200_selftest_lin2srgb(C.byref(checked), C.byref(bad)) == 0, lib.avirb200_last_error()
+    # everything below 3.0e38 (positive patterns up to it, all negative non-NaN patterns incl. -inf)
+    assert checked.value > (1 << 32) - (1 << 25), checked.value
+    assert bad.value == 0, "%d of %d float patterns differ" % (bad.value, checked.value)
+
+
 # ---- LANCIR ---------------------------------------------------------------------------------
 
 LANCIR = [
