@@ -197,7 +197,41 @@ def run_reference(args):
                                    % (len(times), cores, os.cpu_count() or 1)},
         "e2e": {"value": val, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
+    fast = reference_fast_build(src, fp, cores, max(1, min(3, len(times))))
+    if fast is not None:
+        line["cpu_baseline_fast_build"] = fast
     print(json.dumps(line))
+
+
+def reference_fast_build(src, fp, cores, n):
+    """the same upstream headers built -O3 -mavx2 -mfma (oracle/_ref/libavir_ref_fast.so).
+    FMA contraction changes upstream's bits, so this build is never a parity oracle: a labelled
+    timing beside the pinned one, nothing else.  None when the build is not there or does not load."""
+    path = os.path.join(ROOT, "oracle", "_ref", "libavir_ref_fast.so")
+    try:
+        lib = C.CDLL(path)
+        lib.avir_ref_resize.restype = C.c_int
+        lib.avir_ref_resize.argtypes = [
+            C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
+            C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_double, C.c_double,
+            C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+        dst = np.zeros((DST_H, DST_W, CH), np.float32)
+
+        def call():
+            return lib.avir_ref_resize(fp, 2, 2, src.ctypes.data, SRC_W, SRC_H, 0, dst.ctypes.data, DST_W, DST_H, CH,
+                                       0.0, 16, 0, 0.0, 0.0, 0, -1, -1, cores, 0)
+        if call() != 0:
+            return None
+        ts = []
+        for _ in range(n):
+            t0 = time.perf_counter()
+            call()
+            ts.append(time.perf_counter() - t0)
+        return {"value": SRC_W * SRC_H * len(ts) / sum(ts) / 1e6, "unit": "Mpix/s", "cores": cores, "kind": "reference",
+                "flags": "-O3 -mavx2 -mfma (FMA contraction: bits may differ from the pinned oracle)",
+                "sample": "%d full frames" % len(ts)}
+    except Exception:
+        return None
 
 
 def workload_config(args, n):
